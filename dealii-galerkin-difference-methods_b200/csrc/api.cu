@@ -1,0 +1,1303 @@
+// extern "C" entry points of libgdm_b200 (see include/gdm/cuda/gdm_c_api.h for the reference
+// interfaces each one stands in for).  Host-side logic: layout/partition (system.h:703-761),
+// constraints folded into the per-direction band tables, operator set-up, vector transfers.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "gdm_internal.h"
+
+namespace gdm
+{
+  static thread_local std::string g_last_error;
+  void set_last_error(const std::string &msg)
+  {
+    g_last_error = msg;
+  }
+
+  // ----------------------------------------------------------------- context
+  void Context::ensure_scratch(size_t n)
+  {
+    if (n <= scratch_size)
+      return;
+    for (int i = 0; i < 4; ++i)
+      {
+        if (scratch[i])
+          cudaFree(scratch[i]);
+        scratch[i] = nullptr;
+      }
+    for (int i = 0; i < 4; ++i)
+      {
+        GDM_CUDA_CHECK(cudaMalloc(&scratch[i], n * sizeof(double)));
+        GDM_CUDA_CHECK(cudaMemsetAsync(scratch[i], 0, n * sizeof(double), stream));
+      }
+    scratch_size = n;
+  }
+
+  double *Context::acquire(size_t n)
+  {
+    double *p = nullptr;
+    for (size_t i = 0; i < pool_free.size(); ++i)
+      if (pool_free[i].first == n)
+        {
+          p = pool_free[i].second;
+          pool_free.erase(pool_free.begin() + i);
+          break;
+        }
+    if (!p)
+      GDM_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(double)));
+    GDM_CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(double), stream));
+    pool_used.emplace_back(n, p);
+    return p;
+  }
+
+  void Context::release(double *p)
+  {
+    if (!p)
+      return;
+    for (size_t i = 0; i < pool_used.size(); ++i)
+      if (pool_used[i].second == p)
+        {
+          pool_free.push_back(pool_used[i]);
+          pool_used.erase(pool_used.begin() + i);
+          return;
+        }
+  }
+
+  Context::~Context()
+  {
+    comm_destroy(*this);
+    for (auto &e : pool_free)
+      cudaFree(e.second);
+    for (auto &e : pool_used)
+      cudaFree(e.second);
+    for (int i = 0; i < 4; ++i)
+      if (scratch[i])
+        cudaFree(scratch[i]);
+    if (d_partials)
+      cudaFree(d_partials);
+    if (d_sums)
+      cudaFree(d_sums);
+    if (d_counters)
+      cudaFree(d_counters);
+    if (h_pinned)
+      cudaFreeHost(h_pinned);
+    if (comm_stream)
+      cudaStreamDestroy(comm_stream);
+    if (ev_a)
+      cudaEventDestroy(ev_a);
+    if (ev_b)
+      cudaEventDestroy(ev_b);
+  }
+
+  Vector::~Vector()
+  {
+    if (d && owns)
+      cudaFree(d);
+  }
+
+  CsrOverlay::~CsrOverlay()
+  {
+    cudaFree(d_row_off);
+    cudaFree(d_rowptr);
+    cudaFree(d_col_off);
+    cudaFree(d_val);
+  }
+
+  Operator::~Operator()
+  {
+    for (int d = 0; d < 3; ++d)
+      {
+        cudaFree(dA[d]);
+        cudaFree(dB[d]);
+        cudaFree(ddiagA[d]);
+        cudaFree(ddiagB[d]);
+      }
+    cudaFree(tmp);
+    cudaFree(host_src);
+    cudaFree(host_dst);
+    if (fused)
+      fused_plan_destroy(*this);
+  }
+
+  // ------------------------------------------------------------------ layout
+  static void make_layout(const gdm_system_desc &desc, Layout &L)
+  {
+    GDM_REQUIRE(desc.dim >= 1 && desc.dim <= 3, GDM_ERR_INVALID, "dim must be 1, 2 or 3");
+    GDM_REQUIRE(desc.fe_degree >= 1 && desc.fe_degree <= MAX_DEGREE && desc.fe_degree % 2 == 1,
+                GDM_ERR_NOT_IMPLEMENTED, "fe_degree must be odd and <= 9 (fe.h:322)");
+    GDM_REQUIRE(desc.n_components >= 1, GDM_ERR_INVALID, "n_components >= 1");
+    GDM_REQUIRE(desc.n_ranks >= 1 && desc.rank >= 0 && desc.rank < desc.n_ranks, GDM_ERR_INVALID, "bad rank");
+    L.dim = desc.dim;
+    L.p   = desc.fe_degree;
+    L.nc  = desc.n_components;
+    for (int d = 0; d < 3; ++d)
+      {
+        if (d < L.dim)
+          {
+            GDM_REQUIRE((int)desc.n_subdivisions[d] >= L.p, GDM_ERR_INVALID,
+                        "n_subdivisions must be >= fe_degree in every direction");
+            GDM_REQUIRE(desc.hi[d] > desc.lo[d], GDM_ERR_INVALID, "empty domain");
+            L.N[d]  = (int)desc.n_subdivisions[d];
+            L.nn[d] = L.N[d] + 1;
+            L.lo[d] = desc.lo[d];
+            L.hi[d] = desc.hi[d];
+            L.h[d]  = (desc.hi[d] - desc.lo[d]) / L.N[d];
+          }
+        else
+          {
+            L.N[d]  = 0;
+            L.nn[d] = 1;
+            L.lo[d] = 0;
+            L.hi[d] = 1;
+            L.h[d]  = 1;
+          }
+      }
+    L.rank    = desc.rank;
+    L.n_ranks = desc.n_ranks;
+    L.pdim    = L.dim - 1;
+    L.ghost   = L.p + (desc.add_ghost_layer ? 1 : 0);
+    // system.h:729-737
+    const int n_last = L.nn[L.pdim];
+    const int stride = (L.N[L.pdim] + L.n_ranks - 1) / L.n_ranks;
+    const int start  = (L.rank == 0) ? 0 : (stride * L.rank + 1);
+    const int end    = stride * (L.rank + 1) + 1;
+    L.own0           = std::min(start, n_last);
+    L.own1           = std::min(end, n_last);
+    L.loc0           = std::max(0, L.own0 - L.ghost);
+    L.loc1           = std::min(n_last, L.own1 + L.ghost);
+    if (L.own1 <= L.own0)
+      L.loc0 = L.loc1 = L.own0 = L.own1; // empty rank
+    for (int d = 0; d < 3; ++d)
+      L.ln[d] = L.nn[d];
+    L.ln[L.pdim] = L.loc1 - L.loc0;
+    // rows start on 32-byte sector boundaries (and satisfy TMA's 16-byte global stride rule)
+    const int64_t row = (int64_t)L.ln[0] * L.nc;
+    L.pitch           = (L.dim == 1) ? std::max<int64_t>(round_up(row, 4), 4) : round_up(row, 4);
+    L.plane           = L.pitch * L.ln[1];
+    L.size            = std::max<int64_t>(L.plane * L.ln[2], 4);
+    L.stride[0]       = L.nc;
+    L.stride[1]       = L.pitch;
+    L.stride[2]       = L.plane;
+    L.own_off         = (int64_t)(L.own0 - L.loc0) * L.stride[L.pdim];
+    L.own_len         = (int64_t)(L.own1 - L.own0) * L.stride[L.pdim];
+    int64_t face      = L.nc;
+    for (int d = 0; d < L.pdim; ++d)
+      face *= L.nn[d];
+    L.n_owned       = face * (L.own1 - L.own0);
+    L.n_dofs_global = face * L.nn[L.pdim];
+  }
+
+  // --------------------------------------------------------- operator tables
+  static void build_tables(Operator &op)
+  {
+    const Layout &L = op.sys->L;
+    const int     p = L.p, W = 2 * p + 1;
+    for (int d = 0; d < L.dim; ++d)
+      {
+        const int           N = L.N[d];
+        std::vector<double> M, B;
+        band_matrix_1d(p, N, 0, M);
+        for (auto &v : M)
+          v *= L.h[d];
+        switch (op.desc.kind)
+          {
+            case GDM_OP_MASS:
+              break;
+            case GDM_OP_STIFFNESS:
+              band_matrix_1d(p, N, 1, B);
+              for (auto &v : B)
+                v /= L.h[d];
+              break;
+            case GDM_OP_ADVECTION:
+              band_matrix_1d(p, N, 2, B);
+              for (auto &v : B)
+                v *= op.desc.b[d];
+              break;
+            case GDM_OP_ADVECTION_T:
+              {
+                std::vector<double> C;
+                band_matrix_1d(p, N, 2, C);
+                B.assign(C.size(), 0.0);
+                for (int i = 0; i <= N; ++i)
+                  for (int t = 0; t < W; ++t)
+                    {
+                      const int j = i + t - p;
+                      if (j < 0 || j > N)
+                        continue;
+                      B[(size_t)j * W + (i - j + p)] = op.desc.b[d] * C[(size_t)i * W + t];
+                    }
+                break;
+              }
+            default:
+              throw Error(GDM_ERR_INVALID, "unknown operator kind");
+          }
+        // unconstrained diagonals (value of constrained rows: sum_cells |cell_matrix(i,i)|)
+        std::vector<double> diagA(N + 1), diagB(N + 1, 0.0);
+        for (int i = 0; i <= N; ++i)
+          {
+            diagA[i] = M[(size_t)i * W + p];
+            if (!B.empty())
+              diagB[i] = B[(size_t)i * W + p];
+          }
+        auto constrain = [&](std::vector<double> &T) {
+          if (T.empty())
+            return;
+          if (op.periodic[d])
+            {
+              // fold row/column N into row/column 0 (C^T A C); reads wrap modulo N in the kernels
+              for (int t = 0; t < W; ++t)
+                {
+                  T[t] += T[(size_t)N * W + t];
+                  T[(size_t)N * W + t] = 0.0;
+                }
+            }
+          for (int s = 0; s < 2; ++s)
+            if (op.dirichlet[d][s])
+              {
+                const int r = (s == 0) ? 0 : N;
+                for (int t = 0; t < W; ++t)
+                  T[(size_t)r * W + t] = 0.0;
+                for (int i = 0; i <= N; ++i)
+                  for (int t = 0; t < W; ++t)
+                    {
+                      int c = i + t - p;
+                      if (op.periodic[d] && i < N)
+                        {
+                          if (c < 0)
+                            c += N;
+                          else if (c >= N)
+                            c -= N;
+                        }
+                      if (c == r)
+                        T[(size_t)i * W + t] = 0.0;
+                    }
+              }
+        };
+        GDM_REQUIRE(!(op.periodic[d] && N <= 2 * p), GDM_ERR_NOT_IMPLEMENTED,
+                    "periodic direction needs more than 2*fe_degree cells");
+        constrain(M);
+        constrain(B);
+        // slice the local rows of the partitioned direction
+        const int r0 = (d == L.pdim) ? L.loc0 : 0;
+        const int nr = L.ln[d];
+        op.hA[d].assign(M.begin() + (size_t)r0 * W, M.begin() + (size_t)(r0 + nr) * W);
+        op.hdiagA[d].assign(diagA.begin() + r0, diagA.begin() + r0 + nr);
+        if (!B.empty())
+          {
+            op.hB[d].assign(B.begin() + (size_t)r0 * W, B.begin() + (size_t)(r0 + nr) * W);
+            op.hdiagB[d].assign(diagB.begin() + r0, diagB.begin() + r0 + nr);
+          }
+        auto upload = [&](const std::vector<double> &h, double *&dptr) {
+          if (h.empty())
+            return;
+          GDM_CUDA_CHECK(cudaMalloc(&dptr, h.size() * sizeof(double)));
+          GDM_CUDA_CHECK(cudaMemcpy(dptr, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+        };
+        upload(op.hA[d], op.dA[d]);
+        upload(op.hB[d], op.dB[d]);
+        upload(op.hdiagA[d], op.ddiagA[d]);
+        upload(op.hdiagB[d], op.ddiagB[d]);
+      }
+  }
+
+  static void operator_apply(Operator &op, Vector &dst, Vector &src, bool accumulate)
+  {
+    GDM_REQUIRE(dst.sys == op.sys && src.sys == op.sys, GDM_ERR_INVALID, "vector/operator system mismatch");
+    GDM_REQUIRE(dst.d != src.d, GDM_ERR_INVALID, "vmult: dst and src must not alias");
+    Context &ctx = *op.sys->ctx;
+    vector_update_ghosts(src);
+    const bool via_tmp = accumulate && op.csr;
+    double    *out     = dst.d;
+    if (via_tmp)
+      {
+        if (!op.tmp)
+          {
+            GDM_CUDA_CHECK(cudaMalloc(&op.tmp, (size_t)op.sys->L.size * sizeof(double)));
+            GDM_CUDA_CHECK(cudaMemsetAsync(op.tmp, 0, (size_t)op.sys->L.size * sizeof(double), ctx.stream));
+          }
+        out = op.tmp;
+      }
+    const bool acc = accumulate && !via_tmp;
+    if (op.kernel_used == GDM_KERNEL_FUSED)
+      fused_apply(op, out, src.d, acc);
+    else
+      generic_apply(op, out, src.d, acc);
+    if (op.csr)
+      launch_csr_overlay(ctx, *op.csr, out, src.d, false);
+    if (via_tmp)
+      blas_sadd(ctx, dst.d + op.sys->L.own_off, 1.0, 1.0, out + op.sys->L.own_off, op.sys->L.own_len);
+  }
+
+  void vector_update_ghosts(Vector &v)
+  {
+    const Layout &L = v.sys->L;
+    if (L.n_ranks == 1)
+      return;
+    comm_halo_exchange(*v.sys->ctx, L, v.d);
+  }
+
+  // storage offset of a global DoF index (must be stored locally)
+  static int64_t storage_offset(const Layout &L, uint64_t dof)
+  {
+    const uint64_t node = dof / L.nc;
+    const int      c    = (int)(dof % L.nc);
+    int            idx[3];
+    idx[0] = (int)(node % L.nn[0]);
+    idx[1] = (int)((node / L.nn[0]) % L.nn[1]);
+    idx[2] = (int)(node / ((uint64_t)L.nn[0] * L.nn[1]));
+    idx[L.pdim] -= L.loc0;
+    GDM_REQUIRE(idx[L.pdim] >= 0 && idx[L.pdim] < L.ln[L.pdim], GDM_ERR_INVALID,
+                "DoF outside the locally stored range");
+    return (int64_t)idx[2] * L.plane + (int64_t)idx[1] * L.pitch + (int64_t)idx[0] * L.nc + c;
+  }
+} // namespace gdm
+
+using namespace gdm;
+
+#define GDM_TRY try {
+#define GDM_CATCH                                 \
+  }                                               \
+  catch (const gdm::Error &e)                     \
+  {                                               \
+    gdm::set_last_error(e.what());                \
+    return e.code;                                \
+  }                                               \
+  catch (const std::exception &e)                 \
+  {                                               \
+    gdm::set_last_error(e.what());                \
+    return GDM_ERR_INTERNAL;                      \
+  }                                               \
+  return GDM_OK;
+
+#define GDM_ARG(x) GDM_REQUIRE((x) != nullptr, GDM_ERR_INVALID, "null argument " #x)
+
+extern "C" {
+
+const char *gdm_last_error(void)
+{
+  return gdm::g_last_error.c_str();
+}
+
+int gdm_api_version(void)
+{
+  return GDM_API_VERSION;
+}
+
+// ------------------------------------------------------------------ context
+int gdm_context_create(int device, void *stream, gdm_context_t *out)
+{
+  GDM_TRY
+  GDM_ARG(out);
+  if (device < 0)
+    {
+      // description-only context: grid / DoF / partition queries work, every compute entry point
+      // fails with GDM_ERR_CUDA (used by the CPU-side tests of the host logic)
+      std::unique_ptr<gdm_context_s> c(new gdm_context_s);
+      c->impl.device = -1;
+      *out           = c.release();
+      return GDM_OK;
+    }
+  int n_dev = 0;
+  GDM_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
+  GDM_REQUIRE(n_dev > 0 && device >= 0 && device < n_dev, GDM_ERR_CUDA,
+              "no usable CUDA device (this library has no CPU fallback)");
+  GDM_CUDA_CHECK(cudaSetDevice(device));
+  std::unique_ptr<gdm_context_s> c(new gdm_context_s);
+  Context                       &ctx = c->impl;
+  ctx.device                         = device;
+  ctx.stream                         = (cudaStream_t)stream;
+  cudaDeviceProp prop;
+  GDM_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  ctx.sm_count         = prop.multiProcessorCount;
+  ctx.partial_capacity = (size_t)ctx.sm_count * 8 * 4;
+  GDM_CUDA_CHECK(cudaMalloc(&ctx.d_partials, ctx.partial_capacity * sizeof(double)));
+  GDM_CUDA_CHECK(cudaMalloc(&ctx.d_sums, N_SUM_SLOTS * sizeof(double)));
+  GDM_CUDA_CHECK(cudaMalloc(&ctx.d_counters, 16 * sizeof(unsigned)));
+  GDM_CUDA_CHECK(cudaMemset(ctx.d_sums, 0, N_SUM_SLOTS * sizeof(double)));
+  GDM_CUDA_CHECK(cudaMemset(ctx.d_counters, 0, 16 * sizeof(unsigned)));
+  GDM_CUDA_CHECK(cudaMallocHost(&ctx.h_pinned, 64 * sizeof(double)));
+  GDM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.comm_stream, cudaStreamNonBlocking));
+  GDM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx.ev_a, cudaEventDisableTiming));
+  GDM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx.ev_b, cudaEventDisableTiming));
+  *out = c.release();
+  GDM_CATCH
+}
+
+int gdm_context_destroy(gdm_context_t ctx)
+{
+  GDM_TRY
+  if (ctx)
+    {
+      if (ctx->impl.device >= 0)
+        {
+          cudaSetDevice(ctx->impl.device);
+          cudaStreamSynchronize(ctx->impl.stream);
+        }
+      delete ctx;
+    }
+  GDM_CATCH
+}
+
+int gdm_context_set_stream(gdm_context_t ctx, void *stream)
+{
+  GDM_TRY
+  GDM_ARG(ctx);
+  ctx->impl.stream = (cudaStream_t)stream;
+  GDM_CATCH
+}
+
+int gdm_context_synchronize(gdm_context_t ctx)
+{
+  GDM_TRY
+  GDM_ARG(ctx);
+  if (ctx->impl.device >= 0)
+    GDM_CUDA_CHECK(cudaStreamSynchronize(ctx->impl.stream));
+  GDM_CATCH
+}
+
+int gdm_context_launch_count(gdm_context_t ctx, uint64_t *count)
+{
+  GDM_TRY
+  GDM_ARG(ctx);
+  GDM_ARG(count);
+  *count = ctx->impl.launches;
+  GDM_CATCH
+}
+
+int gdm_comm_unique_id(void *id128)
+{
+  GDM_TRY
+  GDM_ARG(id128);
+  comm_unique_id(id128);
+  GDM_CATCH
+}
+
+int gdm_context_comm_init(gdm_context_t ctx, const void *id128, int rank, int n_ranks)
+{
+  GDM_TRY
+  GDM_ARG(ctx);
+  GDM_ARG(id128);
+  comm_init(ctx->impl, id128, rank, n_ranks);
+  GDM_CATCH
+}
+
+// -------------------------------------------------------------------- basis
+int gdm_polynomials_1d(int p, double *coeffs)
+{
+  GDM_TRY
+  GDM_ARG(coeffs);
+  GDM_REQUIRE(p >= 1 && p <= MAX_DEGREE && p % 2 == 1, GDM_ERR_NOT_IMPLEMENTED, "fe_degree must be odd and <= 9");
+  for (int v = 0; v < p; ++v)
+    lagrange_monomials(p, v, coeffs + (size_t)v * (p + 1) * (p + 1));
+  GDM_CATCH
+}
+
+// ------------------------------------------------------------------- system
+int gdm_system_create(gdm_context_t ctx, const gdm_system_desc *desc, gdm_system_t *out)
+{
+  GDM_TRY
+  GDM_ARG(ctx);
+  GDM_ARG(desc);
+  GDM_ARG(out);
+  std::unique_ptr<gdm_system_s> s(new gdm_system_s);
+  s->impl.ctx  = &ctx->impl;
+  s->impl.desc = *desc;
+  make_layout(*desc, s->impl.L);
+  GDM_REQUIRE(desc->n_ranks == 1 || ctx->impl.device < 0 || ctx->impl.n_ranks == desc->n_ranks, GDM_ERR_INVALID,
+              "system n_ranks does not match the context communicator (call gdm_context_comm_init first)");
+  *out = s.release();
+  GDM_CATCH
+}
+
+int gdm_system_destroy(gdm_system_t sys)
+{
+  delete sys;
+  return GDM_OK;
+}
+
+uint64_t gdm_system_n_dofs(gdm_system_t sys)
+{
+  return sys ? (uint64_t)sys->impl.L.n_dofs_global : 0;
+}
+
+uint64_t gdm_system_n_cells(gdm_system_t sys)
+{
+  if (!sys)
+    return 0;
+  uint64_t n = 1;
+  for (int d = 0; d < sys->impl.L.dim; ++d)
+    n *= sys->impl.L.N[d];
+  return n;
+}
+
+int gdm_system_locally_owned_range(gdm_system_t sys, uint64_t *begin, uint64_t *end)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  const Layout &L    = sys->impl.L;
+  uint64_t      face = L.nc;
+  for (int d = 0; d < L.pdim; ++d)
+    face *= L.nn[d];
+  if (begin)
+    *begin = face * L.own0;
+  if (end)
+    *end = face * L.own1;
+  GDM_CATCH
+}
+
+int gdm_system_dofs_per_cell(gdm_system_t sys)
+{
+  if (!sys)
+    return 0;
+  int n = sys->impl.L.nc;
+  for (int d = 0; d < sys->impl.L.dim; ++d)
+    n *= sys->impl.L.p + 1;
+  return n;
+}
+
+int gdm_system_get_dof_indices(gdm_system_t sys, uint64_t cell, uint64_t *out)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(out);
+  const Layout &L = sys->impl.L;
+  GDM_REQUIRE(cell < gdm_system_n_cells(sys), GDM_ERR_INVALID, "cell index out of range");
+  int      ci[3] = {0, 0, 0}, off[3] = {0, 0, 0};
+  uint64_t c = cell;
+  for (int d = 0; d < L.dim; ++d)
+    {
+      ci[d] = (int)(c % L.N[d]);
+      c /= L.N[d];
+      off[d] = window_offset(L.p, L.N[d], ci[d]);
+    }
+  const int n1  = L.p + 1;
+  const int npc = gdm_system_dofs_per_cell(sys) / L.nc;
+  int       cc  = 0;
+  for (int k = 0; k < (L.dim >= 3 ? n1 : 1); ++k)
+    for (int j = 0; j < (L.dim >= 2 ? n1 : 1); ++j)
+      for (int i = 0; i < n1; ++i, ++cc)
+        {
+          const uint64_t node = (uint64_t)(off[0] + i) + (uint64_t)L.nn[0] * ((off[1] + j) + (uint64_t)L.nn[1] * (off[2] + k));
+          for (int comp = 0; comp < L.nc; ++comp)
+            out[comp * npc + cc] = node * L.nc + comp;
+        }
+  GDM_CATCH
+}
+
+int gdm_system_active_fe_index(gdm_system_t sys, uint64_t cell, uint32_t *fe_index)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(fe_index);
+  const Layout &L = sys->impl.L;
+  GDM_REQUIRE(cell < gdm_system_n_cells(sys), GDM_ERR_INVALID, "cell index out of range");
+  uint64_t c = cell;
+  uint32_t idx = 0, mult = 1;
+  for (int d = 0; d < L.dim; ++d)
+    {
+      const int ci = (int)(c % L.N[d]);
+      c /= L.N[d];
+      idx += mult * (uint32_t)cell_variant(L.p, L.N[d], ci);
+      mult *= (uint32_t)L.p;
+    }
+  *fe_index = idx;
+  GDM_CATCH
+}
+
+int gdm_system_matrix_1d(gdm_system_t sys, int d, int kind, double *band)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(band);
+  const Layout &L = sys->impl.L;
+  GDM_REQUIRE(d >= 0 && d < L.dim && kind >= 0 && kind <= 2, GDM_ERR_INVALID, "bad direction or kind");
+  std::vector<double> t;
+  band_matrix_1d(L.p, L.N[d], kind, t);
+  const double s = (kind == 0) ? L.h[d] : (kind == 1 ? 1.0 / L.h[d] : 1.0);
+  for (size_t i = 0; i < t.size(); ++i)
+    band[i] = t[i] * s;
+  GDM_CATCH
+}
+
+int gdm_system_layout(gdm_system_t sys, gdm_layout_info *info)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(info);
+  const Layout &L    = sys->impl.L;
+  info->pitch        = L.pitch;
+  info->plane        = L.plane;
+  info->size         = L.size;
+  info->owned_offset = L.own_off;
+  info->owned_size   = L.own_len;
+  for (int d = 0; d < 3; ++d)
+    info->local_nodes[d] = L.ln[d];
+  info->owned_begin  = L.own0;
+  info->owned_end    = L.own1;
+  info->stored_begin = L.loc0;
+  info->stored_end   = L.loc1;
+  GDM_CATCH
+}
+
+// -------------------------------------------------------------- constraints
+int gdm_constraints_create(gdm_system_t sys, gdm_constraints_t *out)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(out);
+  *out            = new gdm_constraints_s;
+  (*out)->impl.sys = &sys->impl;
+  GDM_CATCH
+}
+
+int gdm_constraints_destroy(gdm_constraints_t c)
+{
+  delete c;
+  return GDM_OK;
+}
+
+int gdm_constraints_make_zero_boundary(gdm_constraints_t c, int surface)
+{
+  GDM_TRY
+  GDM_ARG(c);
+  const int dim = c->impl.sys->L.dim;
+  GDM_REQUIRE(surface >= -1 && surface < 2 * dim, GDM_ERR_INVALID, "surface out of range");
+  GDM_REQUIRE(!c->impl.closed, GDM_ERR_INVALID, "constraints already closed");
+  for (int s = 0; s < 2 * dim; ++s)
+    if (surface < 0 || surface == s)
+      c->impl.dirichlet[s / 2][s % 2] = true;
+  GDM_CATCH
+}
+
+int gdm_constraints_make_periodicity(gdm_constraints_t c, int d)
+{
+  GDM_TRY
+  GDM_ARG(c);
+  GDM_REQUIRE(d >= 0 && d < c->impl.sys->L.dim, GDM_ERR_INVALID, "direction out of range");
+  GDM_REQUIRE(!c->impl.closed, GDM_ERR_INVALID, "constraints already closed");
+  // system.h:454: DoFs that are already constrained keep their constraint
+  if (!c->impl.dirichlet[d][1])
+    c->impl.periodic[d] = true;
+  GDM_CATCH
+}
+
+int gdm_constraints_close(gdm_constraints_t c)
+{
+  GDM_TRY
+  GDM_ARG(c);
+  // a periodic slave whose master is zero-constrained resolves to zero as well
+  for (int d = 0; d < 3; ++d)
+    if (c->impl.periodic[d] && c->impl.dirichlet[d][0])
+      {
+        c->impl.periodic[d]     = false;
+        c->impl.dirichlet[d][1] = true;
+      }
+  c->impl.closed = true;
+  GDM_CATCH
+}
+
+static bool node_constrained(const Constraints &c, const int idx[3])
+{
+  const Layout &L = c.sys->L;
+  for (int d = 0; d < L.dim; ++d)
+    {
+      if (idx[d] == 0 && c.dirichlet[d][0])
+        return true;
+      if (idx[d] == L.N[d] && (c.dirichlet[d][1] || c.periodic[d]))
+        return true;
+    }
+  return false;
+}
+
+uint64_t gdm_constraints_n_constraints(gdm_constraints_t c)
+{
+  if (!c)
+    return 0;
+  const Layout &L = c->impl.sys->L;
+  // inclusion-exclusion over directions: count unconstrained nodes
+  uint64_t free_nodes = 1, all = 1;
+  for (int d = 0; d < L.dim; ++d)
+    {
+      int f = L.nn[d];
+      if (c->impl.dirichlet[d][0])
+        --f;
+      if (c->impl.dirichlet[d][1] || c->impl.periodic[d])
+        --f;
+      free_nodes *= (uint64_t)std::max(f, 0);
+      all *= (uint64_t)L.nn[d];
+    }
+  return (all - free_nodes) * L.nc;
+}
+
+int gdm_constraints_is_constrained(gdm_constraints_t c, uint64_t dof)
+{
+  if (!c)
+    return 0;
+  const Layout &L    = c->impl.sys->L;
+  const uint64_t node = dof / L.nc;
+  int            idx[3];
+  idx[0] = (int)(node % L.nn[0]);
+  idx[1] = (int)((node / L.nn[0]) % L.nn[1]);
+  idx[2] = (int)(node / ((uint64_t)L.nn[0] * L.nn[1]));
+  return node_constrained(c->impl, idx) ? 1 : 0;
+}
+
+int gdm_constraints_distribute(gdm_constraints_t c, gdm_vector_t v)
+{
+  GDM_TRY
+  GDM_ARG(c);
+  GDM_ARG(v);
+  GDM_REQUIRE(v->impl.sys == c->impl.sys, GDM_ERR_INVALID, "vector/constraints system mismatch");
+  Context   &ctx = *c->impl.sys->ctx;
+  const bool no_periodic[3] = {false, false, false};
+  launch_set_constrained(ctx, c->impl.sys->L, c->impl.dirichlet, no_periodic, v->impl.d, 0.0);
+  launch_periodic_copy(ctx, c->impl.sys->L, c->impl.periodic, v->impl.d);
+  GDM_CATCH
+}
+
+int gdm_constraints_set_zero(gdm_constraints_t c, gdm_vector_t v)
+{
+  GDM_TRY
+  GDM_ARG(c);
+  GDM_ARG(v);
+  GDM_REQUIRE(v->impl.sys == c->impl.sys, GDM_ERR_INVALID, "vector/constraints system mismatch");
+  launch_set_constrained(*c->impl.sys->ctx, c->impl.sys->L, c->impl.dirichlet, c->impl.periodic, v->impl.d, 0.0);
+  GDM_CATCH
+}
+
+// ------------------------------------------------------------------ vectors
+int gdm_vector_create(gdm_system_t sys, gdm_vector_t *out)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(out);
+  GDM_REQUIRE(sys->impl.ctx->device >= 0, GDM_ERR_CUDA, "description-only context: no CUDA device (no CPU fallback)");
+  std::unique_ptr<gdm_vector_s> v(new gdm_vector_s);
+  v->impl.sys = &sys->impl;
+  GDM_CUDA_CHECK(cudaSetDevice(sys->impl.ctx->device));
+  GDM_CUDA_CHECK(cudaMalloc(&v->impl.d, (size_t)sys->impl.L.size * sizeof(double)));
+  GDM_CUDA_CHECK(cudaMemsetAsync(v->impl.d, 0, (size_t)sys->impl.L.size * sizeof(double), sys->impl.ctx->stream));
+  *out = v.release();
+  GDM_CATCH
+}
+
+int gdm_vector_destroy(gdm_vector_t v)
+{
+  delete v;
+  return GDM_OK;
+}
+
+void *gdm_vector_device_ptr(gdm_vector_t v)
+{
+  return v ? v->impl.d : nullptr;
+}
+
+static void vector_transfer(Vector &v, double *host, bool upload)
+{
+  const Layout &L   = v.sys->L;
+  Context      &ctx = *v.sys->ctx;
+  double       *dev = v.d + L.own_off;
+  if (L.own1 <= L.own0)
+    return;
+  if (L.dim == 1)
+    {
+      const size_t bytes = (size_t)(L.own1 - L.own0) * L.nc * sizeof(double);
+      GDM_CUDA_CHECK(upload ? cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx.stream) :
+                              cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx.stream));
+    }
+  else
+    {
+      const size_t width = (size_t)L.ln[0] * L.nc * sizeof(double);
+      const size_t rows  = (L.dim == 2) ? (size_t)(L.own1 - L.own0) : (size_t)(L.own1 - L.own0) * L.ln[1];
+      const size_t dpitch = (size_t)L.pitch * sizeof(double);
+      GDM_CUDA_CHECK(upload ? cudaMemcpy2DAsync(dev, dpitch, host, width, width, rows, cudaMemcpyHostToDevice, ctx.stream) :
+                              cudaMemcpy2DAsync(host, width, dev, dpitch, width, rows, cudaMemcpyDeviceToHost, ctx.stream));
+    }
+}
+
+int gdm_vector_upload(gdm_vector_t v, const double *host)
+{
+  GDM_TRY
+  GDM_ARG(v);
+  GDM_ARG(host);
+  vector_transfer(v->impl, const_cast<double *>(host), true);
+  GDM_CUDA_CHECK(cudaStreamSynchronize(v->impl.sys->ctx->stream));
+  GDM_CATCH
+}
+
+int gdm_vector_download(gdm_vector_t v, double *host)
+{
+  GDM_TRY
+  GDM_ARG(v);
+  GDM_ARG(host);
+  vector_transfer(v->impl, host, false);
+  GDM_CUDA_CHECK(cudaStreamSynchronize(v->impl.sys->ctx->stream));
+  GDM_CATCH
+}
+
+int gdm_vector_set(gdm_vector_t v, double value)
+{
+  GDM_TRY
+  GDM_ARG(v);
+  const Layout &L = v->impl.sys->L;
+  if (value == 0.0)
+    GDM_CUDA_CHECK(cudaMemsetAsync(v->impl.d, 0, (size_t)L.size * sizeof(double), v->impl.sys->ctx->stream));
+  else
+    blas_set_strided(*v->impl.sys->ctx, L, v->impl.d, value);
+  GDM_CATCH
+}
+
+#define GDM_SAME_SYS(a, b) GDM_REQUIRE((a)->impl.sys == (b)->impl.sys, GDM_ERR_INVALID, "vectors belong to different systems")
+
+int gdm_vector_copy(gdm_vector_t dst, gdm_vector_t src)
+{
+  GDM_TRY
+  GDM_ARG(dst);
+  GDM_ARG(src);
+  GDM_SAME_SYS(dst, src);
+  const Layout &L = dst->impl.sys->L;
+  blas_copy(*dst->impl.sys->ctx, dst->impl.d + L.own_off, src->impl.d + L.own_off, L.own_len);
+  GDM_CATCH
+}
+
+int gdm_vector_scale(gdm_vector_t v, double a)
+{
+  GDM_TRY
+  GDM_ARG(v);
+  const Layout &L = v->impl.sys->L;
+  blas_scale(*v->impl.sys->ctx, v->impl.d + L.own_off, L.own_len, a);
+  GDM_CATCH
+}
+
+int gdm_vector_add(gdm_vector_t v, double a, gdm_vector_t x)
+{
+  GDM_TRY
+  GDM_ARG(v);
+  GDM_ARG(x);
+  GDM_SAME_SYS(v, x);
+  const Layout &L = v->impl.sys->L;
+  blas_sadd(*v->impl.sys->ctx, v->impl.d + L.own_off, 1.0, a, x->impl.d + L.own_off, L.own_len);
+  GDM_CATCH
+}
+
+int gdm_vector_sadd(gdm_vector_t v, double s, double a, gdm_vector_t x)
+{
+  GDM_TRY
+  GDM_ARG(v);
+  GDM_ARG(x);
+  GDM_SAME_SYS(v, x);
+  const Layout &L = v->impl.sys->L;
+  blas_sadd(*v->impl.sys->ctx, v->impl.d + L.own_off, s, a, x->impl.d + L.own_off, L.own_len);
+  GDM_CATCH
+}
+
+int gdm_vector_scale_by(gdm_vector_t v, gdm_vector_t d)
+{
+  GDM_TRY
+  GDM_ARG(v);
+  GDM_ARG(d);
+  GDM_SAME_SYS(v, d);
+  const Layout &L = v->impl.sys->L;
+  blas_mul(*v->impl.sys->ctx, v->impl.d + L.own_off, d->impl.d + L.own_off, L.own_len);
+  GDM_CATCH
+}
+
+int gdm_vector_dot(gdm_vector_t a, gdm_vector_t b, double *result)
+{
+  GDM_TRY
+  GDM_ARG(a);
+  GDM_ARG(b);
+  GDM_ARG(result);
+  GDM_SAME_SYS(a, b);
+  const Layout &L   = a->impl.sys->L;
+  Context      &ctx = *a->impl.sys->ctx;
+  blas_dot(ctx, a->impl.d + L.own_off, b->impl.d + L.own_off, L.own_len, SUM_DOT);
+  *result = read_sum(ctx, SUM_DOT, true);
+  GDM_CATCH
+}
+
+int gdm_vector_l2_norm(gdm_vector_t a, double *result)
+{
+  double    d  = 0;
+  const int rc = gdm_vector_dot(a, a, &d);
+  if (rc == GDM_OK && result)
+    *result = std::sqrt(d);
+  return rc;
+}
+
+int gdm_vector_linfty_norm(gdm_vector_t a, double *result)
+{
+  GDM_TRY
+  GDM_ARG(a);
+  GDM_ARG(result);
+  const Layout &L   = a->impl.sys->L;
+  Context      &ctx = *a->impl.sys->ctx;
+  blas_absmax(ctx, a->impl.d + L.own_off, L.own_len, SUM_DOT);
+  *result = read_sum(ctx, SUM_DOT, true, true);
+  GDM_CATCH
+}
+
+int gdm_vector_update_ghost_values(gdm_vector_t v)
+{
+  GDM_TRY
+  GDM_ARG(v);
+  vector_update_ghosts(v->impl);
+  GDM_CATCH
+}
+
+// ---------------------------------------------------------------- operators
+int gdm_operator_create(gdm_system_t sys, gdm_constraints_t c, const gdm_operator_desc *desc, gdm_operator_t *out)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(desc);
+  GDM_ARG(out);
+  GDM_REQUIRE(c == nullptr || c->impl.sys == &sys->impl, GDM_ERR_INVALID, "constraints belong to another system");
+  GDM_REQUIRE(c == nullptr || c->impl.closed, GDM_ERR_INVALID, "constraints must be closed (AffineConstraints::close)");
+  GDM_REQUIRE(sys->impl.ctx->device >= 0, GDM_ERR_CUDA, "description-only context: no CUDA device (no CPU fallback)");
+  std::unique_ptr<gdm_operator_s> o(new gdm_operator_s);
+  Operator                       &op = o->impl;
+  op.sys                             = &sys->impl;
+  op.desc                            = *desc;
+  for (int d = 0; d < 3; ++d)
+    {
+      op.periodic[d]     = c ? c->impl.periodic[d] : false;
+      op.dirichlet[d][0] = c ? c->impl.dirichlet[d][0] : false;
+      op.dirichlet[d][1] = c ? c->impl.dirichlet[d][1] : false;
+      GDM_REQUIRE(!(op.periodic[d] && d == sys->impl.L.pdim && sys->impl.L.n_ranks > 1), GDM_ERR_NOT_IMPLEMENTED,
+                  "periodicity along the partitioned direction with more than one rank");
+    }
+  op.has_B      = desc->kind != GDM_OP_MASS;
+  op.b_symmetry = (desc->kind == GDM_OP_STIFFNESS) ? +1 : -1;
+  GDM_REQUIRE(!(desc->constrained_diagonal == GDM_DIAG_ASSEMBLED &&
+                (desc->kind == GDM_OP_ADVECTION || desc->kind == GDM_OP_ADVECTION_T)),
+              GDM_ERR_NOT_IMPLEMENTED, "advection operators use residual (vector assembly) semantics: GDM_DIAG_ZERO");
+  GDM_CUDA_CHECK(cudaSetDevice(sys->impl.ctx->device));
+  build_tables(op);
+  op.kernel_used = GDM_KERNEL_GENERIC;
+  if (desc->kernel != GDM_KERNEL_GENERIC && fused_supported(op))
+    {
+      fused_plan_create(op);
+      op.kernel_used = GDM_KERNEL_FUSED;
+    }
+  GDM_REQUIRE(!(desc->kernel == GDM_KERNEL_FUSED && op.kernel_used != GDM_KERNEL_FUSED), GDM_ERR_NOT_IMPLEMENTED,
+              "the fused kernel does not cover this configuration");
+  *out = o.release();
+  GDM_CATCH
+}
+
+int gdm_operator_destroy(gdm_operator_t op)
+{
+  delete op;
+  return GDM_OK;
+}
+
+int gdm_operator_attach_csr(gdm_operator_t op, uint64_t n_rows, const uint64_t *row_ids, const uint64_t *rowptr,
+                            const uint64_t *col, const double *val)
+{
+  GDM_TRY
+  GDM_ARG(op);
+  const Layout &L = op->impl.sys->L;
+  std::unique_ptr<CsrOverlay> csr(new CsrOverlay);
+  csr->n_rows = (int64_t)n_rows;
+  if (n_rows > 0)
+    {
+      GDM_ARG(row_ids);
+      GDM_ARG(rowptr);
+      csr->nnz = (int64_t)rowptr[n_rows];
+      std::vector<int64_t> row_off(n_rows), rp(n_rows + 1), col_off(csr->nnz);
+      uint64_t own_b, own_e;
+      gdm_system_locally_owned_range(reinterpret_cast<gdm_system_t>(op->impl.sys), &own_b, &own_e);
+      for (uint64_t i = 0; i < n_rows; ++i)
+        {
+          GDM_REQUIRE(row_ids[i] >= own_b && row_ids[i] < own_e, GDM_ERR_INVALID, "CSR row is not locally owned");
+          row_off[i] = storage_offset(L, row_ids[i]);
+          rp[i]      = (int64_t)rowptr[i];
+        }
+      rp[n_rows] = csr->nnz;
+      for (int64_t i = 0; i < csr->nnz; ++i)
+        col_off[i] = storage_offset(L, col[i]);
+      auto up = [&](auto *&dptr, const void *h, size_t bytes) {
+        GDM_CUDA_CHECK(cudaMalloc(&dptr, std::max<size_t>(bytes, 8)));
+        GDM_CUDA_CHECK(cudaMemcpy(dptr, h, bytes, cudaMemcpyHostToDevice));
+      };
+      up(csr->d_row_off, row_off.data(), row_off.size() * 8);
+      up(csr->d_rowptr, rp.data(), rp.size() * 8);
+      up(csr->d_col_off, col_off.data(), col_off.size() * 8);
+      up(csr->d_val, val, (size_t)csr->nnz * 8);
+    }
+  op->impl.csr = std::move(csr);
+  GDM_CATCH
+}
+
+int gdm_operator_vmult(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src)
+{
+  GDM_TRY
+  GDM_ARG(op);
+  GDM_ARG(dst);
+  GDM_ARG(src);
+  operator_apply(op->impl, dst->impl, src->impl, false);
+  GDM_CATCH
+}
+
+int gdm_operator_vmult_add(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src)
+{
+  GDM_TRY
+  GDM_ARG(op);
+  GDM_ARG(dst);
+  GDM_ARG(src);
+  operator_apply(op->impl, dst->impl, src->impl, true);
+  GDM_CATCH
+}
+
+int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *src_host)
+{
+  GDM_TRY
+  GDM_ARG(op);
+  GDM_ARG(dst_host);
+  GDM_ARG(src_host);
+  System  &sys = *op->impl.sys;
+  Context &ctx = *sys.ctx;
+  Operator &o = op->impl;
+  if (!o.host_src)
+    {
+      GDM_CUDA_CHECK(cudaMalloc(&o.host_src, (size_t)sys.L.size * sizeof(double)));
+      GDM_CUDA_CHECK(cudaMalloc(&o.host_dst, (size_t)sys.L.size * sizeof(double)));
+      GDM_CUDA_CHECK(cudaMemsetAsync(o.host_src, 0, (size_t)sys.L.size * sizeof(double), ctx.stream));
+      GDM_CUDA_CHECK(cudaMemsetAsync(o.host_dst, 0, (size_t)sys.L.size * sizeof(double), ctx.stream));
+    }
+  Vector vs, vd;
+  vs.sys = vd.sys = &sys;
+  vs.d    = o.host_src;
+  vd.d    = o.host_dst;
+  vs.owns = vd.owns = false;
+  vector_transfer(vs, const_cast<double *>(src_host), true);
+  operator_apply(o, vd, vs, false);
+  vector_transfer(vd, dst_host, false);
+  GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+  GDM_CATCH
+}
+
+int gdm_operator_diagonal(gdm_operator_t op, gdm_vector_t diag)
+{
+  GDM_TRY
+  GDM_ARG(op);
+  GDM_ARG(diag);
+  GDM_REQUIRE(diag->impl.sys == op->impl.sys, GDM_ERR_INVALID, "vector/operator system mismatch");
+  GDM_REQUIRE(!op->impl.csr, GDM_ERR_NOT_IMPLEMENTED, "diagonal of an operator with CSR overlay rows");
+  System  &sys = *op->impl.sys;
+  Context &ctx = *sys.ctx;
+  launch_diagonal(ctx, sys.L, op->impl, diag->impl.d);
+  if (op->impl.desc.constrained_diagonal == GDM_DIAG_ASSEMBLED)
+    {
+      ctx.ensure_scratch((size_t)sys.L.size);
+      blas_set(ctx, ctx.scratch[0], sys.L.size, 1.0);
+      launch_constrained_rows(ctx, sys.L, op->impl, diag->impl.d, ctx.scratch[0], true);
+    }
+  GDM_CATCH
+}
+
+int gdm_operator_lumped_mass_inverse(gdm_operator_t op, gdm_vector_t inv)
+{
+  GDM_TRY
+  GDM_ARG(op);
+  GDM_ARG(inv);
+  GDM_REQUIRE(op->impl.desc.kind == GDM_OP_MASS, GDM_ERR_INVALID, "lumped mass needs a MASS operator");
+  GDM_REQUIRE(inv->impl.sys == op->impl.sys, GDM_ERR_INVALID, "vector/operator system mismatch");
+  // cell_vector(i) = sum_j (phi_i, phi_j) over ALL local j, then distribute_local_to_global on a
+  // vector (matrix_creator.h:99-112): periodic slave rows fold into their masters, Dirichlet rows are
+  // dropped, but the COLUMNS of constrained DoFs still count.  => apply a mass operator that keeps the
+  // periodic folding and has no Dirichlet masking to the ones vector, then clear the constrained rows.
+  // Constrained entries return 0 here where the reference produces 1/0 = inf (never used downstream).
+  System  &sys = *op->impl.sys;
+  Context &ctx = *sys.ctx;
+  Operator tmp;
+  tmp.sys                       = &sys;
+  tmp.desc                      = op->impl.desc;
+  tmp.desc.constrained_diagonal = GDM_DIAG_ZERO;
+  tmp.desc.scale                = 1.0;
+  for (int d = 0; d < 3; ++d)
+    {
+      tmp.periodic[d]     = op->impl.periodic[d];
+      tmp.dirichlet[d][0] = tmp.dirichlet[d][1] = false;
+    }
+  build_tables(tmp);
+  ctx.ensure_scratch((size_t)sys.L.size);
+  std::unique_ptr<gdm_vector_s> ones(new gdm_vector_s);
+  ones->impl.sys = &sys;
+  GDM_CUDA_CHECK(cudaMalloc(&ones->impl.d, (size_t)sys.L.size * sizeof(double)));
+  GDM_CUDA_CHECK(cudaMemsetAsync(ones->impl.d, 0, (size_t)sys.L.size * sizeof(double), ctx.stream));
+  // all stored planes (ghosts included) hold ones
+  {
+    Layout all = sys.L;
+    all.own0   = all.loc0;
+    all.own1   = all.loc1;
+    all.own_off = 0;
+    blas_set_strided(ctx, all, ones->impl.d, 1.0);
+  }
+  generic_apply(tmp, inv->impl.d, ones->impl.d, false);
+  launch_set_constrained(ctx, sys.L, op->impl.dirichlet, op->impl.periodic, inv->impl.d, 0.0);
+  blas_invert(ctx, inv->impl.d + sys.L.own_off, sys.L.own_len);
+  GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+  GDM_CATCH
+}
+
+int gdm_operator_kernel_used(gdm_operator_t op)
+{
+  return op ? op->impl.kernel_used : 0;
+}
+
+uint64_t gdm_operator_m(gdm_operator_t op)
+{
+  return op ? (uint64_t)op->impl.sys->L.n_dofs_global : 0;
+}
+
+// ------------------------------------------------------------------- solver
+int gdm_solver_cg(gdm_operator_t A, gdm_vector_t x, gdm_vector_t b, int precondition, gdm_vector_t pvec,
+                  gdm_reduction_control *control)
+{
+  int status = GDM_OK;
+  GDM_TRY
+  GDM_ARG(A);
+  GDM_ARG(x);
+  GDM_ARG(b);
+  GDM_ARG(control);
+  GDM_REQUIRE(x->impl.sys == A->impl.sys && b->impl.sys == A->impl.sys, GDM_ERR_INVALID, "vector/operator system mismatch");
+  GDM_REQUIRE(precondition != GDM_PRECONDITION_DIAGONAL || pvec != nullptr, GDM_ERR_INVALID, "DIAGONAL needs a vector");
+  status = cg_solve(A->impl, x->impl, b->impl, precondition, pvec ? &pvec->impl : nullptr, *control);
+  if (status == GDM_ERR_NO_CONVERGENCE)
+    gdm::set_last_error("Iterative method reported convergence failure in step " + std::to_string(control->last_step) +
+                        ". The residual in the last step was " + std::to_string(control->last_value) + ".");
+  if (status != GDM_OK)
+    return status;
+  GDM_CATCH
+}
+
+// ------------------------------------------------------------- vector tools
+int gdm_interpolate(gdm_system_t sys, gdm_function_fn f, void *user, gdm_vector_t v)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(f);
+  GDM_ARG(v);
+  GDM_REQUIRE(v->impl.sys == &sys->impl, GDM_ERR_INVALID, "vector/system mismatch");
+  const Layout       &L = sys->impl.L;
+  std::vector<double> host((size_t)L.n_owned);
+  // owned nodes in lexicographic order
+  int lo[3] = {0, 0, 0}, hi[3] = {L.nn[0], L.nn[1], L.nn[2]};
+  lo[L.pdim] = L.own0;
+  hi[L.pdim] = L.own1;
+  size_t o   = 0;
+  for (int k = lo[2]; k < hi[2]; ++k)
+    for (int j = lo[1]; j < hi[1]; ++j)
+      for (int i = lo[0]; i < hi[0]; ++i)
+        {
+          const double pt[3] = {L.lo[0] + i * L.h[0], L.lo[1] + j * L.h[1], L.lo[2] + k * L.h[2]};
+          for (int c = 0; c < L.nc; ++c)
+            host[o++] = f(pt, c, user);
+        }
+  vector_transfer(v->impl, host.data(), true);
+  GDM_CUDA_CHECK(cudaStreamSynchronize(sys->impl.ctx->stream));
+  GDM_CATCH
+}
+
+int gdm_integrate_difference(gdm_system_t sys, gdm_vector_t v, gdm_function_fn exact, void *user, double *cellwise,
+                             double *global_l2)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(v);
+  GDM_ARG(exact);
+  GDM_REQUIRE(v->impl.sys == &sys->impl, GDM_ERR_INVALID, "vector/system mismatch");
+  const Layout &L = sys->impl.L;
+  Context      &ctx = *sys->impl.ctx;
+  // postprocessing, not on the hot path: evaluate on the host from the stored (owned + ghost) block
+  vector_update_ghosts(v->impl);
+  std::vector<double> u((size_t)L.size);
+  GDM_CUDA_CHECK(cudaMemcpyAsync(u.data(), v->impl.d, u.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+  const int                p = L.p, n1 = p + 1;
+  std::vector<long double> xq, wq;
+  gauss_legendre_01(n1, xq, wq);
+  // shape values per variant: val[v][q][k]
+  std::vector<double> val((size_t)p * n1 * n1);
+  for (int vv = 0; vv < p; ++vv)
+    for (int q = 0; q < n1; ++q)
+      {
+        long double t[MAX_DEGREE + 1];
+        lagrange_eval(p, vv, xq[q], t, nullptr);
+        for (int k = 0; k < n1; ++k)
+          val[((size_t)vv * n1 + q) * n1 + k] = (double)t[k];
+      }
+  const uint64_t n_cells = gdm_system_n_cells(sys);
+  if (cellwise)
+    std::fill(cellwise, cellwise + n_cells, 0.0);
+  // owned cells: last index in [stride*rank, stride*(rank+1))  (system.h:755)
+  const int stride  = (L.N[L.pdim] + L.n_ranks - 1) / L.n_ranks;
+  double    sum_sq  = 0.0;
+  const int nq[3]   = {n1, L.dim >= 2 ? n1 : 1, L.dim >= 3 ? n1 : 1};
+  double    jac     = 1.0;
+  for (int d = 0; d < L.dim; ++d)
+    jac *= L.h[d];
+  for (uint64_t cell = 0; cell < n_cells; ++cell)
+    {
+      int      ci[3] = {0, 0, 0}, off[3] = {0, 0, 0}, var[3] = {0, 0, 0};
+      uint64_t c = cell;
+      for (int d = 0; d < L.dim; ++d)
+        {
+          ci[d] = (int)(c % L.N[d]);
+          c /= L.N[d];
+          off[d] = window_offset(p, L.N[d], ci[d]);
+          var[d] = cell_variant(p, L.N[d], ci[d]);
+        }
+      if (ci[L.pdim] / stride != L.rank)
+        continue;
+      double diff = 0.0;
+      for (int qz = 0; qz < nq[2]; ++qz)
+        for (int qy = 0; qy < nq[1]; ++qy)
+          for (int qx = 0; qx < nq[0]; ++qx)
+            {
+              const double pt[3] = {L.lo[0] + (ci[0] + (double)xq[qx]) * L.h[0],
+                                    L.lo[1] + (ci[1] + (L.dim >= 2 ? (double)xq[qy] : 0.0)) * L.h[1],
+                                    L.lo[2] + (ci[2] + (L.dim >= 3 ? (double)xq[qz] : 0.0)) * L.h[2]};
+              double       w     = (double)wq[qx] * (L.dim >= 2 ? (double)wq[qy] : 1.0) * (L.dim >= 3 ? (double)wq[qz] : 1.0) * jac;
+              for (int comp = 0; comp < L.nc; ++comp)
+                {
+                  double uh = 0.0;
+                  for (int kz = 0; kz < nq[2]; ++kz)
+                    {
+                      const double sz = L.dim >= 3 ? val[((size_t)var[2] * n1 + qz) * n1 + kz] : 1.0;
+                      for (int ky = 0; ky < nq[1]; ++ky)
+                        {
+                          const double sy = L.dim >= 2 ? val[((size_t)var[1] * n1 + qy) * n1 + ky] : 1.0;
+                          for (int kx = 0; kx < n1; ++kx)
+                            {
+                              int idx[3] = {off[0] + kx, off[1] + ky, off[2] + kz};
+                              idx[L.pdim] -= L.loc0;
+                              const int64_t o = (int64_t)idx[2] * L.plane + (int64_t)idx[1] * L.pitch + (int64_t)idx[0] * L.nc + comp;
+                              uh += val[((size_t)var[0] * n1 + qx) * n1 + kx] * sy * sz * u[(size_t)o];
+                            }
+                        }
+                    }
+                  const double e = uh - exact(pt, comp, user);
+                  diff += e * e * w;
+                }
+            }
+      if (cellwise)
+        cellwise[cell] = std::sqrt(diff);
+      sum_sq += diff;
+    }
+  if (global_l2)
+    {
+      if (L.n_ranks > 1)
+        {
+          GDM_CUDA_CHECK(cudaMemcpyAsync(ctx.d_sums + SUM_TMP, &sum_sq, sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+          sum_sq = read_sum(ctx, SUM_TMP, true);
+        }
+      *global_l2 = std::sqrt(sum_sq);
+    }
+  GDM_CATCH
+}
+
+} // extern "C"

@@ -1,0 +1,202 @@
+// Multi-GPU plumbing: one process per GPU, NCCL over NVLink/NVSwitch.
+//
+// Stands in for the MPI traffic the reference generates through deal.II
+// (LinearAlgebra::distributed::Vector::update_ghost_values -> Partitioner Isend/Irecv,
+// MPI_Allreduce inside SolverCG; call sites listed in SURVEY.md section 2b, e.g.
+// tests/poisson_02_gdm.cc:225,236 and applications/wave/include/gdm/wave/stiffness.h:149).
+// The slab partition is the reference's own (include/gdm/system.h:720-757): ghost planes are
+// contiguous in memory, so the halo exchange needs no pack kernel -- ncclSend/ncclRecv straight
+// from/to the vector storage.  NCCL is resolved with dlopen at comm-init time so that the
+// single-GPU path has no NCCL dependency (and picks up the libnccl torch already loaded).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "gdm_internal.h"
+
+namespace gdm
+{
+  namespace
+  {
+    typedef struct ncclComm *ncclComm_t;
+    struct ncclUniqueId
+    {
+      char internal[128];
+    };
+    enum
+    {
+      ncclSuccess = 0
+    };
+    enum
+    {
+      ncclFloat64 = 8
+    };
+    enum
+    {
+      ncclSum = 0,
+      ncclMax = 2
+    };
+
+    struct Nccl
+    {
+      void *lib = nullptr;
+      int (*GetUniqueId)(ncclUniqueId *)                                                     = nullptr;
+      int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int)                              = nullptr;
+      int (*CommDestroy)(ncclComm_t)                                                         = nullptr;
+      int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t)     = nullptr;
+      int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t)                  = nullptr;
+      int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t)                        = nullptr;
+      int (*GroupStart)()                                                                    = nullptr;
+      int (*GroupEnd)()                                                                      = nullptr;
+      const char *(*GetErrorString)(int)                                                     = nullptr;
+    };
+
+    Nccl &nccl()
+    {
+      static Nccl n;
+      if (n.lib)
+        return n;
+      const char *names[] = {"libnccl.so.2", "libnccl.so"};
+      for (const char *nm : names)
+        {
+          n.lib = dlopen(nm, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+          if (n.lib)
+            break;
+        }
+      for (const char *nm : names)
+        {
+          if (n.lib)
+            break;
+          n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        }
+      if (!n.lib)
+        throw Error(GDM_ERR_COMM, std::string("cannot load libnccl: ") + dlerror());
+#define GDM_NCCL_SYM(field, name)                                          \
+  n.field = reinterpret_cast<decltype(n.field)>(dlsym(n.lib, name));       \
+  if (!n.field)                                                            \
+    throw Error(GDM_ERR_COMM, std::string("libnccl lacks symbol ") + name);
+      GDM_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+      GDM_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+      GDM_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+      GDM_NCCL_SYM(AllReduce, "ncclAllReduce");
+      GDM_NCCL_SYM(Send, "ncclSend");
+      GDM_NCCL_SYM(Recv, "ncclRecv");
+      GDM_NCCL_SYM(GroupStart, "ncclGroupStart");
+      GDM_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+      GDM_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef GDM_NCCL_SYM
+      return n;
+    }
+
+    void check(int rc, const char *what)
+    {
+      if (rc != ncclSuccess)
+        throw Error(GDM_ERR_COMM, std::string(what) + ": " + nccl().GetErrorString(rc));
+    }
+  } // namespace
+
+  struct Comm
+  {
+    ncclComm_t comm = nullptr;
+    ~Comm()
+    {
+      if (comm)
+        nccl().CommDestroy(comm);
+    }
+  };
+
+  void comm_unique_id(void *id128)
+  {
+    ncclUniqueId id;
+    check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(id128, &id, sizeof(id));
+  }
+
+  void comm_init(Context &ctx, const void *id128, int rank, int n_ranks)
+  {
+    GDM_REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, GDM_ERR_INVALID, "bad rank");
+    GDM_CUDA_CHECK(cudaSetDevice(ctx.device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    std::unique_ptr<Comm> c(new Comm);
+    check(nccl().CommInitRank(&c->comm, n_ranks, id, rank), "ncclCommInitRank");
+    comm_destroy(ctx);
+    ctx.comm    = c.release();
+    ctx.rank    = rank;
+    ctx.n_ranks = n_ranks;
+  }
+
+  void comm_destroy(Context &ctx)
+  {
+    delete ctx.comm;
+    ctx.comm = nullptr;
+  }
+
+  void comm_allreduce_sum(Context &ctx, double *d_buf, int count, bool max_op)
+  {
+    GDM_REQUIRE(ctx.comm && ctx.comm->comm, GDM_ERR_COMM, "communicator not initialised");
+    check(nccl().AllReduce(d_buf, d_buf, (size_t)count, ncclFloat64, max_op ? ncclMax : ncclSum, ctx.comm->comm,
+                           ctx.stream),
+          "ncclAllReduce");
+  }
+
+  namespace
+  {
+    void owned_range(const Layout &L, int rank, int &o0, int &o1)
+    {
+      const int n_last = L.nn[L.pdim];
+      const int stride = (L.N[L.pdim] + L.n_ranks - 1) / L.n_ranks;
+      o0               = std::min((rank == 0) ? 0 : (stride * rank + 1), n_last);
+      o1               = std::min(stride * (rank + 1) + 1, n_last);
+    }
+  } // namespace
+
+  // Import L.ghost planes from each neighbouring slab into the ghost zones of v.
+  void comm_halo_exchange(Context &ctx, const Layout &L, double *v)
+  {
+    if (L.n_ranks == 1 || L.own1 <= L.own0)
+      return;
+    GDM_REQUIRE(ctx.comm && ctx.comm->comm, GDM_ERR_COMM, "communicator not initialised");
+    // neighbours = nearest non-empty ranks
+    int prev = -1, next = -1, o0, o1;
+    for (int r = L.rank - 1; r >= 0 && prev < 0; --r)
+      {
+        owned_range(L, r, o0, o1);
+        if (o1 > o0)
+          prev = r;
+      }
+    for (int r = L.rank + 1; r < L.n_ranks && next < 0; ++r)
+      {
+        owned_range(L, r, o0, o1);
+        if (o1 > o0)
+          next = r;
+      }
+    const int64_t unit = L.stride[L.pdim];
+    const int     own  = L.own1 - L.own0;
+    const int     glo  = L.own0 - L.loc0; // planes received from prev
+    const int     ghi  = L.loc1 - L.own1; // planes received from next
+    // what the neighbours expect from me
+    const int s_dn = (prev >= 0) ? std::min(L.ghost, L.nn[L.pdim] - L.own0) : 0; // prev's upper ghost
+    const int s_up = (next >= 0) ? std::min(L.ghost, L.own1) : 0;                // next's lower ghost
+    GDM_REQUIRE(s_dn <= own && s_up <= own, GDM_ERR_NOT_IMPLEMENTED,
+                "slab thinner than the ghost zone: use fewer ranks or a larger grid");
+    Nccl &n = nccl();
+    check(n.GroupStart(), "ncclGroupStart");
+    if (prev >= 0)
+      {
+        check(n.Send(v + L.own_off, (size_t)s_dn * unit, ncclFloat64, prev, ctx.comm->comm, ctx.stream), "ncclSend");
+        check(n.Recv(v, (size_t)glo * unit, ncclFloat64, prev, ctx.comm->comm, ctx.stream), "ncclRecv");
+      }
+    if (next >= 0)
+      {
+        check(n.Send(v + L.own_off + (int64_t)(own - s_up) * unit, (size_t)s_up * unit, ncclFloat64, next,
+                     ctx.comm->comm, ctx.stream),
+              "ncclSend");
+        check(n.Recv(v + (int64_t)(L.own1 - L.loc0) * unit, (size_t)ghi * unit, ncclFloat64, next, ctx.comm->comm,
+                     ctx.stream),
+              "ncclRecv");
+      }
+    check(n.GroupEnd(), "ncclGroupEnd");
+  }
+} // namespace gdm

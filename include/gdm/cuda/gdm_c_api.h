@@ -1,0 +1,242 @@
+/* gdm_c_api.h -- C ABI of the B200-native GDM hot path (libgdm_b200.so).
+ *
+ * What this boundary replaces.  The reference has no FFI layer: its hot path
+ * sits behind deal.II's operator/vector concept and a handful of GDM entry
+ * points.  Each group of functions below names the reference interface it
+ * stands in for (paths relative to the reference repository root):
+ *
+ *   gdm_system_*        GDM::System<dim>                 include/gdm/system.h:339-827
+ *   gdm_polynomials_1d  GDM::generate_polynomials_1D     include/gdm/fe.h:55-336
+ *   gdm_constraints_*   dealii::AffineConstraints as filled by
+ *                       System::make_zero_boundary_constraints / make_periodicity_constraints
+ *                                                        include/gdm/system.h:427-508
+ *   gdm_operator_create(MASS)       GDM::MatrixCreator::create_mass_matrix   include/gdm/matrix_creator.h:9-62
+ *   gdm_operator_lumped_mass_inverse  ...::create_lumped_mass_matrix          include/gdm/matrix_creator.h:64-117
+ *   gdm_operator_create(STIFFNESS)  assembly loop        tests/poisson_02_gdm.cc:160-206
+ *   gdm_operator_create(ADVECTION)  residual loop        prototypes/advection_01_gdm.cc:164-206,
+ *                                                        applications/advection/include/gdm/advection/stiffness.h:373-418
+ *   gdm_operator_vmult[_add]        SparseMatrix::vmult at every solver.solve site
+ *                                                        tests/poisson_02_gdm.cc:215, tests/mass_01_gdm.cc:131, ...
+ *   gdm_operator_attach_csr         cut-cell / ghost-penalty rows
+ *                                                        applications/wave/include/gdm/wave/stiffness.h:589-799
+ *   gdm_vector_*        LinearAlgebra::distributed::Vector<double> (deal.II)
+ *   gdm_solver_cg       SolverCG + ReductionControl      tests/poisson_01_gdm.cc:164-170
+ *   gdm_rk_*            TimeStepping::ExplicitRungeKutta prototypes/advection_01_gdm.cc:259-281
+ *   gdm_interpolate / gdm_integrate_difference
+ *                       GDM::VectorTools                 include/gdm/vector_tools.h:11-86
+ *
+ * Conventions: C linkage, opaque handles, plain pointers and sizes.  Every
+ * function returns 0 on success or a gdm_status; the message is available from
+ * gdm_last_error() (thread local).  Nothing throws across the ABI.  All device
+ * work is enqueued on the context's stream (caller supplied cudaStream_t or the
+ * legacy default stream); functions that return host data synchronise that
+ * stream.  One context per GPU; handles are not thread safe, distinct contexts
+ * are.  There is no CPU fallback: if no CUDA device is usable the compute
+ * entry points fail with GDM_ERR_CUDA.
+ */
+#ifndef GDM_C_API_H
+#define GDM_C_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDM_API_VERSION 1
+
+typedef enum gdm_status {
+  GDM_OK                 = 0,
+  GDM_ERR_INVALID        = 1, /* bad argument (deal.II: ExcMessage / ExcDimensionMismatch) */
+  GDM_ERR_NOT_IMPLEMENTED= 2, /* deal.II: ExcNotImplemented */
+  GDM_ERR_CUDA           = 3, /* CUDA runtime / driver failure */
+  GDM_ERR_NO_CONVERGENCE = 4, /* deal.II: SolverControl::NoConvergence */
+  GDM_ERR_COMM           = 5, /* NCCL failure */
+  GDM_ERR_INTERNAL       = 6
+} gdm_status;
+
+typedef struct gdm_context_s     *gdm_context_t;
+typedef struct gdm_system_s      *gdm_system_t;
+typedef struct gdm_constraints_s *gdm_constraints_t;
+typedef struct gdm_operator_s    *gdm_operator_t;
+typedef struct gdm_vector_s      *gdm_vector_t;
+typedef struct gdm_rk_s          *gdm_rk_t;
+
+const char *gdm_last_error(void);
+int         gdm_api_version(void);
+
+/* ---------------------------------------------------------------- context */
+/* device: CUDA ordinal; stream: cudaStream_t (may be NULL = default stream). */
+int gdm_context_create(int device, void *stream, gdm_context_t *ctx);
+int gdm_context_destroy(gdm_context_t ctx);
+int gdm_context_set_stream(gdm_context_t ctx, void *stream);
+int gdm_context_synchronize(gdm_context_t ctx);
+/* Number of kernels this library launched on the context since creation. */
+int gdm_context_launch_count(gdm_context_t ctx, uint64_t *count);
+/* Multi-GPU (one process per GPU).  The unique id is 128 bytes (ncclUniqueId);
+ * rank 0 creates it, the caller broadcasts it (e.g. torch.distributed), every
+ * rank calls gdm_context_comm_init.  Collectives used: ncclSend/ncclRecv for the
+ * ghost planes, ncclAllReduce for CG scalars. */
+int gdm_comm_unique_id(void *id128);
+int gdm_context_comm_init(gdm_context_t ctx, const void *id128, int rank, int n_ranks);
+
+/* ----------------------------------------------------------------- basis */
+/* Monomial coefficients of all p variants, lowest power first:
+ * coeffs[(v*(p+1) + k)*(p+1) + power], v = variant, k = basis function. */
+int gdm_polynomials_1d(int fe_degree, double *coeffs);
+
+/* ---------------------------------------------------------------- system */
+typedef struct gdm_system_desc {
+  int      dim;               /* 1, 2, 3 */
+  int      fe_degree;         /* odd: 1,3,5,7,9 */
+  int      n_components;      /* interleaved: dof = node*n_components + comp */
+  uint32_t n_subdivisions[3]; /* cells per direction (>= fe_degree) */
+  double   lo[3], hi[3];      /* subdivided_hyper_rectangle(p1, p2) */
+  int      rank, n_ranks;     /* slab partition along the last direction (system.h:720-757) */
+  int      add_ghost_layer;   /* widens the ghost zone by one plane (flux sparsity) */
+} gdm_system_desc;
+
+int      gdm_system_create(gdm_context_t ctx, const gdm_system_desc *desc, gdm_system_t *sys);
+int      gdm_system_destroy(gdm_system_t sys);
+uint64_t gdm_system_n_dofs(gdm_system_t sys);             /* global, all components */
+uint64_t gdm_system_n_cells(gdm_system_t sys);
+int      gdm_system_locally_owned_range(gdm_system_t sys, uint64_t *begin, uint64_t *end);
+int      gdm_system_dofs_per_cell(gdm_system_t sys);
+/* system.h:195-246; cell = lexicographic cell index; out has dofs_per_cell entries,
+ * component-major (FESystem numbering), lexicographic inside a component. */
+int      gdm_system_get_dof_indices(gdm_system_t sys, uint64_t cell, uint64_t *out);
+/* system.h:404-424 */
+int      gdm_system_active_fe_index(gdm_system_t sys, uint64_t cell, uint32_t *fe_index);
+/* Physical 1D band matrix of direction d without constraints:
+ * kind 0 = mass (h*M1), 1 = stiffness (K1/h), 2 = convection (C1, row = test fn).
+ * band[(row*(2p+1)) + tap], column = row + tap - p, rows 0..N_d. */
+int      gdm_system_matrix_1d(gdm_system_t sys, int d, int kind, double *band);
+/* Device storage geometry of vectors of this system (doubles). */
+typedef struct gdm_layout_info {
+  uint64_t pitch, plane, size;   /* row pitch, plane stride, total storage */
+  uint64_t owned_offset, owned_size; /* contiguous owned block inside the storage */
+  uint32_t local_nodes[3];       /* stored nodes per direction (incl. ghost planes) */
+  uint32_t owned_begin, owned_end; /* owned node range in the partitioned direction (global) */
+  uint32_t stored_begin, stored_end;
+} gdm_layout_info;
+int      gdm_system_layout(gdm_system_t sys, gdm_layout_info *info);
+
+/* ----------------------------------------------------------- constraints */
+int gdm_constraints_create(gdm_system_t sys, gdm_constraints_t *c);
+int gdm_constraints_destroy(gdm_constraints_t c);
+/* surface = 2*d + side, or -1 for all 2*dim faces (system.h:466-508) */
+int gdm_constraints_make_zero_boundary(gdm_constraints_t c, int surface);
+/* node N_d == node 0 in direction d, weight 1 (system.h:427-463) */
+int gdm_constraints_make_periodicity(gdm_constraints_t c, int d);
+int gdm_constraints_close(gdm_constraints_t c);
+uint64_t gdm_constraints_n_constraints(gdm_constraints_t c);
+int gdm_constraints_is_constrained(gdm_constraints_t c, uint64_t dof);
+/* AffineConstraints::distribute / set_zero on a device vector */
+int gdm_constraints_distribute(gdm_constraints_t c, gdm_vector_t v);
+int gdm_constraints_set_zero(gdm_constraints_t c, gdm_vector_t v);
+
+/* --------------------------------------------------------------- vectors */
+int gdm_vector_create(gdm_system_t sys, gdm_vector_t *v);          /* zero initialised */
+int gdm_vector_destroy(gdm_vector_t v);
+/* host buffers hold the locally owned DoFs, compact, lexicographic (x fastest) */
+int gdm_vector_upload(gdm_vector_t v, const double *host);
+int gdm_vector_download(gdm_vector_t v, double *host);
+void *gdm_vector_device_ptr(gdm_vector_t v);                       /* start of storage */
+int gdm_vector_set(gdm_vector_t v, double value);                  /* owned entries (pads stay 0) */
+int gdm_vector_copy(gdm_vector_t dst, gdm_vector_t src);           /* dst = src */
+int gdm_vector_scale(gdm_vector_t v, double a);                    /* v *= a */
+int gdm_vector_add(gdm_vector_t v, double a, gdm_vector_t x);      /* v += a x          (Vector::add) */
+int gdm_vector_sadd(gdm_vector_t v, double s, double a, gdm_vector_t x); /* v = s v + a x (Vector::sadd) */
+int gdm_vector_scale_by(gdm_vector_t v, gdm_vector_t d);           /* v *= d entrywise (Vector::scale) */
+int gdm_vector_dot(gdm_vector_t a, gdm_vector_t b, double *result); /* all ranks; synchronises */
+int gdm_vector_l2_norm(gdm_vector_t a, double *result);
+int gdm_vector_linfty_norm(gdm_vector_t a, double *result);
+int gdm_vector_update_ghost_values(gdm_vector_t v);                /* import p ghost planes per neighbour */
+
+/* -------------------------------------------------------------- operators */
+typedef enum gdm_operator_kind {
+  GDM_OP_MASS        = 0, /* (phi_i, phi_j) */
+  GDM_OP_STIFFNESS   = 1, /* (grad phi_i, grad phi_j) */
+  GDM_OP_ADVECTION   = 2, /* (phi_i, b . grad phi_j)      prototypes/advection_01_gdm.cc:164-206 (times scale=-1) */
+  GDM_OP_ADVECTION_T = 3  /* (b . grad phi_i, phi_j)      advection/stiffness.h:373-418 (alpha = 0 form) */
+} gdm_operator_kind;
+
+typedef enum gdm_constrained_diagonal {
+  GDM_DIAG_ZERO      = 0, /* constrained rows give 0: vector assembly (residual) semantics */
+  GDM_DIAG_ASSEMBLED = 1  /* sum_cells |cell_matrix(i,i)|: AffineConstraints::distribute_local_to_global on a matrix */
+} gdm_constrained_diagonal;
+
+enum { GDM_KERNEL_AUTO = 0, GDM_KERNEL_GENERIC = 1, GDM_KERNEL_FUSED = 2 };
+
+typedef struct gdm_operator_desc {
+  int    kind;                 /* gdm_operator_kind */
+  double scale;                /* y = scale * A x */
+  double b[3];                 /* advection velocity (constant) */
+  int    constrained_diagonal; /* gdm_constrained_diagonal */
+  int    kernel;               /* GDM_KERNEL_* : AUTO picks the fused sm_100a kernel when it covers the case */
+} gdm_operator_desc;
+
+int gdm_operator_create(gdm_system_t sys, gdm_constraints_t c /* may be NULL */,
+                        const gdm_operator_desc *desc, gdm_operator_t *op);
+int gdm_operator_destroy(gdm_operator_t op);
+/* Irregular rows (cut cells, ghost penalty, Nitsche): CSR rows that REPLACE the
+ * tensor-product result in those rows.  row_ids/col are global DoF indices;
+ * rows must be locally owned, columns within the ghost zone. */
+int gdm_operator_attach_csr(gdm_operator_t op, uint64_t n_rows, const uint64_t *row_ids,
+                            const uint64_t *rowptr, const uint64_t *col, const double *val);
+int gdm_operator_vmult(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src);     /* imports ghosts of src */
+int gdm_operator_vmult_add(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src);
+/* Host-buffer form of vmult (the call a deal.II user makes with host vectors):
+ * copies src to the device, applies, copies dst back; synchronises. */
+int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *src_host);
+int gdm_operator_diagonal(gdm_operator_t op, gdm_vector_t diag);   /* matrix diagonal (Jacobi) */
+/* 1 / (row sums of the mass operator): matrix_creator.h:64-117; op must be MASS */
+int gdm_operator_lumped_mass_inverse(gdm_operator_t op, gdm_vector_t inv);
+int gdm_operator_kernel_used(gdm_operator_t op);                   /* GDM_KERNEL_GENERIC or _FUSED */
+uint64_t gdm_operator_m(gdm_operator_t op);
+
+/* ----------------------------------------------------------------- solver */
+typedef struct gdm_reduction_control {
+  uint32_t max_steps;  /* ReductionControl(n, tol, reduce) */
+  double   tolerance;
+  double   reduce;
+  /* results */
+  uint32_t last_step;
+  double   last_value;
+  double   initial_value;
+} gdm_reduction_control;
+
+typedef enum gdm_precondition {
+  GDM_PRECONDITION_IDENTITY = 0,
+  GDM_PRECONDITION_JACOBI   = 1, /* PreconditionJacobi, relaxation 1 */
+  GDM_PRECONDITION_DIAGONAL = 2  /* DiagonalMatrix: z = d .* r with caller supplied d */
+} gdm_precondition;
+
+/* deal.II SolverCG::solve(A, x, b, P).  Returns GDM_ERR_NO_CONVERGENCE where
+ * deal.II throws SolverControl::NoConvergence (control still filled in). */
+int gdm_solver_cg(gdm_operator_t A, gdm_vector_t x, gdm_vector_t b, int precondition,
+                  gdm_vector_t precondition_vector /* DIAGONAL only */, gdm_reduction_control *control);
+
+/* ------------------------------------------------------------ time stepping */
+typedef enum gdm_rk_method { GDM_RK_FORWARD_EULER = 0, GDM_RK_THIRD_ORDER = 1, GDM_RK_CLASSIC_FOURTH_ORDER = 2 } gdm_rk_method;
+/* f(t, y[0..n_blocks), out[0..n_blocks)) enqueues out = f(t, y) on the context stream. */
+typedef int (*gdm_rk_rhs_fn)(double t, const gdm_vector_t *y, gdm_vector_t *out, void *user);
+int gdm_rk_create(gdm_system_t sys, int method, int n_blocks, gdm_rk_t *rk);
+int gdm_rk_destroy(gdm_rk_t rk);
+/* ExplicitRungeKutta::evolve_one_time_step; returns t + dt in *t_new */
+int gdm_rk_evolve_one_time_step(gdm_rk_t rk, gdm_rk_rhs_fn f, void *user, double t, double dt,
+                                gdm_vector_t *y, double *t_new);
+
+/* -------------------------------------------------------------- vector tools */
+typedef double (*gdm_function_fn)(const double *point, int component, void *user);
+int gdm_interpolate(gdm_system_t sys, gdm_function_fn f, void *user, gdm_vector_t v);
+/* cellwise L2 error (length n_cells of the locally owned cells' global numbering;
+ * cells of other ranks are left 0) and its global l2 sum over all ranks */
+int gdm_integrate_difference(gdm_system_t sys, gdm_vector_t v, gdm_function_fn exact, void *user,
+                             double *cellwise /* may be NULL */, double *global_l2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDM_C_API_H */

@@ -1,0 +1,57 @@
+"""The C-ABI library loads and exports every symbol include/gdm/cuda/gdm_c_api.h declares (CPU only)."""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "gdm", "cuda", "gdm_c_api.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(gdm_[a-z0-9_]+)\s*\(", src))
+    names -= {n for n in names if n.endswith("_fn")}
+    return names
+
+
+def test_every_declared_symbol_is_exported(lib):
+    out = subprocess.check_output(["nm", "-D", "--defined-only",
+                                   os.path.join(ROOT, "dealii-galerkin-difference-methods_b200", "libgdm_b200.so")], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    declared = _declared()
+    assert len(declared) > 50
+    missing = declared - exported
+    assert not missing, missing
+
+
+def test_binding_table_covers_header(lib):
+    import gdm_b200
+    declared = _declared()
+    assert declared == set(gdm_b200.capi.SIGNATURES), declared ^ set(gdm_b200.capi.SIGNATURES)
+    assert lib.gdm_api_version() == 1
+
+
+def test_compute_fails_loudly_without_gpu(lib):
+    """No CPU fallback: a description-only context refuses vectors and operators."""
+    import ctypes as C
+    import pytest
+    import gdm_b200
+    from gdm_b200 import capi
+    ctx = C.c_void_p()
+    assert lib.gdm_context_create(-1, None, C.byref(ctx)) == 0
+    d = capi.SystemDesc()
+    d.dim, d.fe_degree, d.n_components = 2, 3, 1
+    d.n_subdivisions[0] = d.n_subdivisions[1] = 8
+    d.hi[0] = d.hi[1] = 1.0
+    d.rank, d.n_ranks = 0, 1
+    sys_h = C.c_void_p()
+    assert lib.gdm_system_create(ctx, C.byref(d), C.byref(sys_h)) == 0
+    v = C.c_void_p()
+    assert lib.gdm_vector_create(sys_h, C.byref(v)) == capi.ERR_CUDA
+    od = capi.OperatorDesc()
+    od.kind = capi.OP_MASS
+    op = C.c_void_p()
+    assert lib.gdm_operator_create(sys_h, None, C.byref(od), C.byref(op)) == capi.ERR_CUDA
+    assert b"no CPU fallback" in lib.gdm_last_error()
+    lib.gdm_system_destroy(sys_h)
+    lib.gdm_context_destroy(ctx)

@@ -1,0 +1,183 @@
+"""Pin the oracle against the reference's committed golden outputs (CPU only).
+
+Every assertion names the golden file it checks; the files under tests/golden/ are
+verbatim copies made by tests/golden/make_golden.py.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle.basis import lagrange_coefficients, basis_values
+
+
+def _read(golden_dir, name):
+    return open(os.path.join(golden_dir, name)).read()
+
+
+@pytest.mark.parametrize("p", [1, 3, 5, 7, 9])
+def test_basis_tables_match_fe_h(golden_dir, p):
+    """include/gdm/fe.h:62-320 tables == closed-form Lagrange basis."""
+    tabs = json.load(open(os.path.join(golden_dir, "fe_coefficients.json")))
+    assert len(tabs[str(p)]) == p
+    for v in range(p):
+        mine = np.array([[float(c) for c in row] for row in lagrange_coefficients(p, v)])
+        ref = np.array(tabs[str(p)][v])
+        assert mine.shape == ref.shape
+        assert np.abs(mine - ref).max() < 1e-15
+
+
+def test_poly_01_output(golden_dir):
+    """tests/poly_01.output: basis values on 21 points, every variant, p = 1..9, %7.3f."""
+    lines = _read(golden_dir, "poly_01.output").split("\n")
+    it = iter(lines)
+    x = np.arange(21) / 20.0
+    for p in (1, 3, 5, 7, 9):
+        for v in range(p):
+            vals = basis_values(p, v, x, n_der=0)[0]  # [k][point]
+            for j in range(21):
+                gold = [float(t) for t in next(it).split()]
+                assert len(gold) == p + 1
+                mine = [float("%7.3f" % vals[k, j]) for k in range(p + 1)]
+                assert np.allclose(mine, gold, atol=1.001e-3), (p, v, j)
+            assert next(it).strip() == "" and next(it).strip() == ""
+        assert next(it).strip() == "" and next(it).strip() == ""
+
+
+def test_fe_02_output(golden_dir):
+    """tests/fe_02_gdm.output: |value|, |1st..4th derivative| at x=0 of the interior variant."""
+    txt = _read(golden_dir, "fe_02_gdm.output")
+    blocks = txt.split("FESystem<1>[FE_GDM<1>(")[1:]
+    assert len(blocks) == 4
+    for blk in blocks:
+        p = int(blk.split(")")[0])
+        rows = blk.split("\n")[1:p + 2]
+        bv = basis_values(p, p // 2, [0.0], n_der=4)
+        for k, row in enumerate(rows):
+            gold = [float(t) for t in row.split()]
+            mine = [abs(bv[d, k, 0]) for d in range(5)]
+            assert np.allclose(mine, gold, atol=0.51e-3), (p, k, mine, gold)
+
+
+def _poisson_1d(p, n=10):
+    s = O.System(1, p)
+    s.subdivided_hyper_cube(n)
+    c = O.Constraints()
+    s.make_zero_boundary_constraints(c)
+    c.close()
+    A = O.assemble_cell_loop(s, c, "stiffness", literal=True)
+    b = O.rhs_cell_loop(s, c, lambda pts, comp: 1.0)
+    return s, c, A, b
+
+
+def test_poisson_01_output(golden_dir):
+    """tests/poisson_01_gdm.output: CG count 5, nodal values, L2 error for p = 1,3,5,7,9."""
+    tok = _read(golden_dir, "poisson_01_gdm.output").split()
+    pos = 0
+    for p in (1, 3, 5, 7, 9):
+        s, c, A, b = _poisson_1d(p)
+        ctl = O.ReductionControl(100, 1e-10, 1e-4)
+        x = O.solver_cg(A, np.zeros(11), b, O.PreconditionIdentity(), ctl)
+        assert ctl.last_step() == int(tok[pos])
+        gold = np.array([float(t) for t in tok[pos + 1:pos + 12]])
+        assert np.allclose([float("%g" % v) for v in x], gold, atol=1e-12)
+        err = O.compute_global_error(O.integrate_difference(s, x, lambda pts, comp: 0.125 - 0.5 * (pts[:, 0] - 0.5) ** 2))
+        assert "%14.8f" % err == "%14.8f" % float(tok[pos + 13])
+        pos += 14
+
+
+@pytest.mark.parametrize("ranks", [1, 3])
+def test_poisson_02_output(golden_dir, ranks):
+    """tests/poisson_02_gdm.mpirun={1,3}.output: 21 + 441 solution values (AMG count not reproducible)."""
+    tok = _read(golden_dir, f"poisson_02_gdm.mpirun={ranks}.output").split()
+    gold = {1: np.array([float(t) for t in tok[1:22]]), 2: np.array([float(t) for t in tok[23:23 + 441]])}
+    for dim in (1, 2):
+        s = O.System(dim, 3)
+        s.subdivided_hyper_cube(20)
+        c = O.Constraints()
+        s.make_zero_boundary_constraints(c)
+        c.close()
+        A = O.assemble_cell_loop(s, c, "stiffness")
+        b = O.rhs_cell_loop(s, c, lambda pts, comp: 1.0)
+        x = O.solver_cg(A, np.zeros(s.n_dofs()), b, O.PreconditionIdentity(), O.ReductionControl(1000, 1e-14, 1e-12))
+        c.distribute(x)
+        assert np.allclose([float("%g" % v) for v in x], gold[dim], atol=1e-12)
+
+
+@pytest.mark.parametrize("nc,name", [(1, "mass_01_gdm.output"), (2, "mass_02_gdm.output")])
+def test_mass_outputs(golden_dir, nc, name):
+    """tests/mass_0{1,2}_gdm.output: L2 projection error after Jacobi-CG(100, 1e-10, 1e-8)."""
+    gold = _read(golden_dir, name).split()[1]
+    s = O.System(2, 3, nc)
+    s.subdivided_hyper_cube(40)
+    c = O.Constraints()
+    c.close()
+    A = O.assemble_cell_loop(s, c, "mass")
+    f = lambda pts, comp: pts[:, 0] + comp
+    b = O.rhs_cell_loop(s, c, f)
+    ctl = O.ReductionControl(100, 1e-10, 1e-8)
+    x = O.solver_cg(A, np.zeros(s.n_dofs()), b, O.PreconditionJacobi(A), ctl)
+    err = O.compute_global_error(O.integrate_difference(s, x, f))
+    assert "%g" % err == gold
+    assert ctl.last_step() == 18
+
+
+@pytest.mark.parametrize("dim,p,n,bc", [(1, 3, 9, "dirichlet"), (2, 3, 7, "dirichlet"), (2, 5, 12, "periodic"),
+                                         (3, 3, 7, "dirichlet"), (3, 1, 4, "periodic"), (2, 3, 8, "none")])
+@pytest.mark.parametrize("kind", ["mass", "stiffness"])
+def test_kronecker_equals_cell_loop(dim, p, n, bc, kind):
+    """The structure the CUDA kernels rely on: assembled matrix == Kronecker sum of 1D band matrices."""
+    s = O.System(dim, p)
+    reps = [n + d for d in range(dim)]
+    s.subdivided_hyper_rectangle(reps, [0.0] * dim, [1.0 + 0.5 * d for d in range(dim)])
+    c = O.Constraints()
+    if bc == "dirichlet":
+        s.make_zero_boundary_constraints(c)
+    elif bc == "periodic":
+        for d in range(dim):
+            s.make_periodicity_constraints(d, c)
+    c.close()
+    A = O.assemble_cell_loop(s, c, kind)
+    K = O.kron_operator(s, c, kind)
+    scale = abs(A).max()
+    assert abs(A - K).max() <= 1e-13 * scale
+    if dim <= 2:
+        Al = O.assemble_cell_loop(s, c, kind, literal=True)
+        assert abs(A - Al).max() <= 1e-14 * scale
+
+
+def test_advection_residual_is_kronecker():
+    """prototypes/advection_01_gdm.cc:144-206 == -C^T... folded Kronecker form used by the kernels."""
+    s = O.System(2, 3)
+    s.subdivided_hyper_cube(9)
+    c = O.Constraints()
+    for d in range(2):
+        s.make_periodicity_constraints(d, c)
+    c.close()
+    b = [1.0, 0.15]
+    rng = np.random.default_rng(0)
+    u = rng.uniform(-1, 1, s.n_dofs())
+    r = O.advection_residual_cell_loop(s, c, u, b)
+    K = O.kron_operator(s, c, "advection", b=b, constrained_diagonal="zero")
+    assert np.abs(r + K @ u).max() < 1e-13
+
+
+def test_discrete_time_and_rk4():
+    t = O.DiscreteTime(0.0, 0.1, 0.0125)
+    steps = []
+    while not t.is_at_end():
+        steps.append(t.get_next_step_size())
+        t.advance_time()
+    assert len(steps) == 8 and abs(sum(steps) - 0.1) < 1e-15
+    # heat_0.output:11-13 style: last step shortened to land on end
+    t = O.DiscreteTime(0.0, 0.1, 0.03025)
+    n = 0
+    while not t.is_at_end():
+        t.advance_time()
+        n += 1
+    assert n == 4 and t.get_current_time() == 0.1
+    rk = O.ExplicitRungeKutta4()
+    tt, y = rk.evolve_one_time_step(lambda t, y: -y, 0.0, 0.1, np.array([1.0]))
+    assert abs(y[0] - (1 - 0.1 + 0.005 - 0.1 ** 3 / 6 + 0.1 ** 4 / 24)) < 1e-15
