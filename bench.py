@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""Benchmark of the GDM hot path: matrix-free stiffness apply (FP64, 3D, p=3) on 256^3 cells.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one operator application y = K x over the whole grid (BASELINE.json config 2:
+"3D Poisson GDM p=3 on 256^3 cells, matrix-free stiffness apply + CG, 1 B200").  Vectors ping-pong
+(x -> y -> x ...), 2 x 136 MB per GPU, i.e. larger than L2.  N > 1 (torchrun, one rank per GPU):
+weak scaling, every rank owns a 256 x 256 x 256-cell slab of a 256 x 256 x (256 N) grid, ghost planes
+exchanged over NCCL before each apply.  `value` = owned DoFs of all ranks x K / max-over-ranks device
+time.  `e2e` = the same apply through the host-buffer entry point gdm_operator_vmult_host (pinned
+host memory -> H2D -> apply -> D2H).  `cpu_baseline` / `--impl reference`: the reference's CPU path
+(assembled CSR + SpMV, OpenMP over all host cores) restated in oracle/csr_baseline.c, timed on a
+bounded sample (96^3 cells) because the CSR of 256^3 would need ~70 GB.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gdm_stiffness_apply_3d_p3_fp64"
+UNIT = "GDoF/s"
+ALG_BYTES_PER_DOF = 16.0  # read x + write y
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                               "--format=csv,noheader,nounits"], text=True, timeout=5)
+                self.samples.append([t.strip() for t in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_csr_sample(n_cells, p, steps, warmup):
+    """The reference's CPU path on a bounded sample: assembled CSR SpMV, all host cores."""
+    import numpy as np
+    import oracle as O
+    from oracle.csr_baseline import CsrOperator, num_threads
+    s = O.System(3, p)
+    s.subdivided_hyper_cube(n_cells)
+    c = O.Constraints()
+    s.make_zero_boundary_constraints(c)
+    c.close()
+    A = CsrOperator(s, c, "stiffness")
+    x = np.random.default_rng(0).uniform(-1, 1, A.n_rows)
+    y = np.zeros_like(x)
+    for _ in range(warmup):
+        A.vmult(y, x)
+        x, y = y, x
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        A.vmult(y, x)
+        x, y = y, x
+    dt = time.perf_counter() - t0
+    return {"value": A.n_rows * steps / dt / 1e9, "unit": UNIT, "cores": num_threads(), "kind": "port",
+            "sample": f"{steps} CSR SpMV on {n_cells}^3 cells p={p} ({A.n_rows} DoFs, {A.nnz} nnz, int32 col + fp64 val), "
+                      f"OpenMP static row slabs; nproc={os.cpu_count()}",
+            "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    base = cpu_csr_sample(args.cpu_cells, args.p, min(steps, 50), min(warmup, 5))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": min(steps, 50), "warmup": min(warmup, 5), "ms_per_step": base["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D Poisson GDM p={args.p} stiffness apply; reference CPU path (assembled CSR SpMV) "
+                                   f"on a {args.cpu_cells}^3-cell sample of the {args.cells}^3-cell grid"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import gdm_b200 as g
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    ctx = g.init_distributed(local) if world > 1 else g.default_context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    n, p = args.cells, args.p
+    sys_ = g.System(3, p, 1, comm="world" if world > 1 else None, context=ctx)
+    sys_.subdivided_hyper_rectangle([n, n, n * world], [0.0, 0.0, 0.0], [1.0, 1.0, float(world)])
+    con = g.AffineConstraints()
+    sys_.make_zero_boundary_constraints(con)
+    con.close()
+    A = g.SparseMatrix()
+    g.MatrixCreator.create_laplace_matrix(g.MappingQ1(), sys_, g.QGauss(p + 1), A, con)
+    n_owned = sys_.n_locally_owned_dofs()
+    rng = np.random.default_rng(rank)
+    xh = rng.uniform(-1, 1, n_owned)
+    # two (input, output) pairs used alternately: 4 x 136 MB per GPU cycle through HBM, the inputs
+    # are never L2 resident and the values stay bounded (no repeated application to the same data)
+    x, y = g.Vector(sys_, xh), g.Vector(sys_)
+    x2, y2 = g.Vector(sys_, xh[::-1].copy()), g.Vector(sys_)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    pairs = [(x, y), (x2, y2)]
+
+    def step(i):
+        a, b = pairs[i & 1]
+        A.vmult(b, a)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_owned)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(tot, op=torch.distributed.ReduceOp.SUM)
+    ms, total_dofs = float(t.item()), float(tot.item())
+    value = total_dofs * args.steps / (ms * 1e-3) / 1e9
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "quick": True,
+                              "frac_of_hbm_roofline": ALG_BYTES_PER_DOF * value / peaks()[0]}))
+        return
+    # ---- end to end through the host-buffer entry point (pinned host memory)
+    e2e_steps = max(3, min(args.steps, 10))
+    hx = torch.empty(n_owned, dtype=torch.float64).pin_memory()
+    hy = torch.empty(n_owned, dtype=torch.float64).pin_memory()
+    hx.copy_(torch.from_numpy(xh))
+    hxn, hyn = hx.numpy(), hy.numpy()
+    A.vmult_host(hyn, hxn)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        A.vmult_host(hyn, hxn)
+        hxn, hyn = hyn, hxn
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    e2e_value = total_dofs * e2e_steps / (ms_e2e * 1e-3) / 1e9
+
+    # ---- CG solve time on the same grid (the second half of BASELINE.json's metric)
+    cg = None
+    if args.cg_steps > 0:
+        b = g.Vector(sys_)
+        b.set(1.0)
+        con.set_zero(b)
+        u = g.Vector(sys_)
+        ctl = g.ReductionControl(args.cg_steps, 1e-30, 1e-30)
+        barrier()
+        e0.record()
+        try:
+            g.SolverCG(ctl).solve(A, u, b, g.PreconditionIdentity())
+        except g.NoConvergence:
+            pass
+        e1.record()
+        barrier()
+        ms_cg = e0.elapsed_time(e1)
+        cg = {"iterations": ctl.last_step(), "ms_per_iteration": ms_cg / max(ctl.last_step(), 1),
+              "gdof_iterations_per_s": total_dofs * ctl.last_step() / (ms_cg * 1e-3) / 1e9}
+
+    if rank != 0:
+        return
+    peak, which = peaks()
+    achieved = ALG_BYTES_PER_DOF * (total_dofs / world) / (ms / args.steps * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)",
+                "kernel": "kron3d_kernel (fused TMA-staged tensor-product apply)" if A.kernel_used() == 2 else "generic band passes",
+                "algorithmic_bytes_per_launch": ALG_BYTES_PER_DOF * total_dofs / world,
+                "note": "duration = CUDA-event time of the timed region / steps (includes the constrained-face kernels)"}
+    base = cpu_csr_sample(args.cpu_cells, p, 10, 2) if world == 1 or True else None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D Poisson GDM p={p}, {n}x{n}x{n * world} cells ({int(total_dofs)} DoFs), zero Dirichlet, "
+                                   f"matrix-free stiffness apply y=Kx; x~U(-1,1) seed rank; ping-pong two alternating (x,y) pairs "
+                                   f"(4 x {n_owned * 8 / 1e6:.0f} MB per GPU > L2, no L2 flush needed)",
+                       "parallelism": f"slab{world}", "kernel": roofline["kernel"]},
+            "roofline": roofline, "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_owned * 8, "d2h_bytes_per_step": n_owned * 8,
+                    "steps": e2e_steps, "api": "gdm_operator_vmult_host (pinned host buffers)"},
+            "gpu_launches": int(launches), "clocks": clocks, "cg": cg}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=256, help="cells per direction per GPU")
+    ap.add_argument("--p", type=int, default=3)
+    ap.add_argument("--cpu-cells", type=int, default=96, help="grid of the bounded CPU sample")
+    ap.add_argument("--cg-steps", type=int, default=50)
+    ap.add_argument("--quick", action="store_true", help="timed applies only (for ncu captures)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

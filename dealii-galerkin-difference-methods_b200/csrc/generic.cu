@@ -68,7 +68,9 @@ namespace gdm
       const double *src;
       const double *diagA[3], *diagB[3];
       int           dim, nc, has_B, accumulate;
-      int           d, node; // face: local index `node` in direction d
+      int           n_faces;           // all constrained faces are handled by ONE launch
+      int           face_d[6], face_node[6]; // face f: local index face_node[f] in direction face_d[f]
+      int64_t       face_off[7];       // prefix sums of the face sizes
       int           ln[3];
       int           con_lo[3], con_hi[3]; // constrained end nodes per direction (local index or -1)
       int           own_lo, own_hi, pdim; // owned window (local indices) in pdim
@@ -101,15 +103,22 @@ namespace gdm
 
     __global__ void constrained_rows_kernel(const FaceK a)
     {
-      const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-      int           idx[3];
-      bool          valid;
-      face_index(a.dim, a.d, a.ln, tid, a.node, idx, valid);
+      int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (tid >= a.face_off[a.n_faces])
+        return;
+      int f = 0;
+      while (tid >= a.face_off[f + 1])
+        ++f;
+      tid -= a.face_off[f];
+      const int fd = a.face_d[f];
+      int       idx[3];
+      bool      valid;
+      face_index(a.dim, fd, a.ln, tid, a.face_node[f], idx, valid);
       if (!valid)
         return;
       if (idx[a.pdim] < a.own_lo || idx[a.pdim] >= a.own_hi)
         return;
-      for (int e = 0; e < a.d; ++e) // the lowest constrained direction handles the node
+      for (int e = 0; e < fd; ++e) // the lowest constrained direction handles the node
         if (idx[e] == a.con_lo[e] || idx[e] == a.con_hi[e])
           return;
       double val;
@@ -322,7 +331,8 @@ namespace gdm
     a.pdim       = L.pdim;
     a.own_lo     = L.own0 - L.loc0;
     a.own_hi     = L.own1 - L.loc0;
-    a.scale      = op.desc.scale;
+    // GDM_DIAG_ZERO: constrained rows are written as exact zeros (residual semantics)
+    a.scale      = (op.desc.constrained_diagonal == GDM_DIAG_ASSEMBLED) ? op.desc.scale : 0.0;
     for (int d = 0; d < 3; ++d)
       {
         a.diagA[d]  = op.ddiagA[d];
@@ -331,19 +341,25 @@ namespace gdm
         a.stride[d] = L.stride[d];
         constrained_ends(L, op.dirichlet, op.periodic, d, a.con_lo[d], a.con_hi[d]);
       }
+    a.n_faces     = 0;
+    a.face_off[0] = 0;
     for (int d = 0; d < L.dim; ++d)
       for (int s = 0; s < 2; ++s)
         {
           const int node = s == 0 ? a.con_lo[d] : a.con_hi[d];
-          if (node < 0)
+          if (node < 0 || (s == 1 && node == a.con_lo[d]))
             continue;
-          a.d              = d;
-          a.node           = node;
-          const int64_t n  = face_points(L, d);
-          const int     th = 128;
-          constrained_rows_kernel<<<(unsigned)((n + th - 1) / th), th, 0, ctx.stream>>>(a);
-          ctx.launches++;
+          a.face_d[a.n_faces]       = d;
+          a.face_node[a.n_faces]    = node;
+          a.face_off[a.n_faces + 1] = a.face_off[a.n_faces] + face_points(L, d);
+          ++a.n_faces;
         }
+    if (a.n_faces == 0)
+      return;
+    const int64_t n  = a.face_off[a.n_faces];
+    const int     th = 128;
+    constrained_rows_kernel<<<(unsigned)((n + th - 1) / th), th, 0, ctx.stream>>>(a);
+    ctx.launches++;
     GDM_CUDA_CHECK(cudaGetLastError());
   }
 

@@ -1,9 +1,750 @@
-// placeholder: replaced by the fused tensor-product kernel
+// Fused matrix-free GDM operator apply for dim == 3 on sm_100a:
+//
+//     y = scale * ( B_x (x) A_y (x) A_z  +  A_x (x) B_y (x) A_z  +  A_x (x) A_y (x) B_z ) x      (HASB)
+//     y = scale * ( A_x (x) A_y (x) A_z ) x                                                      (mass)
+//
+// A_d, B_d are the assembled 1D GDM band matrices (half bandwidth p, Toeplitz except for the p+1
+// one-sided rows at each end; Dirichlet masks folded in).  This replaces the assembled
+// SparseMatrix::vmult of the reference (343 nnz/row at p=3: tests/poisson_02_gdm.cc:215,
+// applications/wave/include/gdm/wave/problem.h:486-488) by sum factorisation with every input
+// element read from HBM once and every output written once (16 B/DoF).
+//
+// Structure (2.5D blocking): a CTA owns a TX x TY tile of the xy plane and streams a chunk of z.
+//   * TMA (cp.async.bulk.tensor.3d, mbarrier complete_tx) stages the (TX+2p) x (TY+2p) input tile of
+//     plane k+STAGES into shared memory while plane k is processed; out-of-range coordinates are
+//     zero filled by the TMA unit, which provides the domain-edge padding for free.
+//   * x pass: tasks of RX consecutive outputs per row, lanes mapped to rows (conflict-free 128-bit
+//     LDS/STS through odd 16-byte pitches); symmetric taps share the pair sums between A and B.
+//   * y pass: lanes mapped to x (conflict-free 64-bit LDS), RY consecutive rows per thread.
+//   * z pass: in registers, scatter form: 2p running accumulators per point, shifted by the FMA
+//     itself (acc[j-1] = acc[j] + c_j u); per-plane coefficient rows come from a table, so the
+//     one-sided z rows and the slab offset of a multi-GPU partition need no special code.
+//   * one __syncthreads per plane; a,b fields are double buffered.
+// Non-Toeplitz rows in x / y are recomputed from the row tables by the few threads that own them.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+
 #include "gdm_internal.h"
+
 namespace gdm
 {
-  bool fused_supported(const Operator &) { return false; }
-  void fused_plan_create(Operator &) {}
-  void fused_plan_destroy(Operator &) {}
-  void fused_apply(Operator &, double *, const double *, bool) { throw Error(GDM_ERR_INTERNAL, "fused kernel not built"); }
+  namespace
+  {
+    // ------------------------------------------------------------------ PTX helpers
+    __device__ __forceinline__ uint32_t smem_u32(const void *p)
+    {
+      return (uint32_t)__cvta_generic_to_shared(p);
+    }
+    __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+    {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    }
+    __device__ __forceinline__ void mbar_fence_init()
+    {
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+    {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    }
+    __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+    {
+      asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+    }
+    __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+    {
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                   "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                   : "memory");
+    }
+
+    // ------------------------------------------------------------------ configuration
+    template <int P_, int TX_, int RY_, int NRB_, int RX_, int STAGES_, int MINB_>
+    struct Cfg
+    {
+      static constexpr int P = P_, TX = TX_, RY = RY_, NRB = NRB_, RX = RX_, STAGES = STAGES_, MINB = MINB_;
+      static constexpr int W       = 2 * P + 1;
+      static constexpr int TY      = RY * NRB;
+      static constexpr int NR      = TY + 2 * P;            // rows of the staged tile
+      static constexpr int PIN     = TX + 2 * P;            // pitch of the staged tile (dense TMA box)
+      static constexpr int PAB     = TX + 2;                // pitch of the a/b fields
+      static constexpr int THREADS = TX * NRB;
+      static constexpr int NXB     = TX / RX;
+      static constexpr int NTASK   = NXB * NR;
+      static_assert(TX % 32 == 0 && TX % RX == 0 && RX % 2 == 0, "tile shape");
+      static_assert(((PIN / 2) & 1) == 1 && ((PAB / 2) & 1) == 1, "16-byte pitches must be odd for conflict-free LDS.128");
+      static constexpr int STAGE_DOUBLES = (NR * PIN + 15) / 16 * 16; // stage stride, 128-byte aligned for TMA
+    };
+
+    template <int P>
+    struct KArgs
+    {
+      double       *dst;
+      int64_t       pitch, plane;
+      int           cx0, cx1, cy0, cy1, cz0, cz1; // output window (local node indices)
+      int           xorg;                         // x origin of the tile grid: xorg - P is even (TMA needs 16-byte aligned box starts)
+      int           nx, ny;                       // cells per direction (boundary rows: <= P or >= N-P)
+      int           tiles_x, tiles_y, lz;
+      int           nz_local;
+      int           accumulate;
+      int           dbg; // ablation switches for profiling (GDM_FUSED_DBG): 1 no stores, 2 no TMA, 4 no x pass, 8 no y/z pass
+      const double *tabAx, *tabBx, *tabAy, *tabBy; // row tables [node][2P+1]
+      const double *zsA, *zsB;                     // scatter rows [plane][2P+1], scale folded in
+      double        Ax[P + 1], Bx[P + 1], Ay[P + 1], By[P + 1]; // interior taps by distance
+    };
+
+    template <class C, bool HASB>
+    constexpr size_t smem_bytes()
+    {
+      return (size_t)(C::STAGES * C::STAGE_DOUBLES + 2 * (HASB ? 2 : 1) * C::NR * C::PAB + 2 * 2 * 16) * sizeof(double) +
+             C::STAGES * sizeof(uint64_t) + 128;
+    }
+
+    // ------------------------------------------------------------------ the kernel
+    template <class C, bool HASB, int BSYM, bool ACCUM>
+    __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_kernel(const __grid_constant__ CUtensorMap tmap, const KArgs<C::P> g)
+    {
+      constexpr int P = C::P, W = C::W, TX = C::TX, RY = C::RY, RX = C::RX, NR = C::NR, PIN = C::PIN, PAB = C::PAB;
+      constexpr int NF = HASB ? 2 : 1;
+      // dynamic shared memory, addressed through the typed array so that the compiler emits LDS/STS
+      extern __shared__ __align__(128) double smem[];
+      constexpr int OFF_AB  = C::STAGES * C::STAGE_DOUBLES; // [2][NF][NR][PAB]
+      constexpr int OFF_ZT  = OFF_AB + 2 * NF * NR * PAB;   // [2][2][16]
+      constexpr int OFF_BAR = OFF_ZT + 2 * 2 * 16;          // [STAGES] mbarriers
+      uint64_t     *bars    = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+
+      const int tid = threadIdx.x;
+      int       b   = blockIdx.x;
+      const int tx  = b % g.tiles_x;
+      b /= g.tiles_x;
+      const int ty    = b % g.tiles_y;
+      const int chunk = b / g.tiles_y;
+      const int x0    = g.xorg + tx * TX;
+      const int y0    = g.cy0 + ty * C::TY;
+      const int zc0   = g.cz0 + chunk * g.lz;
+      const int zc1   = min(zc0 + g.lz, g.cz1);
+      const int kbeg = zc0 - P, kend = zc1 + P;
+      const int ncols   = min(TX, g.cx1 - x0);    // output columns of this tile (columns below cx0 are masked)
+      const int nrows   = min(C::TY, g.cy1 - y0); // valid output rows
+      const int nr_need = nrows + 2 * P;          // staged rows that feed valid outputs
+
+      constexpr unsigned STAGE_BYTES = NR * PIN * sizeof(double);
+      if (tid == 0)
+        {
+          for (int s = 0; s < C::STAGES; ++s)
+            mbar_init(&bars[s], 1);
+          mbar_fence_init();
+        }
+      __syncthreads();
+      if (tid == 0 && !(g.dbg & 2))
+        for (int s = 0; s < C::STAGES; ++s)
+          if (kbeg + s < kend)
+            {
+              mbar_expect_tx(&bars[s], STAGE_BYTES);
+              tma_load_3d(smem + s * C::STAGE_DOUBLES, &tmap, &bars[s], x0 - P, y0 - P, kbeg + s);
+            }
+
+      // y/z pass ownership: lane -> x, rb -> RY consecutive rows
+      const int  lx        = tid % TX;
+      const int  rb        = tid / TX;
+      const int  gy_first  = y0 + rb * RY;
+      const bool yz_active = (lx < ncols) && (x0 + lx >= g.cx0) && (rb * RY < nrows);
+      const bool y_bnd     = (gy_first <= P) || (gy_first + RY - 1 >= g.ny - P);
+      // x pass ownership (one or more tasks per thread): lanes -> rows
+      double acc[RY][2 * P];
+#pragma unroll
+      for (int i = 0; i < RY; ++i)
+#pragma unroll
+        for (int j = 0; j < 2 * P; ++j)
+          acc[i][j] = 0.0;
+
+      // per-plane z coefficients (uniform), fetched one plane ahead: ZT[buf][field][j]
+      const int     zj = tid % W, zf = (tid / W) & 1;
+      const double *zsrc = (zf ? g.zsB : g.zsA) + zj;
+      double        znext = 0.0;
+      if (tid < 2 * W && kbeg >= 0 && kbeg < g.nz_local)
+        znext = __ldg(zsrc + (int64_t)kbeg * W);
+
+      int stage = 0, parity = 0, buf = 0;
+      for (int k = kbeg; k < kend; ++k)
+        {
+          if (tid < 2 * W)
+            {
+              smem[OFF_ZT + (buf * 2 + zf) * 16 + zj] = znext;
+              znext = (k + 1 >= 0 && k + 1 < g.nz_local) ? __ldg(zsrc + (int64_t)(k + 1) * W) : 0.0;
+            }
+          if (!(g.dbg & 2))
+            mbar_wait(&bars[stage], parity);
+
+          // ------------------------------------------------------------ x pass
+          {
+            const int in_off = stage * C::STAGE_DOUBLES;
+            const int a_off  = OFF_AB + (buf * NF + 0) * NR * PAB;
+            const int b_off  = OFF_AB + (buf * NF + (NF - 1)) * NR * PAB;
+            for (int task = tid; task < C::NTASK && !(g.dbg & 4); task += C::THREADS)
+              {
+                const int r  = task % NR;
+                const int xb = task / NR;
+                if (r >= nr_need || xb * RX >= ncols)
+                  continue;
+                double v[RX + 2 * P];
+                {
+                  const double2 *src = reinterpret_cast<const double2 *>(smem + in_off + r * PIN + xb * RX);
+#pragma unroll
+                  for (int q = 0; q < (RX + 2 * P) / 2; ++q)
+                    {
+                      const double2 t = src[q];
+                      v[2 * q]        = t.x;
+                      v[2 * q + 1]    = t.y;
+                    }
+                }
+                double a[RX], bb[RX];
+#pragma unroll
+                for (int j = 0; j < RX; ++j)
+                  {
+                    const int c   = j + P;
+                    double    ra  = g.Ax[0] * v[c];
+                    double    rbv = (HASB && BSYM > 0) ? g.Bx[0] * v[c] : 0.0;
+#pragma unroll
+                    for (int d = 1; d <= P; ++d)
+                      {
+                        const double s = v[c - d] + v[c + d];
+                        ra             = fma(g.Ax[d], s, ra);
+                        if (HASB)
+                          {
+                            if (BSYM > 0)
+                              rbv = fma(g.Bx[d], s, rbv);
+                            else
+                              rbv = fma(g.Bx[d], v[c + d] - v[c - d], rbv);
+                          }
+                      }
+                    a[j]  = ra;
+                    bb[j] = rbv;
+                  }
+                const int gx_first = x0 + xb * RX;
+                if (gx_first <= P || gx_first + RX - 1 >= g.nx - P)
+                  {
+#pragma unroll
+                    for (int j = 0; j < RX; ++j)
+                      {
+                        const int gx = gx_first + j;
+                        if ((gx <= P || gx >= g.nx - P) && gx >= 0 && gx <= g.nx)
+                          {
+                            double ra = 0.0, rbv = 0.0;
+#pragma unroll
+                            for (int t = 0; t < W; ++t)
+                              {
+                                ra = fma(__ldg(g.tabAx + gx * W + t), v[j + t], ra);
+                                if (HASB)
+                                  rbv = fma(__ldg(g.tabBx + gx * W + t), v[j + t], rbv);
+                              }
+                            a[j]  = ra;
+                            bb[j] = rbv;
+                          }
+                      }
+                  }
+                double2 *da = reinterpret_cast<double2 *>(smem + a_off + r * PAB + xb * RX);
+#pragma unroll
+                for (int q = 0; q < RX / 2; ++q)
+                  da[q] = make_double2(a[2 * q], a[2 * q + 1]);
+                if (HASB)
+                  {
+                    double2 *db = reinterpret_cast<double2 *>(smem + b_off + r * PAB + xb * RX);
+#pragma unroll
+                    for (int q = 0; q < RX / 2; ++q)
+                      db[q] = make_double2(bb[2 * q], bb[2 * q + 1]);
+                  }
+              }
+          }
+          __syncthreads();
+          // stage is free again: prefetch plane k + STAGES
+          if (tid == 0 && k + C::STAGES < kend && !(g.dbg & 2))
+            {
+              mbar_expect_tx(&bars[stage], STAGE_BYTES);
+              tma_load_3d(smem + stage * C::STAGE_DOUBLES, &tmap, &bars[stage], x0 - P, y0 - P, k + C::STAGES);
+            }
+
+          // ------------------------------------------------------------ y pass + z pass
+          if (yz_active && !(g.dbg & 8))
+            {
+              const int a_off = OFF_AB + (buf * NF + 0) * NR * PAB + (rb * RY) * PAB + lx;
+              const int b_off = OFF_AB + (buf * NF + (NF - 1)) * NR * PAB + (rb * RY) * PAB + lx;
+              double    u1[RY], u2[RY];
+              {
+                double aw[RY + 2 * P], bw[RY + 2 * P];
+#pragma unroll
+                for (int j = 0; j < RY + 2 * P; ++j)
+                  {
+                    aw[j] = smem[a_off + j * PAB];
+                    if (HASB)
+                      bw[j] = smem[b_off + j * PAB];
+                  }
+                if (!y_bnd)
+                  {
+#pragma unroll
+                    for (int i = 0; i < RY; ++i)
+                      {
+                        const int c = i + P;
+                        double    t1 = g.Ay[0] * aw[c], t2 = 0.0;
+                        if (HASB)
+                          {
+                            t2 = g.Ay[0] * bw[c];
+                            if (BSYM > 0)
+                              t2 = fma(g.By[0], aw[c], t2);
+                          }
+#pragma unroll
+                        for (int d = 1; d <= P; ++d)
+                          {
+                            const double sa = aw[c - d] + aw[c + d];
+                            t1              = fma(g.Ay[d], sa, t1);
+                            if (HASB)
+                              {
+                                const double sb = bw[c - d] + bw[c + d];
+                                t2              = fma(g.Ay[d], sb, t2);
+                                if (BSYM > 0)
+                                  t2 = fma(g.By[d], sa, t2);
+                                else
+                                  t2 = fma(g.By[d], aw[c + d] - aw[c - d], t2);
+                              }
+                          }
+                        u1[i] = t1;
+                        u2[i] = t2;
+                      }
+                  }
+                else
+                  {
+#pragma unroll
+                    for (int i = 0; i < RY; ++i)
+                      {
+                        const int     gy = min(gy_first + i, g.ny); // rows past the domain are never stored
+                        const double *ta = g.tabAy + gy * W;
+                        const double *tb = g.tabBy + gy * W;
+                        double        t1 = 0.0, t2 = 0.0;
+#pragma unroll
+                        for (int t = 0; t < W; ++t)
+                          {
+                            const double ca = __ldg(ta + t);
+                            t1              = fma(ca, aw[i + t], t1);
+                            if (HASB)
+                              {
+                                t2 = fma(ca, bw[i + t], t2);
+                                t2 = fma(__ldg(tb + t), aw[i + t], t2);
+                              }
+                          }
+                        u1[i] = t1;
+                        u2[i] = t2;
+                      }
+                  }
+              }
+              // z pass (scatter form): y_r += A_z[r][k] u2 + B_z[r][k] u1 for the 2P+1 rows r around plane k
+              double zA[W], zB[W];
+#pragma unroll
+              for (int j = 0; j < W; ++j)
+                {
+                  zA[j] = smem[OFF_ZT + (buf * 2 + 0) * 16 + j];
+                  zB[j] = HASB ? smem[OFF_ZT + (buf * 2 + 1) * 16 + j] : 0.0;
+                }
+              double res[RY];
+#pragma unroll
+              for (int i = 0; i < RY; ++i)
+                {
+                  const double u = HASB ? u2[i] : u1[i];
+                  double       t = fma(zA[0], u, acc[i][0]);
+                  if (HASB)
+                    t = fma(zB[0], u1[i], t);
+                  res[i] = t;
+#pragma unroll
+                  for (int j = 1; j < 2 * P; ++j)
+                    {
+                      double s = fma(zA[j], u, acc[i][j]);
+                      if (HASB)
+                        s = fma(zB[j], u1[i], s);
+                      acc[i][j - 1] = s;
+                    }
+                  double s = zA[2 * P] * u;
+                  if (HASB)
+                    s = fma(zB[2 * P], u1[i], s);
+                  acc[i][2 * P - 1] = s;
+                }
+              const int r_out = k - P; // output plane completed by this input plane
+              if (r_out >= zc0 && r_out < zc1 && !(g.dbg & 1))
+                {
+                  double *out = g.dst + (int64_t)r_out * g.plane + (int64_t)gy_first * g.pitch + (x0 + lx);
+#pragma unroll
+                  for (int i = 0; i < RY; ++i)
+                    if (gy_first + i < g.cy1)
+                      {
+                        double *o = out + (int64_t)i * g.pitch;
+                        double  t = res[i];
+                        if (ACCUM)
+                          t += *o;
+                        *o = t;
+                      }
+                }
+            }
+          if (++stage == C::STAGES)
+            {
+              stage = 0;
+              parity ^= 1;
+            }
+          buf ^= 1;
+        }
+    }
+
+    // ------------------------------------------------------------------ host side
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+    EncodeTiledFn encode_fn()
+    {
+      static EncodeTiledFn fn = nullptr;
+      if (!fn)
+        {
+          void                           *p = nullptr;
+          cudaDriverEntryPointQueryResult qres;
+          GDM_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+          GDM_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, GDM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+          fn = reinterpret_cast<EncodeTiledFn>(p);
+        }
+      return fn;
+    }
+
+    struct FusedPlan
+    {
+      int      cfg = 0;     // index into GDM_FUSED_CONFIGS
+      int      tiles_x = 0, tiles_y = 0, n_chunks = 0, lz = 0;
+      int      cx0, cx1, cy0, cy1, cz0, cz1, xorg;
+      bool     tune = false; // pick the z-chunk length by timing candidates on the first apply
+      double  *d_zsA = nullptr, *d_zsB = nullptr;
+      std::map<const void *, CUtensorMap> maps;
+      ~FusedPlan()
+      {
+        cudaFree(d_zsA);
+        cudaFree(d_zsB);
+      }
+    };
+
+    // available tile configurations (selected per degree; GDM_FUSED_CFG=<id> overrides for tuning)
+    //                      id        P  TX RY NRB RX ST MINB
+#define GDM_FUSED_CONFIGS(X)            \
+  X(0, Cfg<1, 32, 8, 4, 8, 3, 3>)       \
+  X(1, Cfg<3, 32, 7, 6, 8, 3, 2>)       \
+  X(2, Cfg<5, 32, 4, 6, 8, 3, 2>)       \
+  X(3, Cfg<3, 32, 8, 4, 8, 2, 3>)       \
+  X(4, Cfg<3, 64, 7, 6, 8, 3, 1>)       \
+  X(5, Cfg<3, 32, 6, 7, 8, 3, 2>)       \
+  X(6, Cfg<3, 32, 4, 8, 8, 3, 2>)       \
+  X(7, Cfg<3, 64, 4, 8, 8, 3, 1>)       \
+  X(8, Cfg<3, 32, 7, 6, 8, 2, 2>)       \
+  X(9, Cfg<3, 32, 7, 6, 8, 4, 2>)       \
+  X(10, Cfg<3, 32, 5, 8, 8, 3, 2>)      \
+  X(11, Cfg<3, 32, 8, 4, 8, 3, 2>)      \
+  X(12, Cfg<3, 32, 4, 8, 8, 2, 2>)      \
+  X(13, Cfg<3, 64, 8, 4, 8, 2, 1>)      \
+  X(14, Cfg<3, 32, 4, 8, 4, 3, 2>)
+
+    template <class F>
+    void with_config(int id, F &&f)
+    {
+      switch (id)
+        {
+#define GDM_CASE(ID, ...) \
+  case ID:                \
+    f(__VA_ARGS__{});     \
+    break;
+          GDM_FUSED_CONFIGS(GDM_CASE)
+#undef GDM_CASE
+          default:
+            throw Error(GDM_ERR_INTERNAL, "unknown fused kernel configuration");
+        }
+    }
+
+    int default_config(int p)
+    {
+      int id = (p == 1) ? 0 : (p == 3 ? 1 : 2);
+      if (const char *env = std::getenv("GDM_FUSED_CFG"))
+        {
+          const int e = atoi(env);
+          int       ep = -1;
+          try
+            {
+              with_config(e, [&](auto c) { ep = decltype(c)::P; });
+            }
+          catch (...)
+            {}
+          if (ep == p)
+            id = e;
+        }
+      return id;
+    }
+
+    template <class C>
+    void fill_interior(const Operator &op, KArgs<C::P> &a)
+    {
+      constexpr int P = C::P, W = C::W;
+      const Layout &L = op.sys->L;
+      // any interior (Toeplitz) row: P+1 is interior because N >= 2P+2 is required
+      const int ix = P + 1, iy = P + 1;
+      for (int d = 0; d <= P; ++d)
+        {
+          a.Ax[d] = op.hA[0][(size_t)ix * W + P + d];
+          a.Ay[d] = op.hA[1][(size_t)iy * W + P + d];
+          a.Bx[d] = op.has_B ? op.hB[0][(size_t)ix * W + P + d] : 0.0;
+          a.By[d] = op.has_B ? op.hB[1][(size_t)iy * W + P + d] : 0.0;
+        }
+      (void)L;
+    }
+
+    template <class C, bool HASB, int BSYM, bool ACCUM>
+    void launch_variant(Operator &op, FusedPlan &plan, const CUtensorMap &map, double *dst)
+    {
+      Context      &ctx = *op.sys->ctx;
+      const Layout &L   = op.sys->L;
+      KArgs<C::P>   a;
+      a.dst        = dst;
+      a.pitch      = L.pitch;
+      a.plane      = L.plane;
+      a.cx0        = plan.cx0;
+      a.cx1        = plan.cx1;
+      a.cy0        = plan.cy0;
+      a.cy1        = plan.cy1;
+      a.cz0        = plan.cz0;
+      a.cz1        = plan.cz1;
+      a.xorg       = plan.xorg;
+      a.nx         = L.N[0];
+      a.ny         = L.N[1];
+      a.tiles_x    = plan.tiles_x;
+      a.tiles_y    = plan.tiles_y;
+      a.lz         = plan.lz;
+      a.nz_local   = L.ln[2];
+      a.accumulate = ACCUM ? 1 : 0;
+      a.dbg        = std::getenv("GDM_FUSED_DBG") ? atoi(std::getenv("GDM_FUSED_DBG")) : 0;
+      a.tabAx      = op.dA[0];
+      a.tabBx      = op.dB[0];
+      a.tabAy      = op.dA[1];
+      a.tabBy      = op.dB[1];
+      a.zsA        = plan.d_zsA;
+      a.zsB        = plan.d_zsB;
+      fill_interior<C>(op, a);
+      auto         kern  = kron3d_kernel<C, HASB, BSYM, ACCUM>;
+      const size_t smem  = smem_bytes<C, HASB>();
+      static bool  attr_set = false;
+      if (!attr_set)
+        {
+          GDM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          attr_set = true;
+        }
+      const int grid = plan.tiles_x * plan.tiles_y * plan.n_chunks;
+      if (grid <= 0)
+        return;
+      kern<<<grid, C::THREADS, smem, ctx.stream>>>(map, a);
+      ctx.launches++;
+      GDM_CUDA_CHECK(cudaGetLastError());
+    }
+
+    template <class C>
+    const CUtensorMap &get_map(Operator &op, FusedPlan &plan, const double *src)
+    {
+      auto it = plan.maps.find(src);
+      if (it != plan.maps.end())
+        return it->second;
+      if (plan.maps.size() > 64)
+        plan.maps.clear();
+      const Layout &L = op.sys->L;
+      CUtensorMap   m;
+      cuuint64_t    dims[3]    = {(cuuint64_t)L.ln[0], (cuuint64_t)L.ln[1], (cuuint64_t)L.ln[2]};
+      cuuint64_t    strides[2] = {(cuuint64_t)L.pitch * 8, (cuuint64_t)L.plane * 8};
+      cuuint32_t    box[3]     = {(cuuint32_t)C::PIN, (cuuint32_t)C::NR, 1};
+      cuuint32_t    estr[3]    = {1, 1, 1};
+      const CUresult rc = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(src), dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      GDM_REQUIRE(rc == CUDA_SUCCESS, GDM_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)rc));
+      return plan.maps.emplace(src, m).first->second;
+    }
+  } // namespace
+
+  bool fused_supported(const Operator &op)
+  {
+    const Layout &L = op.sys->L;
+    if (L.dim != 3 || L.nc != 1)
+      return false;
+    if (!(L.p == 1 || L.p == 3 || L.p == 5))
+      return false;
+    for (int d = 0; d < 3; ++d)
+      if (op.periodic[d] || L.N[d] < 2 * L.p + 2)
+        return false;
+    if (L.own1 <= L.own0)
+      return false;
+    const char *env = std::getenv("GDM_DISABLE_FUSED");
+    if (env && env[0] == '1')
+      return false;
+    return true;
+  }
+
+  void fused_plan_create(Operator &op)
+  {
+    const Layout &L    = op.sys->L;
+    Context      &ctx  = *op.sys->ctx;
+    auto         *plan = new FusedPlan;
+    op.fused           = plan;
+    const int P = L.p, W = 2 * P + 1;
+    // output window: Dirichlet faces are written by the constrained-row kernel
+    plan->cx0 = op.dirichlet[0][0] ? 1 : 0;
+    plan->cx1 = L.nn[0] - (op.dirichlet[0][1] ? 1 : 0);
+    plan->cy0 = op.dirichlet[1][0] ? 1 : 0;
+    plan->cy1 = L.nn[1] - (op.dirichlet[1][1] ? 1 : 0);
+    int z0 = L.own0, z1 = L.own1; // global
+    if (op.dirichlet[2][0])
+      z0 = std::max(z0, 1);
+    if (op.dirichlet[2][1])
+      z1 = std::min(z1, L.nn[2] - 1);
+    plan->cz0 = z0 - L.loc0;
+    plan->cz1 = std::max(z1 - L.loc0, plan->cz0);
+    int tx = 32, ty = 32, min_blocks = 2;
+    plan->cfg = default_config(P);
+    with_config(plan->cfg, [&](auto c) {
+      using C    = decltype(c);
+      tx         = C::TX;
+      ty         = C::TY;
+      min_blocks = C::MINB;
+    });
+    // TMA box starts must be 16-byte aligned: keep (x0 - P) even by starting one column early if needed
+    plan->xorg    = plan->cx0 - ((plan->cx0 - P) & 1);
+    plan->tiles_x = (plan->cx1 - plan->xorg + tx - 1) / tx;
+    plan->tiles_y = (plan->cy1 - plan->cy0 + ty - 1) / ty;
+    const int nz    = plan->cz1 - plan->cz0;
+    const int tiles = std::max(1, plan->tiles_x * plan->tiles_y);
+    const int slots = ctx.sm_count * min_blocks;
+    // z chunking: start from "one CTA per slot"; large problems are refined by a timed search below
+    int       nch   = std::max(1, slots / tiles);
+    int       lz    = (nz + nch - 1) / std::max(nch, 1);
+    const int min_lz = 4 * P;
+    if (lz < min_lz)
+      lz = std::min(nz, min_lz);
+    bool lz_forced = false;
+    if (const char *env = std::getenv("GDM_FUSED_LZ"))
+      {
+        lz        = std::max(1, atoi(env));
+        lz_forced = true;
+      }
+    lz             = std::max(lz, 1);
+    plan->lz       = lz;
+    plan->n_chunks = (nz + lz - 1) / lz;
+    plan->tune     = !lz_forced && (int64_t)nz * (plan->cx1 - plan->cx0) * (plan->cy1 - plan->cy0) > (int64_t)(1 << 21);
+    // scatter rows: zs[k][j] = scale * T_z[k - P + j][2P - j]
+    std::vector<double> zsA((size_t)L.ln[2] * W, 0.0), zsB((size_t)L.ln[2] * W, 0.0);
+    for (int k = 0; k < L.ln[2]; ++k)
+      for (int j = 0; j < W; ++j)
+        {
+          const int r = k - P + j;
+          if (r < 0 || r >= L.ln[2])
+            continue;
+          zsA[(size_t)k * W + j] = op.desc.scale * op.hA[2][(size_t)r * W + (2 * P - j)];
+          if (op.has_B)
+            zsB[(size_t)k * W + j] = op.desc.scale * op.hB[2][(size_t)r * W + (2 * P - j)];
+        }
+    GDM_CUDA_CHECK(cudaMalloc(&plan->d_zsA, zsA.size() * sizeof(double)));
+    GDM_CUDA_CHECK(cudaMalloc(&plan->d_zsB, zsB.size() * sizeof(double)));
+    GDM_CUDA_CHECK(cudaMemcpy(plan->d_zsA, zsA.data(), zsA.size() * sizeof(double), cudaMemcpyHostToDevice));
+    GDM_CUDA_CHECK(cudaMemcpy(plan->d_zsB, zsB.data(), zsB.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+
+  void fused_plan_destroy(Operator &op)
+  {
+    delete static_cast<FusedPlan *>(op.fused);
+    op.fused = nullptr;
+  }
+
+  template <class C>
+  static void dispatch(Operator &op, FusedPlan &plan, double *dst, const double *src, bool accumulate)
+  {
+    const CUtensorMap &map = get_map<C>(op, plan, src);
+    if (!op.has_B)
+      accumulate ? launch_variant<C, false, +1, true>(op, plan, map, dst) : launch_variant<C, false, +1, false>(op, plan, map, dst);
+    else if (op.b_symmetry > 0)
+      accumulate ? launch_variant<C, true, +1, true>(op, plan, map, dst) : launch_variant<C, true, +1, false>(op, plan, map, dst);
+    else
+      accumulate ? launch_variant<C, true, -1, true>(op, plan, map, dst) : launch_variant<C, true, -1, false>(op, plan, map, dst);
+  }
+
+  void fused_apply(Operator &op, double *dst, const double *src, bool accumulate)
+  {
+    FusedPlan    &plan = *static_cast<FusedPlan *>(op.fused);
+    Context      &ctx  = *op.sys->ctx;
+    const Layout &L    = op.sys->L;
+    if (plan.tune)
+      {
+        // FFTW-style plan refinement: time a few chunk counts around one/two/three CTAs per slot on
+        // scratch output (same input), keep the fastest.  Runs once per operator.
+        plan.tune = false;
+        ctx.ensure_scratch((size_t)L.size);
+        double     *tmp = ctx.scratch[0];
+        const int   nz  = plan.cz1 - plan.cz0;
+        const int   P   = L.p;
+        int         mb  = 2;
+        with_config(plan.cfg, [&](auto c) { mb = decltype(c)::MINB; });
+        const int    tiles = std::max(1, plan.tiles_x * plan.tiles_y);
+        const double base  = (double)ctx.sm_count * mb / tiles;
+        cudaEvent_t  e0, e1;
+        GDM_CUDA_CHECK(cudaEventCreate(&e0));
+        GDM_CUDA_CHECK(cudaEventCreate(&e1));
+        int   best_lz = plan.lz;
+        float best_ms = 1e30f;
+        int   last_nch = -1;
+        for (double f : {1.0, 1.25, 1.5, 1.75, 2.0, 2.5, 3.0, 4.0})
+          {
+            const int nch = std::max(1, (int)(base * f));
+            int       lz  = std::max((nz + nch - 1) / nch, std::min(nz, 2 * P + 2));
+            const int n   = (nz + lz - 1) / lz;
+            if (n == last_nch)
+              continue;
+            last_nch      = n;
+            plan.lz       = lz;
+            plan.n_chunks = n;
+            float ms = 1e30f;
+            for (int rep = 0; rep < 3; ++rep)
+              {
+                GDM_CUDA_CHECK(cudaEventRecord(e0, ctx.stream));
+                with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, tmp, src, false); });
+                GDM_CUDA_CHECK(cudaEventRecord(e1, ctx.stream));
+                GDM_CUDA_CHECK(cudaEventSynchronize(e1));
+                float t;
+                GDM_CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
+                if (rep > 0)
+                  ms = std::min(ms, t);
+              }
+            if (ms < best_ms)
+              {
+                best_ms = ms;
+                best_lz = lz;
+              }
+          }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        plan.lz       = best_lz;
+        plan.n_chunks = (nz + best_lz - 1) / best_lz;
+        if (std::getenv("GDM_FUSED_VERBOSE"))
+          fprintf(stderr, "[gdm] fused plan: cfg %d, tiles %d x %d, lz %d (%d chunks), %.3f ms\n", plan.cfg, plan.tiles_x,
+                  plan.tiles_y, plan.lz, plan.n_chunks, best_ms);
+      }
+    with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
+    // Dirichlet faces (skipped by the tiles) and deal.II's constrained diagonal
+    launch_constrained_rows(ctx, L, op, dst, src, accumulate);
+  }
 } // namespace gdm

@@ -20,7 +20,7 @@ restatement validated in 1D/2D.
 from .basis import (lagrange_nodes, lagrange_coefficients, generate_polynomials_1D,
                     basis_values, gauss_legendre_01)
 from .system import System, Constraints
-from .assemble import (assemble_cell_loop, kron_operator, matrices_1d,
+from .assemble import (assemble_cell_loop, kron_operator, kron_unconstrained, matrices_1d,
                        rhs_cell_loop, advection_residual_cell_loop)
 from .solvers import (ReductionControl, SolverControlNoConvergence, solver_cg,
                       PreconditionIdentity, PreconditionJacobi, DiagonalMatrix,

@@ -1,0 +1,149 @@
+"""GPU parity: operator application through the C ABI vs the oracle (tolerance: relative 1e-12
+of max|y_ref| on a single apply, as BASELINE.json's north_star states)."""
+import numpy as np
+import pytest
+
+from helpers import make_pair, make_operator, oracle_operator, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+CASES = [
+    # dim, p, nc, reps, bc
+    (1, 1, 1, [7], "dirichlet"),
+    (1, 3, 1, [10], "dirichlet"),
+    (1, 5, 1, [13], "periodic"),
+    (1, 9, 1, [21], "none"),
+    (2, 3, 1, [20, 20], "dirichlet"),
+    (2, 3, 2, [9, 7], "none"),
+    (2, 5, 1, [12, 15], "periodic"),
+    (2, 7, 1, [16, 15], "mixed"),
+    (3, 1, 1, [5, 4, 3], "dirichlet"),
+    (3, 3, 1, [17, 9, 12], "dirichlet"),
+    (3, 3, 1, [9, 8, 7], "periodic"),
+    (3, 3, 2, [7, 8, 9], "left"),
+    (3, 5, 1, [11, 12, 13], "mixed"),
+    (3, 5, 1, [12, 11, 13], "none"),
+]
+
+
+@pytest.mark.parametrize("dim,p,nc,reps,bc", CASES)
+@pytest.mark.parametrize("kind", ["mass", "stiffness", "advection", "advection_t"])
+def test_generic_apply_matches_oracle(lib, dim, p, nc, reps, bc, kind):
+    import gdm_b200 as g
+    gs, gc, os_, oc = make_pair(dim, p, nc, reps, bc)
+    b = [1.0, 0.15, -0.05][:dim]
+    scale = -1.0 if kind == "advection" else 1.0
+    A = make_operator(gs, gc, kind, b=b, kernel=g.capi.KERNEL_GENERIC, scale=scale)
+    Ao = oracle_operator(os_, oc, kind, b=b, scale=scale)
+    rng = np.random.default_rng(0)
+    xh = rng.uniform(-1, 1, gs.n_dofs())
+    x, y = g.Vector(gs, xh), g.Vector(gs)
+    A.vmult(y, x)
+    ref = Ao @ xh
+    assert rel_err(y.numpy(), ref) <= TOL
+    # vmult_add and linearity
+    y2 = g.Vector(gs, xh)
+    A.vmult_add(y2, x)
+    assert rel_err(y2.numpy(), ref + xh) <= TOL
+    # host-buffer entry point
+    yh = np.zeros_like(xh)
+    A.vmult_host(yh, xh)
+    assert rel_err(yh, ref) <= TOL
+
+
+@pytest.mark.parametrize("dim,p,nc,reps,bc", [c for c in CASES if c[0] >= 2][:6])
+def test_diagonal_and_jacobi(lib, dim, p, nc, reps, bc):
+    import gdm_b200 as g
+    gs, gc, os_, oc = make_pair(dim, p, nc, reps, bc)
+    for kind in ("mass", "stiffness"):
+        A = make_operator(gs, gc, kind, kernel=g.capi.KERNEL_GENERIC)
+        Ao = oracle_operator(os_, oc, kind)
+        d = A.diagonal().numpy()
+        assert rel_err(d, Ao.diagonal()) <= TOL
+
+
+def test_constraints_distribute_and_set_zero(lib):
+    import gdm_b200 as g
+    gs, gc, os_, oc = make_pair(3, 3, 2, [6, 7, 8], "mixed")
+    rng = np.random.default_rng(1)
+    xh = rng.uniform(-1, 1, gs.n_dofs())
+    v = g.Vector(gs, xh)
+    gc.distribute(v)
+    assert np.array_equal(v.numpy(), oc.distribute(xh.copy()))
+    v = g.Vector(gs, xh)
+    gc.set_zero(v)
+    assert np.array_equal(v.numpy(), oc.set_zero(xh.copy()))
+    assert gc.n_constraints() == len(oc.lines)
+
+
+def test_vector_operations(lib):
+    import gdm_b200 as g
+    gs, gc, os_, oc = make_pair(3, 3, 1, [9, 10, 11], "none")
+    rng = np.random.default_rng(2)
+    a, b = rng.uniform(-1, 1, gs.n_dofs()), rng.uniform(-1, 1, gs.n_dofs())
+    va, vb = g.Vector(gs, a), g.Vector(gs, b)
+    assert abs(va * vb - a @ b) <= 1e-13 * abs(a @ b) + 1e-13
+    assert abs(va.l2_norm() - np.linalg.norm(a)) <= 1e-13 * np.linalg.norm(a)
+    assert va.linfty_norm() == np.abs(a).max()
+    va.add(0.5, vb)
+    assert np.allclose(va.numpy(), a + 0.5 * b, rtol=0, atol=1e-15)
+    va.sadd(2.0, -1.0, vb)
+    assert np.allclose(va.numpy(), 2 * (a + 0.5 * b) - b, rtol=0, atol=1e-15)
+    va.scale(3.0)
+    va.scale(vb)
+    assert np.allclose(va.numpy(), 3 * (2 * (a + 0.5 * b) - b) * b, rtol=0, atol=1e-14)
+    vc = va.copy()
+    assert np.array_equal(vc.numpy(), va.numpy())
+    vc.set(1.5)
+    assert np.array_equal(vc.numpy(), np.full(gs.n_dofs(), 1.5))
+    assert abs(vc.l2_norm() - 1.5 * np.sqrt(gs.n_dofs())) < 1e-10  # pads stay zero
+
+
+def test_csr_overlay_rows_replace_tensor_rows(lib):
+    """Irregular rows (cut cells / ghost penalty) as CSR rows that replace the regular result."""
+    import gdm_b200 as g
+    gs, gc, os_, oc = make_pair(2, 3, 1, [10, 9], "dirichlet")
+    A = make_operator(gs, gc, "stiffness", kernel=g.capi.KERNEL_GENERIC)
+    Ao = oracle_operator(os_, oc, "stiffness").tolil()
+    rng = np.random.default_rng(3)
+    n = gs.n_dofs()
+    rows = np.sort(rng.choice(n, 17, replace=False))
+    rowptr, col, val = [0], [], []
+    for r in rows:
+        cols = np.sort(rng.choice(n, 23, replace=False))
+        vals = rng.uniform(-1, 1, 23)
+        Ao[r, :] = 0.0
+        for c, v in zip(cols, vals):
+            Ao[r, c] = v
+        col += list(cols)
+        val += list(vals)
+        rowptr.append(len(col))
+    A.attach_csr(rows, rowptr, col, val)
+    xh = rng.uniform(-1, 1, n)
+    x, y = g.Vector(gs, xh), g.Vector(gs)
+    A.vmult(y, x)
+    ref = Ao.tocsr() @ xh
+    assert rel_err(y.numpy(), ref) <= TOL
+    y2 = g.Vector(gs, xh)
+    A.vmult_add(y2, x)
+    assert rel_err(y2.numpy(), ref + xh) <= TOL
+
+
+def test_lumped_mass(lib):
+    import gdm_b200 as g
+    import oracle as O
+    gs, gc, os_, oc = make_pair(2, 3, 1, [8, 9], "periodic")
+    inv = g.Vector(gs)
+    g.MatrixCreator.create_lumped_mass_matrix(g.MappingQ1(), gs, g.QGauss(4), inv, gc)
+    M = O.kron_unconstrained(os_, "mass")
+    rows = np.asarray(M.sum(axis=1)).ravel()
+    lumped = np.zeros_like(rows)
+    for i in range(len(rows)):  # distribute_local_to_global on a vector
+        if oc.is_constrained(i):
+            for (j, w) in oc.lines[i][0]:
+                lumped[j] += w * rows[i]
+        else:
+            lumped[i] += rows[i]
+    ref = np.where(lumped != 0, 1.0 / np.where(lumped != 0, lumped, 1.0), 0.0)
+    assert rel_err(inv.numpy(), ref) <= TOL

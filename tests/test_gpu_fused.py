@@ -1,0 +1,97 @@
+"""GPU parity of the fused sm_100a tensor-product kernel (dim 3): vs the oracle at small sizes,
+vs the generic multi-pass kernels and through size-independent properties at BASELINE size."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import make_pair, make_operator, oracle_operator, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+FUSED_CASES = [
+    # p, reps (cells), bc
+    (3, [35, 47, 20], "dirichlet"),
+    (3, [33, 43, 9], "none"),
+    (3, [40, 12, 17], "left"),
+    (1, [37, 35, 11], "dirichlet"),
+    (1, [5, 4, 6], "none"),
+    (5, [35, 29, 14], "dirichlet"),
+    (5, [13, 12, 27], "none"),
+    (3, [8, 8, 8], "dirichlet"),
+]
+
+
+@pytest.mark.parametrize("p,reps,bc", FUSED_CASES)
+@pytest.mark.parametrize("kind", ["mass", "stiffness", "advection", "advection_t"])
+@pytest.mark.parametrize("lz", [None, 8])
+def test_fused_apply_matches_oracle(lib, monkeypatch, p, reps, bc, kind, lz):
+    import gdm_b200 as g
+    if lz is not None:
+        monkeypatch.setenv("GDM_FUSED_LZ", str(lz))
+    else:
+        monkeypatch.delenv("GDM_FUSED_LZ", raising=False)
+    gs, gc, os_, oc = make_pair(3, p, 1, reps, bc)
+    b = [1.0, 0.15, -0.05]
+    scale = -0.5 if kind == "advection" else 1.0
+    A = make_operator(gs, gc, kind, b=b, kernel=g.capi.KERNEL_FUSED, scale=scale)
+    assert A.kernel_used() == g.capi.KERNEL_FUSED
+    Ao = oracle_operator(os_, oc, kind, b=b, scale=scale)
+    rng = np.random.default_rng(0)
+    xh = rng.uniform(-1, 1, gs.n_dofs())
+    x, y = g.Vector(gs, xh), g.Vector(gs)
+    y.set(7.0)  # stale values must be overwritten everywhere
+    A.vmult(y, x)
+    ref = Ao @ xh
+    assert rel_err(y.numpy(), ref) <= TOL
+    y2 = g.Vector(gs, xh)
+    A.vmult_add(y2, x)
+    assert rel_err(y2.numpy(), ref + xh) <= TOL
+    # pads of the padded layout stay zero: the l2 norm over the storage equals the norm of the DoFs
+    assert abs(y.l2_norm() - np.linalg.norm(ref)) <= 1e-11 * np.linalg.norm(ref)
+
+
+def test_auto_picks_fused_and_falls_back(lib):
+    import gdm_b200 as g
+    gs, gc, _, _ = make_pair(3, 3, 1, [12, 12, 12], "dirichlet")
+    assert make_operator(gs, gc, "stiffness").kernel_used() == g.capi.KERNEL_FUSED
+    gs, gc, _, _ = make_pair(3, 3, 1, [12, 12, 12], "periodic")
+    assert make_operator(gs, gc, "stiffness").kernel_used() == g.capi.KERNEL_GENERIC
+    with pytest.raises(g.ExcNotImplemented):
+        make_operator(gs, gc, "stiffness", kernel=g.capi.KERNEL_FUSED)
+    gs, gc, _, _ = make_pair(2, 3, 1, [12, 12], "dirichlet")
+    assert make_operator(gs, gc, "stiffness").kernel_used() == g.capi.KERNEL_GENERIC
+
+
+@pytest.mark.parametrize("p,n", [(3, 256), (5, 128)])
+def test_full_size_properties(lib, p, n):
+    """BASELINE.json config 2 size (256^3 cells, p=3): fused == generic, symmetry, null space, volume."""
+    import gdm_b200 as g
+    gs, gc, _, _ = make_pair(3, p, 1, [n, n, n], "dirichlet", hi=[1.0, 1.0, 1.0])
+    rng = np.random.default_rng(0)
+    nd = gs.n_dofs()
+    xh = rng.uniform(-1, 1, nd)
+    x, y, yg, z, w = g.Vector(gs, xh), g.Vector(gs), g.Vector(gs), g.Vector(gs, rng.uniform(-1, 1, nd)), g.Vector(gs)
+    for kind in ("stiffness", "mass"):
+        Af = make_operator(gs, gc, kind, kernel=g.capi.KERNEL_FUSED)
+        Ag = make_operator(gs, gc, kind, kernel=g.capi.KERNEL_GENERIC)
+        Af.vmult(y, x)
+        Ag.vmult(yg, x)
+        ref = yg.numpy()
+        assert rel_err(y.numpy(), ref) <= TOL
+        # symmetry: <z, A x> == <x, A z>
+        Af.vmult(w, z)
+        s1, s2 = z * y, x * w
+        assert abs(s1 - s2) <= 1e-11 * max(abs(s1), abs(s2), 1.0)
+    # unconstrained operators: constants are in the null space of K; 1^T M 1 = |Omega|
+    gs2, gc2, _, _ = make_pair(3, p, 1, [n, n, n], "none", hi=[1.0, 1.0, 1.0])
+    one, out = g.Vector(gs2), g.Vector(gs2)
+    one.set(1.0)
+    K = make_operator(gs2, gc2, "stiffness", kernel=g.capi.KERNEL_FUSED)
+    K.vmult(out, one)
+    kd = K.diagonal()
+    assert out.linfty_norm() <= 1e-12 * kd.linfty_norm() * 50
+    M = make_operator(gs2, gc2, "mass", kernel=g.capi.KERNEL_FUSED)
+    M.vmult(out, one)
+    assert abs(one * out - 1.0) <= 1e-12

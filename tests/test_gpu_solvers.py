@@ -1,0 +1,169 @@
+"""GPU parity: CG and Runge-Kutta through the C ABI vs the reference's goldens and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from helpers import make_pair, make_operator, oracle_operator, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden(golden_dir, name):
+    return open(os.path.join(golden_dir, name)).read()
+
+
+@pytest.mark.parametrize("p", [1, 3, 5, 7, 9])
+def test_poisson_01_gdm(lib, golden_dir, p):
+    """tests/poisson_01_gdm.cc: 1D, N=10, plain CG(100,1e-10,1e-4): count, values, L2 error."""
+    import gdm_b200 as g
+    tok = _golden(golden_dir, "poisson_01_gdm.output").split()
+    pos = 14 * [1, 3, 5, 7, 9].index(p)
+    gs, gc, os_, oc = make_pair(1, p, 1, [10], "dirichlet", hi=[1.0])
+    A = make_operator(gs, gc, "stiffness")
+    rhs = g.Vector(gs, O.rhs_cell_loop(os_, oc, lambda pts, c: 1.0))
+    sol = g.Vector(gs)
+    ctl = g.ReductionControl(100, 1e-10, 1e-4)
+    g.SolverCG(ctl).solve(A, sol, rhs, g.PreconditionIdentity())
+    assert ctl.last_step() == int(tok[pos]) == 5
+    vals = sol.numpy()
+    gold = np.array([float(t) for t in tok[pos + 1:pos + 12]])
+    assert np.allclose([float("%g" % v) for v in vals], gold, atol=1e-12)
+    exact = lambda pt, c: 0.125 - 0.5 * (pt[0] - 0.5) ** 2
+    cell = g.VectorTools.integrate_difference(g.MappingQ1(), gs, sol, exact, None, g.QGauss(p + 1), "L2_norm")
+    err = g.VectorTools.compute_global_error(None, cell)
+    assert "%14.8f" % err == "%14.8f" % float(tok[pos + 13])
+
+
+@pytest.mark.parametrize("dim", [1, 2])
+def test_poisson_02_gdm_values(lib, golden_dir, dim):
+    """tests/poisson_02_gdm.cc solution values (golden printed with 6 significant digits)."""
+    import gdm_b200 as g
+    tok = _golden(golden_dir, "poisson_02_gdm.mpirun=1.output").split()
+    gold = np.array([float(t) for t in (tok[1:22] if dim == 1 else tok[23:23 + 441])])
+    gs, gc, os_, oc = make_pair(dim, 3, 1, [20] * dim, "dirichlet", hi=[1.0] * dim)
+    A = make_operator(gs, gc, "stiffness")
+    rhs = g.Vector(gs, O.rhs_cell_loop(os_, oc, lambda pts, c: 1.0))
+    sol = g.Vector(gs)
+    ctl = g.ReductionControl(1000, 1e-14, 1e-12)
+    g.SolverCG(ctl).solve(A, sol, rhs, g.PreconditionIdentity())
+    gc.distribute(sol)
+    assert np.allclose([float("%g" % v) for v in sol.numpy()], gold, atol=1e-12)
+    # plain CG with the test's own control needs 10 (1D) / 23 (2D) iterations (oracle-pinned)
+    sol2 = g.Vector(gs)
+    ctl = g.ReductionControl(100, 1e-10, 1e-4)
+    g.SolverCG(ctl).solve(A, sol2, rhs, g.PreconditionIdentity())
+    assert ctl.last_step() == (10 if dim == 1 else 23)
+
+
+@pytest.mark.parametrize("nc,name", [(1, "mass_01_gdm.output"), (2, "mass_02_gdm.output")])
+def test_mass_0x_gdm(lib, golden_dir, nc, name):
+    """tests/mass_01_gdm.cc / mass_02_gdm.cc: Jacobi-CG L2 projection, error printed with %g."""
+    import gdm_b200 as g
+    gold = _golden(golden_dir, name).split()[1]
+    gs, gc, os_, oc = make_pair(2, 3, nc, [40, 40], "none", hi=[1.0, 1.0])
+    A = g.SparseMatrix()
+    g.MatrixCreator.create_mass_matrix(g.MappingQ1(), gs, g.QGauss(4), A, gc)
+    f = lambda pts, c: pts[:, 0] + c
+    rhs = g.Vector(gs, O.rhs_cell_loop(os_, oc, f))
+    sol = g.Vector(gs)
+    pre = g.PreconditionJacobi()
+    pre.initialize(A)
+    ctl = g.ReductionControl(100, 1e-10, 1e-8)
+    g.SolverCG(ctl).solve(A, sol, rhs, pre)
+    assert ctl.last_step() == 18
+    cell = g.VectorTools.integrate_difference(g.MappingQ1(), gs, sol, lambda pt, c: pt[0] + c, None, g.QGauss(4))
+    assert "%g" % g.VectorTools.compute_global_error(None, cell) == gold
+
+
+def test_cg_failure_is_reported(lib):
+    """deal.II throws SolverControl::NoConvergence when max_steps is hit."""
+    import gdm_b200 as g
+    gs, gc, os_, oc = make_pair(2, 3, 1, [20, 20], "dirichlet")
+    A = make_operator(gs, gc, "stiffness")
+    rhs = g.Vector(gs, O.rhs_cell_loop(os_, oc, lambda pts, c: 1.0))
+    sol = g.Vector(gs)
+    ctl = g.ReductionControl(3, 1e-30, 1e-30)
+    with pytest.raises(g.NoConvergence):
+        g.SolverCG(ctl).solve(A, sol, rhs, g.PreconditionIdentity())
+    assert ctl.last_step() == 3
+
+
+@pytest.mark.parametrize("dim,p,reps,bc,pre", [(3, 3, [12, 10, 9], "dirichlet", "identity"),
+                                               (3, 3, [12, 10, 9], "dirichlet", "jacobi"),
+                                               (2, 5, [16, 18], "periodic", "jacobi"),
+                                               (3, 5, [11, 11, 12], "left", "identity")])
+def test_cg_iteration_parity_with_oracle(lib, dim, p, reps, bc, pre):
+    """Same matrix, same rhs, same control => same iteration count and solution as deal.II's loop."""
+    import gdm_b200 as g
+    gs, gc, os_, oc = make_pair(dim, p, 1, reps, bc)
+    kind = "mass" if bc == "periodic" else "stiffness"
+    A = make_operator(gs, gc, kind)
+    Ao = oracle_operator(os_, oc, kind)
+    bh = O.rhs_cell_loop(os_, oc, lambda pts, c: np.sin(3 * pts[:, 0]) + 1.0)
+    rhs, sol = g.Vector(gs, bh), g.Vector(gs)
+    ctl = g.ReductionControl(2000, 1e-12, 1e-9)
+    octl = O.ReductionControl(2000, 1e-12, 1e-9)
+    if pre == "jacobi":
+        P, Po = g.PreconditionJacobi(), O.PreconditionJacobi(Ao)
+        P.initialize(A)
+    else:
+        P, Po = g.PreconditionIdentity(), O.PreconditionIdentity()
+    g.SolverCG(ctl).solve(A, sol, rhs, P)
+    xo = O.solver_cg(Ao, np.zeros(gs.n_dofs()), bh, Po, octl)
+    assert ctl.last_step() == octl.last_step()
+    assert abs(ctl.initial_value() - octl.initial_value()) <= 1e-13 * octl.initial_value()
+    assert rel_err(sol.numpy(), xo) <= 1e-9
+
+
+def test_advection_rk4_matches_oracle(lib):
+    """prototypes/advection_01_gdm.cc in small: periodic, p=5, RK4, Jacobi-CG mass inversion per stage."""
+    import gdm_b200 as g
+    n, p, dim = 12, 5, 2
+    b = [1.0, 0.15]
+    gs, gc, os_, oc = make_pair(dim, p, 1, [n, n], "periodic", hi=[1.0, 1.0])
+    M = g.SparseMatrix()
+    g.MatrixCreator.create_mass_matrix(g.MappingQ1(), gs, g.QGauss(p + 1), M, gc)
+    R = make_operator(gs, gc, "advection", b=b, scale=-1.0)
+    Mo = oracle_operator(os_, oc, "mass")
+    Ro = oracle_operator(os_, oc, "advection", b=b, scale=-1.0)
+    u0 = lambda pts, c: np.sin(2 * np.pi * pts[:, 0]) * np.cos(2 * np.pi * pts[:, 1])
+    uh = O.interpolate(os_, u0)
+    sol = g.Vector(gs)
+    g.VectorTools.interpolate(g.MappingQ1(), gs, lambda pt, c: np.sin(2 * np.pi * pt[0]) * np.cos(2 * np.pi * pt[1]), sol)
+    assert np.abs(sol.numpy() - uh).max() < 1e-15
+    pre = g.PreconditionJacobi()
+    pre.initialize(M)
+    tmp0, tmp1 = g.Vector(gs), g.Vector(gs)
+    iters = []
+
+    def f(t, y, out):
+        tmp0.equ(y)
+        gc.distribute(tmp0)
+        R.vmult(tmp1, tmp0)
+        out.set(0.0)
+        ctl = g.ReductionControl(100, 1e-10, 1e-8)
+        g.SolverCG(ctl).solve(M, out, tmp1, pre)
+        iters.append(ctl.last_step())
+
+    oiters = []
+
+    def fo(t, y):
+        v0 = oc.distribute(y.copy())
+        ctl = O.ReductionControl(100, 1e-10, 1e-8)
+        out = O.solver_cg(Mo, np.zeros_like(y), Ro @ v0, O.PreconditionJacobi(Mo), ctl)
+        oiters.append(ctl.last_step())
+        return out
+
+    rk, rko = g.TimeStepping.ExplicitRungeKutta(g.TimeStepping.RK_CLASSIC_FOURTH_ORDER), O.ExplicitRungeKutta4()
+    time, dt = g.DiscreteTime(0.0, 0.1, 0.5 / n), 0.5 / n
+    uo, t = uh.copy(), 0.0
+    while not time.is_at_end():
+        rk.evolve_one_time_step(f, time.get_current_time(), time.get_next_step_size(), sol)
+        gc.distribute(sol)
+        t, uo = rko.evolve_one_time_step(fo, t, time.get_next_step_size(), uo)
+        oc.distribute(uo)
+        time.advance_time()
+    assert iters == oiters
+    assert rel_err(sol.numpy(), uo) <= 1e-10
