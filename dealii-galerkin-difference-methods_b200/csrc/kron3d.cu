@@ -79,15 +79,22 @@ namespace gdm
       static constexpr int P = P_, TX = TX_, RY = RY_, NRB = NRB_, RX = RX_, STAGES = STAGES_, MINB = MINB_;
       static constexpr int W       = 2 * P + 1;
       static constexpr int TY      = RY * NRB;
-      static constexpr int NR      = TY + 2 * P;            // rows of the staged tile
-      static constexpr int PIN     = TX + 2 * P;            // pitch of the staged tile (dense TMA box)
-      static constexpr int PAB     = TX + 2;                // pitch of the a/b fields
+      static constexpr int NR      = TY + 2 * P;                         // rows of the staged tile
+      static constexpr int PIN     = TX + 2 * P;                         // pitch of the staged tile (dense TMA box)
+      static constexpr int PY      = ((NR / 2) & 1) ? NR : NR + 2;       // column pitch of the transposed a/b fields
       static constexpr int THREADS = TX * NRB;
+      static constexpr int NWARPS  = THREADS / 32;
       static constexpr int NXB     = TX / RX;
       static constexpr int NTASK   = NXB * NR;
-      static_assert(TX % 32 == 0 && TX % RX == 0 && RX % 2 == 0, "tile shape");
-      static_assert(((PIN / 2) & 1) == 1 && ((PAB / 2) & 1) == 1, "16-byte pitches must be odd for conflict-free LDS.128");
-      static constexpr int STAGE_DOUBLES = (NR * PIN + 15) / 16 * 16; // stage stride, 128-byte aligned for TMA
+      static constexpr int NAB     = 3;                                  // a/b buffers in flight (split barrier)
+      // x pass work split: block tasks (RX outputs) on rows [0, NRM), single outputs on rows [NRM, NR)
+      static constexpr int NRM     = (NTASK <= THREADS) ? NR : (THREADS / NXB);
+      static constexpr int NREM    = (NR - NRM) * TX;                    // single-output tasks
+      static constexpr int NBT     = 2 * (P + 1);                        // boundary (non-Toeplitz) rows per direction
+      static constexpr int TB_DOUBLES = 2 * 2 * NBT * 8 * ((2 * P + 1 + 7) / 8); // [dir][field][row][taps padded]
+      static_assert(TX % 32 == 0 && TX % RX == 0 && RX % 2 == 0 && NR % 2 == 0, "tile shape");
+      static_assert(((PIN / 2) & 1) == 1 && ((PY / 2) & 1) == 1, "16-byte pitches must be odd for conflict-free LDS.128");
+      static constexpr int STAGE_DOUBLES = (NR * PIN + 15) / 16 * 16;    // stage stride, 128-byte aligned for TMA
     };
 
     template <int P>
@@ -100,32 +107,72 @@ namespace gdm
       int           nx, ny;                       // cells per direction (boundary rows: <= P or >= N-P)
       int           tiles_x, tiles_y, lz;
       int           nz_local;
-      int           accumulate;
-      int           dbg; // ablation switches for profiling (GDM_FUSED_DBG): 1 no stores, 2 no TMA, 4 no x pass, 8 no y/z pass
+      int           kz_lo, kz_hi;                 // input planes [kz_lo, kz_hi) only touch Toeplitz z rows
+      int           dbg;                          // profiling ablations (GDM_FUSED_DBG): 1 no stores, 4 no x pass, 8 no y/z pass, 16 no phase barrier, 32 TMA wait by warp 0 only
       const double *tabAx, *tabBx, *tabAy, *tabBy; // row tables [node][2P+1]
       const double *zsA, *zsB;                     // scatter rows [plane][2P+1], scale folded in
       double        Ax[P + 1], Bx[P + 1], Ay[P + 1], By[P + 1]; // interior taps by distance
+      double        Az[2 * P + 1], Bz[2 * P + 1];               // interior scatter row, scale folded in
     };
 
     template <class C, bool HASB>
     constexpr size_t smem_bytes()
     {
-      return (size_t)(C::STAGES * C::STAGE_DOUBLES + 2 * (HASB ? 2 : 1) * C::NR * C::PAB + 2 * 2 * 16) * sizeof(double) +
-             C::STAGES * sizeof(uint64_t) + 128;
+      return (size_t)(C::STAGES * C::STAGE_DOUBLES + C::NAB * (HASB ? 2 : 1) * C::TX * C::PY + C::NAB * 2 * 16 + C::TB_DOUBLES) * sizeof(double) +
+             (C::STAGES + 1) * sizeof(uint64_t) + 128;
+    }
+
+    __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+    {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    }
+
+    // z pass (scatter form): y_r += A_z[r][k] u2 + B_z[r][k] u1 for the 2P+1 rows r around input plane k;
+    // the accumulators shift by one plane through the FMAs themselves.
+    template <int P, int RY, bool HASB>
+    __device__ __forceinline__ void z_pass(const double (&zA)[2 * P + 1], const double (&zB)[2 * P + 1], const double (&u1)[RY],
+                                           const double (&u2)[RY], double (&acc)[RY][2 * P], double (&res)[RY])
+    {
+#pragma unroll
+      for (int i = 0; i < RY; ++i)
+        {
+          const double u = HASB ? u2[i] : u1[i];
+          double       t = fma(zA[0], u, acc[i][0]);
+          if (HASB)
+            t = fma(zB[0], u1[i], t);
+          res[i] = t;
+#pragma unroll
+          for (int j = 1; j < 2 * P; ++j)
+            {
+              double s = fma(zA[j], u, acc[i][j]);
+              if (HASB)
+                s = fma(zB[j], u1[i], s);
+              acc[i][j - 1] = s;
+            }
+          double s = zA[2 * P] * u;
+          if (HASB)
+            s = fma(zB[2 * P], u1[i], s);
+          acc[i][2 * P - 1] = s;
+        }
     }
 
     // ------------------------------------------------------------------ the kernel
     template <class C, bool HASB, int BSYM, bool ACCUM>
     __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_kernel(const __grid_constant__ CUtensorMap tmap, const KArgs<C::P> g)
     {
-      constexpr int P = C::P, W = C::W, TX = C::TX, RY = C::RY, RX = C::RX, NR = C::NR, PIN = C::PIN, PAB = C::PAB;
-      constexpr int NF = HASB ? 2 : 1;
+      constexpr int P = C::P, W = C::W, TX = C::TX, RY = C::RY, RX = C::RX, NR = C::NR, PIN = C::PIN, PY = C::PY;
+      constexpr int NF = HASB ? 2 : 1, NAB = C::NAB;
       // dynamic shared memory, addressed through the typed array so that the compiler emits LDS/STS
       extern __shared__ __align__(128) double smem[];
-      constexpr int OFF_AB  = C::STAGES * C::STAGE_DOUBLES; // [2][NF][NR][PAB]
-      constexpr int OFF_ZT  = OFF_AB + 2 * NF * NR * PAB;   // [2][2][16]
-      constexpr int OFF_BAR = OFF_ZT + 2 * 2 * 16;          // [STAGES] mbarriers
+      constexpr int AB_BUF  = NF * TX * PY;                 // one a/b buffer: [field][x][PY] (y contiguous)
+      constexpr int OFF_AB  = C::STAGES * C::STAGE_DOUBLES;
+      constexpr int OFF_ZT  = OFF_AB + NAB * AB_BUF;        // [NAB][2][16]
+      constexpr int OFF_TB  = OFF_ZT + NAB * 2 * 16;        // boundary-row coefficient tables [dir][field][row class][WP]
+      constexpr int WP      = 8 * ((W + 7) / 8);            // padded taps per row
+      constexpr int NBT     = C::NBT;
+      constexpr int OFF_BAR = OFF_TB + C::TB_DOUBLES;       // [STAGES] TMA barriers + 1 phase barrier
       uint64_t     *bars    = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+      uint64_t     *xbar    = bars + C::STAGES;             // "x pass of plane k done by every warp"
 
       const int tid = threadIdx.x;
       int       b   = blockIdx.x;
@@ -147,10 +194,20 @@ namespace gdm
         {
           for (int s = 0; s < C::STAGES; ++s)
             mbar_init(&bars[s], 1);
+          mbar_init(xbar, C::NWARPS);
           mbar_fence_init();
         }
+      // the 2(P+1) one-sided rows of A/B in x and y (row class c: node c for c <= P, node N-P+(c-P-1) above)
+      for (int e = tid; e < 2 * 2 * NBT * W; e += C::THREADS)
+        {
+          const int t = e % W, c = (e / W) % NBT, f = (e / (W * NBT)) % 2, d = e / (W * NBT * 2);
+          const int n    = d ? g.ny : g.nx;
+          const int node = (c <= P) ? c : n - P + (c - P - 1);
+          const double *tab = d ? (f ? g.tabBy : g.tabAy) : (f ? g.tabBx : g.tabAx);
+          smem[OFF_TB + ((d * 2 + f) * NBT + c) * WP + t] = (HASB || f == 0) ? __ldg(tab + node * W + t) : 0.0;
+        }
       __syncthreads();
-      if (tid == 0 && !(g.dbg & 2))
+      if (tid == 0)
         for (int s = 0; s < C::STAGES; ++s)
           if (kbeg + s < kend)
             {
@@ -164,7 +221,9 @@ namespace gdm
       const int  gy_first  = y0 + rb * RY;
       const bool yz_active = (lx < ncols) && (x0 + lx >= g.cx0) && (rb * RY < nrows);
       const bool y_bnd     = (gy_first <= P) || (gy_first + RY - 1 >= g.ny - P);
-      // x pass ownership (one or more tasks per thread): lanes -> rows
+      // output plane pointer; advanced by one plane at the top of every iteration (first target: kbeg - P)
+      double    *out       = g.dst + (int64_t)(kbeg - P - 1) * g.plane + (int64_t)gy_first * g.pitch + (x0 + lx);
+
       double acc[RY][2 * P];
 #pragma unroll
       for (int i = 0; i < RY; ++i)
@@ -172,133 +231,236 @@ namespace gdm
         for (int j = 0; j < 2 * P; ++j)
           acc[i][j] = 0.0;
 
-      // per-plane z coefficients (uniform), fetched one plane ahead: ZT[buf][field][j]
+      // per-plane z coefficients for the non-Toeplitz planes, fetched one plane ahead: ZT[it % NAB][field][j]
       const int     zj = tid % W, zf = (tid / W) & 1;
       const double *zsrc = (zf ? g.zsB : g.zsA) + zj;
       double        znext = 0.0;
       if (tid < 2 * W && kbeg >= 0 && kbeg < g.nz_local)
         znext = __ldg(zsrc + (int64_t)kbeg * W);
 
-      int stage = 0, parity = 0, buf = 0;
-      for (int k = kbeg; k < kend; ++k)
-        {
-          if (tid < 2 * W)
-            {
-              smem[OFF_ZT + (buf * 2 + zf) * 16 + zj] = znext;
-              znext = (k + 1 >= 0 && k + 1 < g.nz_local) ? __ldg(zsrc + (int64_t)(k + 1) * W) : 0.0;
-            }
-          if (!(g.dbg & 2))
-            mbar_wait(&bars[stage], parity);
-
-          // ------------------------------------------------------------ x pass
+      // x pass of one plane: staged tile `stage` -> a/b buffer `ab`
+      auto x_pass = [&](int stage, int ab) {
+        const int in_off = stage * C::STAGE_DOUBLES;
+        const int a_off  = OFF_AB + ab * AB_BUF;
+        const int b_off  = a_off + (NF - 1) * TX * PY;
+        for (int task = tid; task < C::NXB * C::NRM; task += C::THREADS)
           {
-            const int in_off = stage * C::STAGE_DOUBLES;
-            const int a_off  = OFF_AB + (buf * NF + 0) * NR * PAB;
-            const int b_off  = OFF_AB + (buf * NF + (NF - 1)) * NR * PAB;
-            for (int task = tid; task < C::NTASK && !(g.dbg & 4); task += C::THREADS)
-              {
-                const int r  = task % NR;
-                const int xb = task / NR;
-                if (r >= nr_need || xb * RX >= ncols)
-                  continue;
-                double v[RX + 2 * P];
-                {
-                  const double2 *src = reinterpret_cast<const double2 *>(smem + in_off + r * PIN + xb * RX);
+            const int r  = task % C::NRM;
+            const int xb = task / C::NRM;
+            if (r >= nr_need || xb * RX >= ncols)
+              continue;
+            double v[RX + 2 * P];
+            {
+              const double2 *src = reinterpret_cast<const double2 *>(smem + in_off + r * PIN + xb * RX);
 #pragma unroll
-                  for (int q = 0; q < (RX + 2 * P) / 2; ++q)
-                    {
-                      const double2 t = src[q];
-                      v[2 * q]        = t.x;
-                      v[2 * q + 1]    = t.y;
-                    }
+              for (int q = 0; q < (RX + 2 * P) / 2; ++q)
+                {
+                  const double2 t = src[q];
+                  v[2 * q]        = t.x;
+                  v[2 * q + 1]    = t.y;
                 }
-                double a[RX], bb[RX];
+            }
+            double a[RX], bb[RX];
+#pragma unroll
+            for (int j = 0; j < RX; ++j)
+              {
+                const int c   = j + P;
+                double    ra  = g.Ax[0] * v[c];
+                double    rbv = (HASB && BSYM > 0) ? g.Bx[0] * v[c] : 0.0;
+#pragma unroll
+                for (int d = 1; d <= P; ++d)
+                  {
+                    const double s = v[c - d] + v[c + d];
+                    ra             = fma(g.Ax[d], s, ra);
+                    if (HASB)
+                      {
+                        if (BSYM > 0)
+                          rbv = fma(g.Bx[d], s, rbv);
+                        else
+                          rbv = fma(g.Bx[d], v[c + d] - v[c - d], rbv);
+                      }
+                  }
+                a[j]  = ra;
+                bb[j] = rbv;
+              }
+            const int gx_first = x0 + xb * RX;
+            if (gx_first <= P || gx_first + RX - 1 >= g.nx - P)
+              {
 #pragma unroll
                 for (int j = 0; j < RX; ++j)
                   {
-                    const int c   = j + P;
-                    double    ra  = g.Ax[0] * v[c];
-                    double    rbv = (HASB && BSYM > 0) ? g.Bx[0] * v[c] : 0.0;
+                    const int gx = gx_first + j;
+                    if ((gx <= P || gx >= g.nx - P) && gx >= 0 && gx <= g.nx)
+                      {
+                        const int     rc = (gx <= P) ? gx : gx - (g.nx - P) + P + 1;
+                        const double *ta = smem + OFF_TB + (0 * NBT + rc) * WP;
+                        const double *tb = smem + OFF_TB + (1 * NBT + rc) * WP;
+                        double        ra = 0.0, rbv = 0.0;
+#pragma unroll
+                        for (int t = 0; t < W; ++t)
+                          {
+                            ra = fma(ta[t], v[j + t], ra);
+                            if (HASB)
+                              rbv = fma(tb[t], v[j + t], rbv);
+                          }
+                        a[j]  = ra;
+                        bb[j] = rbv;
+                      }
+                  }
+              }
+            // transposed store: [x][row], consecutive lanes -> consecutive rows
+#pragma unroll
+            for (int j = 0; j < RX; ++j)
+              {
+                smem[a_off + (xb * RX + j) * PY + r] = a[j];
+                if (HASB)
+                  smem[b_off + (xb * RX + j) * PY + r] = bb[j];
+              }
+          }
+        // remainder rows: one output per task, spread evenly over all warps (keeps the warps in step)
+        if constexpr (C::NREM > 0)
+          {
+            constexpr int PER_WARP = (C::NREM + C::NWARPS - 1) / C::NWARPS;
+            for (int l = (tid & 31); l < PER_WARP; l += 32)
+              {
+                const int o = (tid >> 5) * PER_WARP + l;
+                const int r = C::NRM + o / TX, x = o % TX;
+                if (o >= C::NREM || r >= nr_need || x >= ncols)
+                  continue;
+                double v[W];
+#pragma unroll
+                for (int t = 0; t < W; ++t)
+                  v[t] = smem[in_off + r * PIN + x + t];
+                const int gx = x0 + x;
+                double    ra, rbv = 0.0;
+                if ((gx <= P || gx >= g.nx - P) && gx >= 0 && gx <= g.nx)
+                  {
+                    const int     rc = (gx <= P) ? gx : gx - (g.nx - P) + P + 1;
+                    const double *ta = smem + OFF_TB + (0 * NBT + rc) * WP;
+                    const double *tb = smem + OFF_TB + (1 * NBT + rc) * WP;
+                    ra               = 0.0;
+#pragma unroll
+                    for (int t = 0; t < W; ++t)
+                      {
+                        ra = fma(ta[t], v[t], ra);
+                        if (HASB)
+                          rbv = fma(tb[t], v[t], rbv);
+                      }
+                  }
+                else
+                  {
+                    ra = g.Ax[0] * v[P];
+                    if (HASB && BSYM > 0)
+                      rbv = g.Bx[0] * v[P];
 #pragma unroll
                     for (int d = 1; d <= P; ++d)
                       {
-                        const double s = v[c - d] + v[c + d];
+                        const double s = v[P - d] + v[P + d];
                         ra             = fma(g.Ax[d], s, ra);
                         if (HASB)
                           {
                             if (BSYM > 0)
                               rbv = fma(g.Bx[d], s, rbv);
                             else
-                              rbv = fma(g.Bx[d], v[c + d] - v[c - d], rbv);
-                          }
-                      }
-                    a[j]  = ra;
-                    bb[j] = rbv;
-                  }
-                const int gx_first = x0 + xb * RX;
-                if (gx_first <= P || gx_first + RX - 1 >= g.nx - P)
-                  {
-#pragma unroll
-                    for (int j = 0; j < RX; ++j)
-                      {
-                        const int gx = gx_first + j;
-                        if ((gx <= P || gx >= g.nx - P) && gx >= 0 && gx <= g.nx)
-                          {
-                            double ra = 0.0, rbv = 0.0;
-#pragma unroll
-                            for (int t = 0; t < W; ++t)
-                              {
-                                ra = fma(__ldg(g.tabAx + gx * W + t), v[j + t], ra);
-                                if (HASB)
-                                  rbv = fma(__ldg(g.tabBx + gx * W + t), v[j + t], rbv);
-                              }
-                            a[j]  = ra;
-                            bb[j] = rbv;
+                              rbv = fma(g.Bx[d], v[P + d] - v[P - d], rbv);
                           }
                       }
                   }
-                double2 *da = reinterpret_cast<double2 *>(smem + a_off + r * PAB + xb * RX);
-#pragma unroll
-                for (int q = 0; q < RX / 2; ++q)
-                  da[q] = make_double2(a[2 * q], a[2 * q + 1]);
+                smem[a_off + x * PY + r] = ra;
                 if (HASB)
-                  {
-                    double2 *db = reinterpret_cast<double2 *>(smem + b_off + r * PAB + xb * RX);
-#pragma unroll
-                    for (int q = 0; q < RX / 2; ++q)
-                      db[q] = make_double2(bb[2 * q], bb[2 * q + 1]);
-                  }
+                  smem[b_off + x * PY + r] = rbv;
               }
           }
-          __syncthreads();
-          // stage is free again: prefetch plane k + STAGES
-          if (tid == 0 && k + C::STAGES < kend && !(g.dbg & 2))
-            {
-              mbar_expect_tx(&bars[stage], STAGE_BYTES);
-              tma_load_3d(smem + stage * C::STAGE_DOUBLES, &tmap, &bars[stage], x0 - P, y0 - P, k + C::STAGES);
-            }
+      };
 
-          // ------------------------------------------------------------ y pass + z pass
+      // prologue: x pass of the first plane
+      int stage = 0, parity = 0; // TMA ring position of the plane whose x pass runs next
+      int xphase = 0;            // phase parity of xbar
+      int abk    = 0;            // a/b buffer of the plane consumed by the current y/z pass
+      mbar_wait(&bars[0], 0);
+      x_pass(0, 0);
+      if (tid < 2 * W)
+        {
+          smem[OFF_ZT + (0 * 2 + zf) * 16 + zj] = znext;
+          znext = (kbeg + 1 >= 0 && kbeg + 1 < g.nz_local) ? __ldg(zsrc + (int64_t)(kbeg + 1) * W) : 0.0;
+        }
+      __syncwarp();
+      if ((tid & 31) == 0)
+        mbar_arrive(xbar);
+      mbar_wait(xbar, xphase);
+      xphase ^= 1;
+      if (tid == 0 && kbeg + C::STAGES < kend)
+        {
+          mbar_expect_tx(&bars[0], STAGE_BYTES);
+          tma_load_3d(smem, &tmap, &bars[0], x0 - P, y0 - P, kbeg + C::STAGES);
+        }
+      stage = 1 % C::STAGES;
+      if (stage == 0)
+        parity ^= 1;
+
+      for (int k = kbeg; k < kend; ++k)
+        {
+          const int abn = (abk + 1 == NAB) ? 0 : abk + 1;
+          // ---- x pass of plane k+1 (its buffer was last read by the y/z pass of plane k-2)
+          if (k + 1 < kend)
+            {
+              if (!(g.dbg & 32) || tid < 32)
+                mbar_wait(&bars[stage], parity);
+              if (!(g.dbg & 4))
+                x_pass(stage, abn);
+              if (tid < 2 * W)
+                {
+                  smem[OFF_ZT + (abn * 2 + zf) * 16 + zj] = znext;
+                  znext = (k + 2 >= 0 && k + 2 < g.nz_local) ? __ldg(zsrc + (int64_t)(k + 2) * W) : 0.0;
+                }
+            }
+          __syncwarp();
+          if ((tid & 31) == 0 && !(g.dbg & 16))
+            mbar_arrive(xbar);
+
+          // ---- y pass + z pass of plane k (overlaps the other warps' x pass of plane k+1)
+          out += g.plane;
           if (yz_active && !(g.dbg & 8))
             {
-              const int a_off = OFF_AB + (buf * NF + 0) * NR * PAB + (rb * RY) * PAB + lx;
-              const int b_off = OFF_AB + (buf * NF + (NF - 1)) * NR * PAB + (rb * RY) * PAB + lx;
+              const int a_off = OFF_AB + abk * AB_BUF + lx * PY + rb * RY;
+              const int b_off = a_off + (NF - 1) * TX * PY;
               double    u1[RY], u2[RY];
               {
                 double aw[RY + 2 * P], bw[RY + 2 * P];
-#pragma unroll
-                for (int j = 0; j < RY + 2 * P; ++j)
+                if constexpr (RY % 2 == 0)
                   {
-                    aw[j] = smem[a_off + j * PAB];
-                    if (HASB)
-                      bw[j] = smem[b_off + j * PAB];
+                    const double2 *pa = reinterpret_cast<const double2 *>(smem + a_off);
+                    const double2 *pb = reinterpret_cast<const double2 *>(smem + b_off);
+#pragma unroll
+                    for (int q = 0; q < (RY + 2 * P) / 2; ++q)
+                      {
+                        const double2 t = pa[q];
+                        aw[2 * q]       = t.x;
+                        aw[2 * q + 1]   = t.y;
+                        if (HASB)
+                          {
+                            const double2 s = pb[q];
+                            bw[2 * q]       = s.x;
+                            bw[2 * q + 1]   = s.y;
+                          }
+                      }
+                  }
+                else
+                  {
+#pragma unroll
+                    for (int j = 0; j < RY + 2 * P; ++j)
+                      {
+                        aw[j] = smem[a_off + j];
+                        if (HASB)
+                          bw[j] = smem[b_off + j];
+                      }
                   }
                 if (!y_bnd)
                   {
 #pragma unroll
                     for (int i = 0; i < RY; ++i)
                       {
-                        const int c = i + P;
+                        const int c  = i + P;
                         double    t1 = g.Ay[0] * aw[c], t2 = 0.0;
                         if (HASB)
                           {
@@ -330,19 +492,50 @@ namespace gdm
 #pragma unroll
                     for (int i = 0; i < RY; ++i)
                       {
-                        const int     gy = min(gy_first + i, g.ny); // rows past the domain are never stored
-                        const double *ta = g.tabAy + gy * W;
-                        const double *tb = g.tabBy + gy * W;
-                        double        t1 = 0.0, t2 = 0.0;
-#pragma unroll
-                        for (int t = 0; t < W; ++t)
+                        const int gy = min(gy_first + i, g.ny); // rows past the domain are never stored
+                        double    t1, t2 = 0.0;
+                        if (gy <= P || gy >= g.ny - P)
                           {
-                            const double ca = __ldg(ta + t);
-                            t1              = fma(ca, aw[i + t], t1);
+                            const int     rc = (gy <= P) ? gy : gy - (g.ny - P) + P + 1;
+                            const double *ta = smem + OFF_TB + (2 * NBT + rc) * WP;
+                            const double *tb = smem + OFF_TB + (3 * NBT + rc) * WP;
+                            t1               = 0.0;
+#pragma unroll
+                            for (int t = 0; t < W; ++t)
+                              {
+                                const double ca = ta[t];
+                                t1              = fma(ca, aw[i + t], t1);
+                                if (HASB)
+                                  {
+                                    t2 = fma(ca, bw[i + t], t2);
+                                    t2 = fma(tb[t], aw[i + t], t2);
+                                  }
+                              }
+                          }
+                        else
+                          {
+                            const int c = i + P;
+                            t1          = g.Ay[0] * aw[c];
                             if (HASB)
                               {
-                                t2 = fma(ca, bw[i + t], t2);
-                                t2 = fma(__ldg(tb + t), aw[i + t], t2);
+                                t2 = g.Ay[0] * bw[c];
+                                if (BSYM > 0)
+                                  t2 = fma(g.By[0], aw[c], t2);
+                              }
+#pragma unroll
+                            for (int d = 1; d <= P; ++d)
+                              {
+                                const double sa = aw[c - d] + aw[c + d];
+                                t1              = fma(g.Ay[d], sa, t1);
+                                if (HASB)
+                                  {
+                                    const double sb = bw[c - d] + bw[c + d];
+                                    t2              = fma(g.Ay[d], sb, t2);
+                                    if (BSYM > 0)
+                                      t2 = fma(g.By[d], sa, t2);
+                                    else
+                                      t2 = fma(g.By[d], aw[c + d] - aw[c - d], t2);
+                                  }
                               }
                           }
                         u1[i] = t1;
@@ -350,40 +543,23 @@ namespace gdm
                       }
                   }
               }
-              // z pass (scatter form): y_r += A_z[r][k] u2 + B_z[r][k] u1 for the 2P+1 rows r around plane k
-              double zA[W], zB[W];
-#pragma unroll
-              for (int j = 0; j < W; ++j)
-                {
-                  zA[j] = smem[OFF_ZT + (buf * 2 + 0) * 16 + j];
-                  zB[j] = HASB ? smem[OFF_ZT + (buf * 2 + 1) * 16 + j] : 0.0;
-                }
               double res[RY];
-#pragma unroll
-              for (int i = 0; i < RY; ++i)
+              if (k >= g.kz_lo && k < g.kz_hi)
+                z_pass<P, RY, HASB>(g.Az, g.Bz, u1, u2, acc, res); // Toeplitz rows: coefficients from the constant bank
+              else
                 {
-                  const double u = HASB ? u2[i] : u1[i];
-                  double       t = fma(zA[0], u, acc[i][0]);
-                  if (HASB)
-                    t = fma(zB[0], u1[i], t);
-                  res[i] = t;
+                  double zA[W], zB[W];
 #pragma unroll
-                  for (int j = 1; j < 2 * P; ++j)
+                  for (int j = 0; j < W; ++j)
                     {
-                      double s = fma(zA[j], u, acc[i][j]);
-                      if (HASB)
-                        s = fma(zB[j], u1[i], s);
-                      acc[i][j - 1] = s;
+                      zA[j] = smem[OFF_ZT + (abk * 2 + 0) * 16 + j];
+                      zB[j] = HASB ? smem[OFF_ZT + (abk * 2 + 1) * 16 + j] : 0.0;
                     }
-                  double s = zA[2 * P] * u;
-                  if (HASB)
-                    s = fma(zB[2 * P], u1[i], s);
-                  acc[i][2 * P - 1] = s;
+                  z_pass<P, RY, HASB>(zA, zB, u1, u2, acc, res);
                 }
               const int r_out = k - P; // output plane completed by this input plane
               if (r_out >= zc0 && r_out < zc1 && !(g.dbg & 1))
                 {
-                  double *out = g.dst + (int64_t)r_out * g.plane + (int64_t)gy_first * g.pitch + (x0 + lx);
 #pragma unroll
                   for (int i = 0; i < RY; ++i)
                     if (gy_first + i < g.cy1)
@@ -396,12 +572,21 @@ namespace gdm
                       }
                 }
             }
+          // ---- every warp has finished the x pass of plane k+1: its stage can be refilled
+          if (!(g.dbg & 16))
+            mbar_wait(xbar, xphase);
+          xphase ^= 1;
+          if (tid == 0 && k + 1 + C::STAGES < kend)
+            {
+              mbar_expect_tx(&bars[stage], STAGE_BYTES);
+              tma_load_3d(smem + stage * C::STAGE_DOUBLES, &tmap, &bars[stage], x0 - P, y0 - P, k + 1 + C::STAGES);
+            }
           if (++stage == C::STAGES)
             {
               stage = 0;
               parity ^= 1;
             }
-          buf ^= 1;
+          abk = abn;
         }
     }
 
@@ -442,7 +627,7 @@ namespace gdm
     // available tile configurations (selected per degree; GDM_FUSED_CFG=<id> overrides for tuning)
     //                      id        P  TX RY NRB RX ST MINB
 #define GDM_FUSED_CONFIGS(X)            \
-  X(0, Cfg<1, 32, 8, 4, 8, 3, 3>)       \
+  X(0, Cfg<1, 32, 8, 4, 8, 3, 2>)       \
   X(1, Cfg<3, 32, 7, 6, 8, 3, 2>)       \
   X(2, Cfg<5, 32, 4, 6, 8, 3, 2>)       \
   X(3, Cfg<3, 32, 8, 4, 8, 2, 3>)       \
@@ -456,7 +641,17 @@ namespace gdm
   X(11, Cfg<3, 32, 8, 4, 8, 3, 2>)      \
   X(12, Cfg<3, 32, 4, 8, 8, 2, 2>)      \
   X(13, Cfg<3, 64, 8, 4, 8, 2, 1>)      \
-  X(14, Cfg<3, 32, 4, 8, 4, 3, 2>)
+  X(14, Cfg<3, 32, 4, 8, 4, 3, 2>)      \
+  X(15, Cfg<5, 32, 4, 8, 8, 3, 1>)      \
+  X(16, Cfg<5, 32, 4, 8, 8, 3, 2>)      \
+  X(17, Cfg<3, 32, 4, 8, 4, 2, 2>)      \
+  X(18, Cfg<3, 32, 4, 8, 4, 4, 2>)      \
+  X(19, Cfg<3, 32, 6, 4, 8, 3, 3>)      \
+  X(20, Cfg<3, 32, 4, 4, 4, 3, 4>)      \
+  X(21, Cfg<3, 32, 2, 8, 4, 3, 3>)      \
+  X(22, Cfg<3, 32, 2, 8, 8, 3, 3>)      \
+  X(23, Cfg<3, 32, 2, 8, 4, 2, 4>)      \
+  X(24, Cfg<3, 64, 2, 8, 8, 3, 2>)
 
     template <class F>
     void with_config(int id, F &&f)
@@ -476,7 +671,7 @@ namespace gdm
 
     int default_config(int p)
     {
-      int id = (p == 1) ? 0 : (p == 3 ? 1 : 2);
+      int id = (p == 1) ? 0 : (p == 3 ? 14 : 2);
       if (const char *env = std::getenv("GDM_FUSED_CFG"))
         {
           const int e = atoi(env);
@@ -507,7 +702,35 @@ namespace gdm
           a.Bx[d] = op.has_B ? op.hB[0][(size_t)ix * W + P + d] : 0.0;
           a.By[d] = op.has_B ? op.hB[1][(size_t)iy * W + P + d] : 0.0;
         }
-      (void)L;
+      // interior scatter row of z: zs[k][j] = scale * T_z[k - P + j][2P - j] with all rows Toeplitz,
+      // valid for input planes whose 2P+1 target rows are interior: P < k - P and k + P < N_z - P (global)
+      const int iz = P + 1; // global interior row; local index below
+      a.kz_lo      = 0;
+      a.kz_hi      = 0;
+      if (L.N[2] >= 4 * P + 2)
+        {
+          // the table of direction 2 holds local rows (loc0 .. loc1): use the global Toeplitz row through any local interior row
+          int local_interior = -1;
+          for (int r = 0; r < L.ln[2]; ++r)
+            if (r + L.loc0 > P && r + L.loc0 < L.N[2] - P)
+              {
+                local_interior = r;
+                break;
+              }
+          if (local_interior >= 0)
+            {
+              for (int j = 0; j < W; ++j)
+                {
+                  a.Az[j] = op.desc.scale * op.hA[2][(size_t)local_interior * W + (2 * P - j)];
+                  a.Bz[j] = op.has_B ? op.desc.scale * op.hB[2][(size_t)local_interior * W + (2 * P - j)] : 0.0;
+                }
+              a.kz_lo = std::max(0, 2 * P + 1 - L.loc0);
+              a.kz_hi = std::min(L.ln[2], L.N[2] - 2 * P - L.loc0);
+              if (a.kz_hi < a.kz_lo)
+                a.kz_hi = a.kz_lo;
+            }
+        }
+      (void)iz;
     }
 
     template <class C, bool HASB, int BSYM, bool ACCUM>
@@ -532,8 +755,6 @@ namespace gdm
       a.tiles_y    = plan.tiles_y;
       a.lz         = plan.lz;
       a.nz_local   = L.ln[2];
-      a.accumulate = ACCUM ? 1 : 0;
-      a.dbg        = std::getenv("GDM_FUSED_DBG") ? atoi(std::getenv("GDM_FUSED_DBG")) : 0;
       a.tabAx      = op.dA[0];
       a.tabBx      = op.dB[0];
       a.tabAy      = op.dA[1];
@@ -541,8 +762,10 @@ namespace gdm
       a.zsA        = plan.d_zsA;
       a.zsB        = plan.d_zsB;
       fill_interior<C>(op, a);
+      a.dbg = std::getenv("GDM_FUSED_DBG") ? atoi(std::getenv("GDM_FUSED_DBG")) : 0;
       auto         kern  = kron3d_kernel<C, HASB, BSYM, ACCUM>;
       const size_t smem  = smem_bytes<C, HASB>();
+      GDM_REQUIRE(smem <= 227 * 1024, GDM_ERR_INTERNAL, "fused kernel configuration exceeds the shared memory of an SM");
       static bool  attr_set = false;
       if (!attr_set)
         {

@@ -87,6 +87,37 @@ __global__ void lds_kernel(double *out, int iters)
   if (s == 123.456) out[0] = s;
 }
 
+// dependent-chain latency and single-warp throughput as a function of ILP
+template <int ILP>
+__global__ void dfma_latency_kernel(double *out, long long *cycles, int iters, double a, double b)
+{
+  double v[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) v[i] = threadIdx.x * 1e-3 + i;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it)
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) v[i] = fma(v[i], a, b);
+  long long t1 = clock64();
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += v[i];
+  if (s == 123.456) out[0] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+template <int ILP>
+void latency_line(double *out, int warps)
+{
+  long long *cyc; CK(cudaMalloc(&cyc, 8));
+  const int iters = 2000;
+  dfma_latency_kernel<ILP><<<1, 32 * warps>>>(out, cyc, iters, 1.0000001, 1e-9);
+  dfma_latency_kernel<ILP><<<1, 32 * warps>>>(out, cyc, iters, 1.0000001, 1e-9);
+  long long h; CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+  printf(" \"dfma_cycles_per_instr_ilp%d_warps%d\": %.2f,\n", ILP, warps, (double)h / (iters * ILP));
+  cudaFree(cyc);
+}
+
 template <typename F>
 float time_ms(F f, int reps = 5)
 {
@@ -114,6 +145,9 @@ int main()
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz\": %d,\n", prop.name, sms, prop.clockRate);
   double *out; CK(cudaMalloc(&out, 1024));
   const int iters = 4096;
+  // one CTA on one SM: cycles per DFMA warp-instruction seen by warp 0 (ILP 1 = dependent-issue latency)
+  latency_line<1>(out, 1); latency_line<2>(out, 1); latency_line<4>(out, 1); latency_line<8>(out, 1); latency_line<16>(out, 1);
+  latency_line<1>(out, 4); latency_line<1>(out, 8); latency_line<1>(out, 16); latency_line<2>(out, 16); latency_line<4>(out, 16); latency_line<8>(out, 8);
   {
     const int threads = 512, blocks = sms * 4, ILP = 8;
     float ms = time_ms([&] { dfma_kernel<ILP><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
