@@ -640,6 +640,19 @@ int gdm_system_layout(gdm_system_t sys, gdm_layout_info *info)
   GDM_CATCH
 }
 
+int gdm_system_halo_plan(gdm_system_t sys, int32_t *plan10)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(plan10);
+  const HaloPlan h = halo_plan(sys->impl.L);
+  const int      v[10] = {h.prev, h.next, h.send_lo_plane, h.send_lo_count, h.recv_lo_plane, h.recv_lo_count,
+                          h.send_hi_plane, h.send_hi_count, h.recv_hi_plane, h.recv_hi_count};
+  for (int i = 0; i < 10; ++i)
+    plan10[i] = v[i];
+  GDM_CATCH
+}
+
 // -------------------------------------------------------------- constraints
 int gdm_constraints_create(gdm_system_t sys, gdm_constraints_t *out)
 {

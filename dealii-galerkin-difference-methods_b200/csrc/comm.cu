@@ -152,50 +152,60 @@ namespace gdm
     }
   } // namespace
 
+  // Which planes move in a ghost import (pure host logic; also exported for the CPU-side tests).
+  HaloPlan halo_plan(const Layout &L)
+  {
+    HaloPlan h;
+    if (L.n_ranks == 1 || L.own1 <= L.own0)
+      return h;
+    int o0, o1;
+    for (int r = L.rank - 1; r >= 0 && h.prev < 0; --r)
+      {
+        owned_range(L, r, o0, o1);
+        if (o1 > o0)
+          h.prev = r;
+      }
+    for (int r = L.rank + 1; r < L.n_ranks && h.next < 0; ++r)
+      {
+        owned_range(L, r, o0, o1);
+        if (o1 > o0)
+          h.next = r;
+      }
+    const int own = L.own1 - L.own0;
+    // what I receive
+    h.recv_lo_plane = 0;
+    h.recv_lo_count = (h.prev >= 0) ? L.own0 - L.loc0 : 0;
+    h.recv_hi_plane = L.own1 - L.loc0;
+    h.recv_hi_count = (h.next >= 0) ? L.loc1 - L.own1 : 0;
+    // what the neighbours expect from me: prev's upper ghost zone, next's lower ghost zone
+    h.send_lo_count = (h.prev >= 0) ? std::min(L.ghost, L.nn[L.pdim] - L.own0) : 0;
+    h.send_lo_plane = L.own0 - L.loc0;
+    h.send_hi_count = (h.next >= 0) ? std::min(L.ghost, L.own1) : 0;
+    h.send_hi_plane = L.own0 - L.loc0 + own - h.send_hi_count;
+    GDM_REQUIRE(h.send_lo_count <= own && h.send_hi_count <= own, GDM_ERR_NOT_IMPLEMENTED,
+                "slab thinner than the ghost zone: use fewer ranks or a larger grid");
+    return h;
+  }
+
   // Import L.ghost planes from each neighbouring slab into the ghost zones of v.
   void comm_halo_exchange(Context &ctx, const Layout &L, double *v)
   {
-    if (L.n_ranks == 1 || L.own1 <= L.own0)
+    const HaloPlan h = halo_plan(L);
+    if (h.prev < 0 && h.next < 0)
       return;
     GDM_REQUIRE(ctx.comm && ctx.comm->comm, GDM_ERR_COMM, "communicator not initialised");
-    // neighbours = nearest non-empty ranks
-    int prev = -1, next = -1, o0, o1;
-    for (int r = L.rank - 1; r >= 0 && prev < 0; --r)
-      {
-        owned_range(L, r, o0, o1);
-        if (o1 > o0)
-          prev = r;
-      }
-    for (int r = L.rank + 1; r < L.n_ranks && next < 0; ++r)
-      {
-        owned_range(L, r, o0, o1);
-        if (o1 > o0)
-          next = r;
-      }
     const int64_t unit = L.stride[L.pdim];
-    const int     own  = L.own1 - L.own0;
-    const int     glo  = L.own0 - L.loc0; // planes received from prev
-    const int     ghi  = L.loc1 - L.own1; // planes received from next
-    // what the neighbours expect from me
-    const int s_dn = (prev >= 0) ? std::min(L.ghost, L.nn[L.pdim] - L.own0) : 0; // prev's upper ghost
-    const int s_up = (next >= 0) ? std::min(L.ghost, L.own1) : 0;                // next's lower ghost
-    GDM_REQUIRE(s_dn <= own && s_up <= own, GDM_ERR_NOT_IMPLEMENTED,
-                "slab thinner than the ghost zone: use fewer ranks or a larger grid");
-    Nccl &n = nccl();
+    Nccl         &n    = nccl();
     check(n.GroupStart(), "ncclGroupStart");
-    if (prev >= 0)
+    if (h.prev >= 0)
       {
-        check(n.Send(v + L.own_off, (size_t)s_dn * unit, ncclFloat64, prev, ctx.comm->comm, ctx.stream), "ncclSend");
-        check(n.Recv(v, (size_t)glo * unit, ncclFloat64, prev, ctx.comm->comm, ctx.stream), "ncclRecv");
+        check(n.Send(v + h.send_lo_plane * unit, (size_t)h.send_lo_count * unit, ncclFloat64, h.prev, ctx.comm->comm, ctx.stream), "ncclSend");
+        check(n.Recv(v + h.recv_lo_plane * unit, (size_t)h.recv_lo_count * unit, ncclFloat64, h.prev, ctx.comm->comm, ctx.stream), "ncclRecv");
       }
-    if (next >= 0)
+    if (h.next >= 0)
       {
-        check(n.Send(v + L.own_off + (int64_t)(own - s_up) * unit, (size_t)s_up * unit, ncclFloat64, next,
-                     ctx.comm->comm, ctx.stream),
-              "ncclSend");
-        check(n.Recv(v + (int64_t)(L.own1 - L.loc0) * unit, (size_t)ghi * unit, ncclFloat64, next, ctx.comm->comm,
-                     ctx.stream),
-              "ncclRecv");
+        check(n.Send(v + h.send_hi_plane * unit, (size_t)h.send_hi_count * unit, ncclFloat64, h.next, ctx.comm->comm, ctx.stream), "ncclSend");
+        check(n.Recv(v + h.recv_hi_plane * unit, (size_t)h.recv_hi_count * unit, ncclFloat64, h.next, ctx.comm->comm, ctx.stream), "ncclRecv");
       }
     check(n.GroupEnd(), "ncclGroupEnd");
   }

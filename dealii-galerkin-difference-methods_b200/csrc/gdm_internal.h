@@ -261,6 +261,13 @@ namespace gdm
   void comm_unique_id(void *id128);
   void comm_init(Context &ctx, const void *id128, int rank, int n_ranks);
   void comm_allreduce_sum(Context &ctx, double *d_buf, int count, bool max_op = false);
+  struct HaloPlan // stored-plane indices (local) of one ghost import
+  {
+    int prev = -1, next = -1; // neighbouring non-empty ranks (-1: none)
+    int send_lo_plane = 0, send_lo_count = 0, recv_lo_plane = 0, recv_lo_count = 0;
+    int send_hi_plane = 0, send_hi_count = 0, recv_hi_plane = 0, recv_hi_count = 0;
+  };
+  HaloPlan halo_plan(const Layout &L);
   void comm_halo_exchange(Context &ctx, const Layout &L, double *v);
   void comm_destroy(Context &ctx);
 

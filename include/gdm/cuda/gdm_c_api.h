@@ -121,6 +121,10 @@ typedef struct gdm_layout_info {
   uint32_t stored_begin, stored_end;
 } gdm_layout_info;
 int      gdm_system_layout(gdm_system_t sys, gdm_layout_info *info);
+/* The ghost import of update_ghost_values as plane ranges of the local storage (units of the last
+ * direction): plan10 = {prev_rank, next_rank, send_lo_plane, send_lo_count, recv_lo_plane, recv_lo_count,
+ * send_hi_plane, send_hi_count, recv_hi_plane, recv_hi_count}; ranks are -1 where there is no neighbour. */
+int      gdm_system_halo_plan(gdm_system_t sys, int32_t *plan10);
 
 /* ----------------------------------------------------------- constraints */
 int gdm_constraints_create(gdm_system_t sys, gdm_constraints_t *c);
