@@ -189,7 +189,7 @@ def run_ours(args):
     if args.quick:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "quick": True,
-                              "frac_of_hbm_roofline": ALG_BYTES_PER_DOF * value / peaks()[0]}))
+                              "frac_of_hbm_roofline": ALG_BYTES_PER_DOF * value / world / peaks()[0], "n_gpus": world}))
         return
     # ---- end to end through the host-buffer entry point (pinned host memory)
     e2e_steps = max(3, min(args.steps, 10))

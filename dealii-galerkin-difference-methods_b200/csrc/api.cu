@@ -306,7 +306,9 @@ namespace gdm
     GDM_REQUIRE(dst.sys == op.sys && src.sys == op.sys, GDM_ERR_INVALID, "vector/operator system mismatch");
     GDM_REQUIRE(dst.d != src.d, GDM_ERR_INVALID, "vmult: dst and src must not alias");
     Context &ctx = *op.sys->ctx;
-    vector_update_ghosts(src);
+    const bool overlap = (op.kernel_used == GDM_KERNEL_FUSED); // the fused path imports the ghosts itself, overlapped
+    if (!overlap)
+      vector_update_ghosts(src);
     const bool via_tmp = accumulate && op.csr;
     double    *out     = dst.d;
     if (via_tmp)
@@ -320,7 +322,7 @@ namespace gdm
       }
     const bool acc = accumulate && !via_tmp;
     if (op.kernel_used == GDM_KERNEL_FUSED)
-      fused_apply(op, out, src.d, acc);
+      fused_apply(op, out, src.d, acc, true);
     else
       generic_apply(op, out, src.d, acc);
     if (op.csr)
@@ -417,7 +419,12 @@ int gdm_context_create(int device, void *stream, gdm_context_t *out)
   GDM_CUDA_CHECK(cudaMemset(ctx.d_sums, 0, N_SUM_SLOTS * sizeof(double)));
   GDM_CUDA_CHECK(cudaMemset(ctx.d_counters, 0, 16 * sizeof(unsigned)));
   GDM_CUDA_CHECK(cudaMallocHost(&ctx.h_pinned, 64 * sizeof(double)));
-  GDM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.comm_stream, cudaStreamNonBlocking));
+  {
+    // highest priority: ghost imports and the slab-face launches behind them overtake queued interior CTAs
+    int lo_prio = 0, hi_prio = 0;
+    GDM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    GDM_CUDA_CHECK(cudaStreamCreateWithPriority(&ctx.comm_stream, cudaStreamNonBlocking, hi_prio));
+  }
   GDM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx.ev_a, cudaEventDisableTiming));
   GDM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx.ev_b, cudaEventDisableTiming));
   *out = c.release();

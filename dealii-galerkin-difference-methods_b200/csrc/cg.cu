@@ -37,9 +37,13 @@ namespace gdm
     {
       Context &ctx = *A.sys->ctx;
       if (A.kernel_used == GDM_KERNEL_FUSED)
-        fused_apply(A, dst, src, false);
+        fused_apply(A, dst, src, false, true); // ghost import overlapped with the interior planes
       else
-        generic_apply(A, dst, src, false);
+        {
+          if (A.sys->L.n_ranks > 1)
+            comm_halo_exchange(ctx, A.sys->L, const_cast<double *>(src));
+          generic_apply(A, dst, src, false);
+        }
       if (A.csr)
         launch_csr_overlay(ctx, *A.csr, dst, src, false);
     }
@@ -91,7 +95,6 @@ namespace gdm
       blas_copy(ctx, w.r + off, b.d + off, n);
       if (xx != 0.0)
         {
-          vector_update_ghosts(x);
           apply(A, w.q, x.d);
           blas_sadd(ctx, w.r + off, 1.0, -1.0, w.q + off, n);
         }
@@ -125,7 +128,6 @@ namespace gdm
         while (it < end)
           {
             ++it;
-            vector_update_ghosts(pv);
             apply(A, w.q, w.p);
             blas_dot(ctx, w.p + off, w.q + off, n, SUM_PQ);
             allreduce(SUM_PQ, 1);

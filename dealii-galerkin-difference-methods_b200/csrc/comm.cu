@@ -188,8 +188,10 @@ namespace gdm
   }
 
   // Import L.ghost planes from each neighbouring slab into the ghost zones of v.
-  void comm_halo_exchange(Context &ctx, const Layout &L, double *v)
+  void comm_halo_exchange(Context &ctx, const Layout &L, double *v, cudaStream_t stream)
   {
+    if (stream == nullptr)
+      stream = ctx.stream;
     const HaloPlan h = halo_plan(L);
     if (h.prev < 0 && h.next < 0)
       return;
@@ -199,13 +201,13 @@ namespace gdm
     check(n.GroupStart(), "ncclGroupStart");
     if (h.prev >= 0)
       {
-        check(n.Send(v + h.send_lo_plane * unit, (size_t)h.send_lo_count * unit, ncclFloat64, h.prev, ctx.comm->comm, ctx.stream), "ncclSend");
-        check(n.Recv(v + h.recv_lo_plane * unit, (size_t)h.recv_lo_count * unit, ncclFloat64, h.prev, ctx.comm->comm, ctx.stream), "ncclRecv");
+        check(n.Send(v + h.send_lo_plane * unit, (size_t)h.send_lo_count * unit, ncclFloat64, h.prev, ctx.comm->comm, stream), "ncclSend");
+        check(n.Recv(v + h.recv_lo_plane * unit, (size_t)h.recv_lo_count * unit, ncclFloat64, h.prev, ctx.comm->comm, stream), "ncclRecv");
       }
     if (h.next >= 0)
       {
-        check(n.Send(v + h.send_hi_plane * unit, (size_t)h.send_hi_count * unit, ncclFloat64, h.next, ctx.comm->comm, ctx.stream), "ncclSend");
-        check(n.Recv(v + h.recv_hi_plane * unit, (size_t)h.recv_hi_count * unit, ncclFloat64, h.next, ctx.comm->comm, ctx.stream), "ncclRecv");
+        check(n.Send(v + h.send_hi_plane * unit, (size_t)h.send_hi_count * unit, ncclFloat64, h.next, ctx.comm->comm, stream), "ncclSend");
+        check(n.Recv(v + h.recv_hi_plane * unit, (size_t)h.recv_hi_count * unit, ncclFloat64, h.next, ctx.comm->comm, stream), "ncclRecv");
       }
     check(n.GroupEnd(), "ncclGroupEnd");
   }

@@ -213,7 +213,8 @@ namespace gdm
   bool fused_supported(const Operator &op);
   void fused_plan_create(Operator &op);
   void fused_plan_destroy(Operator &op);
-  void fused_apply(Operator &op, double *dst, const double *src, bool accumulate);
+  // exchange_ghosts: import the ghost planes of src inside the call, overlapped with the interior planes
+  void fused_apply(Operator &op, double *dst, const double *src, bool accumulate, bool exchange_ghosts = false);
 
   // blas1.cu
   enum SumSlot
@@ -268,7 +269,7 @@ namespace gdm
     int send_hi_plane = 0, send_hi_count = 0, recv_hi_plane = 0, recv_hi_count = 0;
   };
   HaloPlan halo_plan(const Layout &L);
-  void comm_halo_exchange(Context &ctx, const Layout &L, double *v);
+  void comm_halo_exchange(Context &ctx, const Layout &L, double *v, cudaStream_t stream = nullptr); // nullptr: ctx.stream
   void comm_destroy(Context &ctx);
 
   // vector helpers

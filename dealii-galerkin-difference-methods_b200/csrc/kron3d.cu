@@ -615,6 +615,8 @@ namespace gdm
       int      tiles_x = 0, tiles_y = 0, n_chunks = 0, lz = 0;
       int      cx0, cx1, cy0, cy1, cz0, cz1, xorg;
       bool     tune = false; // pick the z-chunk length by timing candidates on the first apply
+      int      wz0 = -1, wz1 = -1, wlz = 0; // output-plane sub-window of the next launch (-1: whole slab)
+      bool     use_comm_stream = false;     // launch on the communication stream (slab faces, behind the ghost import)
       double  *d_zsA = nullptr, *d_zsB = nullptr;
       std::map<const void *, CUtensorMap> maps;
       ~FusedPlan()
@@ -746,14 +748,15 @@ namespace gdm
       a.cx1        = plan.cx1;
       a.cy0        = plan.cy0;
       a.cy1        = plan.cy1;
-      a.cz0        = plan.cz0;
-      a.cz1        = plan.cz1;
+      // optional sub-window of output planes (multi-GPU: interior first, slab faces after the halo arrived)
+      a.cz0        = (plan.wz0 >= 0) ? std::max(plan.cz0, plan.wz0) : plan.cz0;
+      a.cz1        = (plan.wz0 >= 0) ? std::min(plan.cz1, plan.wz1) : plan.cz1;
       a.xorg       = plan.xorg;
       a.nx         = L.N[0];
       a.ny         = L.N[1];
       a.tiles_x    = plan.tiles_x;
       a.tiles_y    = plan.tiles_y;
-      a.lz         = plan.lz;
+      a.lz         = (plan.wz0 >= 0 && plan.wlz > 0) ? plan.wlz : plan.lz;
       a.nz_local   = L.ln[2];
       a.tabAx      = op.dA[0];
       a.tabBx      = op.dB[0];
@@ -772,10 +775,13 @@ namespace gdm
           GDM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           attr_set = true;
         }
-      const int grid = plan.tiles_x * plan.tiles_y * plan.n_chunks;
+      if (a.cz1 <= a.cz0)
+        return;
+      const int n_chunks = (a.cz1 - a.cz0 + a.lz - 1) / a.lz;
+      const int grid     = plan.tiles_x * plan.tiles_y * n_chunks;
       if (grid <= 0)
         return;
-      kern<<<grid, C::THREADS, smem, ctx.stream>>>(map, a);
+      kern<<<grid, C::THREADS, smem, plan.use_comm_stream ? ctx.comm_stream : ctx.stream>>>(map, a);
       ctx.launches++;
       GDM_CUDA_CHECK(cudaGetLastError());
     }
@@ -906,7 +912,7 @@ namespace gdm
       accumulate ? launch_variant<C, true, -1, true>(op, plan, map, dst) : launch_variant<C, true, -1, false>(op, plan, map, dst);
   }
 
-  void fused_apply(Operator &op, double *dst, const double *src, bool accumulate)
+  void fused_apply(Operator &op, double *dst, const double *src, bool accumulate, bool exchange_ghosts)
   {
     FusedPlan    &plan = *static_cast<FusedPlan *>(op.fused);
     Context      &ctx  = *op.sys->ctx;
@@ -966,7 +972,44 @@ namespace gdm
           fprintf(stderr, "[gdm] fused plan: cfg %d, tiles %d x %d, lz %d (%d chunks), %.3f ms\n", plan.cfg, plan.tiles_x,
                   plan.tiles_y, plan.lz, plan.n_chunks, best_ms);
       }
-    with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
+    const int P = L.p;
+    if (L.n_ranks > 1 && exchange_ghosts)
+      {
+        // overlap the ghost import (NCCL on the comm stream) with the planes that do not need it
+        const int lo = L.own0 - L.loc0, hi = L.own1 - L.loc0; // owned planes (local indices)
+        const bool thick = (hi - lo) > 4 * P;
+        GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_a, ctx.stream));
+        GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.comm_stream, ctx.ev_a, 0));
+        comm_halo_exchange(ctx, L, const_cast<double *>(src), ctx.comm_stream);
+        if (thick)
+          {
+            // slab faces: behind the ghost import on the comm stream, concurrent with the interior planes
+            plan.use_comm_stream = true;
+            plan.wlz             = P;
+            plan.wz0             = lo;
+            plan.wz1             = lo + P;
+            with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
+            plan.wz0 = hi - P;
+            plan.wz1 = hi;
+            with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
+            plan.use_comm_stream = false;
+            GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_b, ctx.comm_stream));
+            plan.wz0 = lo + P;
+            plan.wz1 = hi - P;
+            plan.wlz = 0;
+            with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
+            plan.wz0 = plan.wz1 = -1;
+            GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, ctx.ev_b, 0));
+          }
+        else
+          {
+            GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_b, ctx.comm_stream));
+            GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, ctx.ev_b, 0));
+            with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
+          }
+      }
+    else
+      with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
     // Dirichlet faces (skipped by the tiles) and deal.II's constrained diagonal
     launch_constrained_rows(ctx, L, op, dst, src, accumulate);
   }
