@@ -62,4 +62,4 @@ def test_advection_01_gdm_against_oracle(lib):
     assert len(lines) == len(errs)
     for (ts, es), (t, e) in zip(lines, errs):
         assert abs(float(ts) - t) < 1e-12
-        assert abs(float(es) - e) <= 1e-6 * e + 1e-12, (ts, es, e)
+        assert abs(float(es) - e) <= 2e-5 * e, (ts, es, e)  # stdout carries 6 significant digits
