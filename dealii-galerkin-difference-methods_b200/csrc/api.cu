@@ -84,6 +84,14 @@ namespace gdm
       cudaFreeHost(h_pinned);
     if (comm_stream)
       cudaStreamDestroy(comm_stream);
+    if (h2d_stream)
+      {
+        cudaStreamDestroy(h2d_stream);
+        cudaStreamDestroy(d2h_stream);
+        for (int i = 0; i < 2; ++i)
+          for (int j = 0; j < 32; ++j)
+            cudaEventDestroy(ev_pipe[i][j]);
+      }
     if (ev_a)
       cudaEventDestroy(ev_a);
     if (ev_b)
@@ -116,6 +124,8 @@ namespace gdm
     cudaFree(tmp);
     cudaFree(host_src);
     cudaFree(host_dst);
+    cudaFree(stage_src);
+    cudaFree(stage_dst);
     if (fused)
       fused_plan_destroy(*this);
   }
@@ -1092,10 +1102,66 @@ int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *s
   vs.d    = o.host_src;
   vd.d    = o.host_dst;
   vs.owns = vd.owns = false;
-  vector_transfer(vs, const_cast<double *>(src_host), true);
-  operator_apply(o, vd, vs, false);
-  vector_transfer(vd, dst_host, false);
-  GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+  const Layout &L = sys.L;
+  if (o.kernel_used == GDM_KERNEL_FUSED && L.n_ranks == 1 && !o.csr && L.ln[2] >= 16 * L.p)
+    {
+      // Pipelined over z chunks: H2D of chunk c+1, apply of the planes whose inputs have arrived and D2H
+      // of finished planes overlap on three streams (PCIe is full duplex; the apply hides behind it).
+      if (!ctx.h2d_stream)
+        {
+          GDM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.h2d_stream, cudaStreamNonBlocking));
+          GDM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.d2h_stream, cudaStreamNonBlocking));
+          for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 32; ++j)
+              GDM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx.ev_pipe[i][j], cudaEventDisableTiming));
+        }
+      const int    nz = L.ln[2], P = L.p;
+      const int    n_chunks = std::min(16, std::max(2, nz / (8 * P)));
+      const int    cz = (nz + n_chunks - 1) / n_chunks;
+      const size_t plane_host = (size_t)L.ln[0] * L.nc * L.ln[1];
+      if (!o.stage_src)
+        {
+          GDM_CUDA_CHECK(cudaMalloc(&o.stage_src, plane_host * nz * sizeof(double)));
+          GDM_CUDA_CHECK(cudaMalloc(&o.stage_dst, plane_host * nz * sizeof(double)));
+        }
+      // the staging buffers were produced on ctx.stream (memset): order the side streams behind it
+      GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_a, ctx.stream));
+      GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.h2d_stream, ctx.ev_a, 0));
+      GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.d2h_stream, ctx.ev_a, 0));
+      int done = 0; // output planes [0, done) have been launched
+      for (int c = 0; c < n_chunks; ++c)
+        {
+          const int c0 = c * cz, c1 = std::min(nz, c0 + cz);
+          if (c1 <= c0)
+            break;
+          // contiguous 1D copy (row-wise 2D copies of 2 KB rows reach only a fraction of the PCIe rate)
+          GDM_CUDA_CHECK(cudaMemcpyAsync(o.stage_src + (size_t)c0 * plane_host, src_host + (size_t)c0 * plane_host,
+                                         (size_t)(c1 - c0) * plane_host * sizeof(double), cudaMemcpyHostToDevice, ctx.h2d_stream));
+          GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_pipe[0][c], ctx.h2d_stream));
+          GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, ctx.ev_pipe[0][c], 0));
+          launch_repack(ctx, L, o.host_src, o.stage_src, c0, c1, true);
+          const int upto = (c1 == nz) ? nz : c1 - P; // outputs whose inputs (up to +P planes) are on the device
+          if (upto > done)
+            {
+              fused_apply_window(o, o.host_dst, o.host_src, done, upto);
+              launch_repack(ctx, L, o.host_dst, o.stage_dst, done, upto, false);
+              GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_pipe[1][c], ctx.stream));
+              GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.d2h_stream, ctx.ev_pipe[1][c], 0));
+              GDM_CUDA_CHECK(cudaMemcpyAsync(dst_host + (size_t)done * plane_host, o.stage_dst + (size_t)done * plane_host,
+                                             (size_t)(upto - done) * plane_host * sizeof(double), cudaMemcpyDeviceToHost, ctx.d2h_stream));
+              done = upto;
+            }
+        }
+      GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.d2h_stream));
+      GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    }
+  else
+    {
+      vector_transfer(vs, const_cast<double *>(src_host), true);
+      operator_apply(o, vd, vs, false);
+      vector_transfer(vd, dst_host, false);
+      GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    }
   GDM_CATCH
 }
 

@@ -83,6 +83,8 @@ namespace gdm
     int          device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr; // host-buffer pipeline (created on first use)
+    cudaEvent_t  ev_pipe[2][32] = {};
     cudaEvent_t  ev_a = nullptr, ev_b = nullptr;
     int          sm_count = 148;
     uint64_t     launches = 0;
@@ -180,7 +182,8 @@ namespace gdm
     std::unique_ptr<CsrOverlay> csr;
     void   *fused = nullptr;          // FusedPlan* (kron3d.cu)
     double *tmp = nullptr;            // vmult_add with CSR overlay
-    double *host_src = nullptr, *host_dst = nullptr; // staging of vmult_host
+    double *host_src = nullptr, *host_dst = nullptr; // staging of vmult_host (padded layout)
+    double *stage_src = nullptr, *stage_dst = nullptr; // contiguous staging (host order) for 1D PCIe copies
     Operator() = default;
     Operator(const Operator &) = delete;
     ~Operator();
@@ -200,7 +203,7 @@ namespace gdm
   };
   void launch_band_pass(Context &ctx, const Layout &L, const bool periodic[3], const BandPassArgs &a);
   void launch_constrained_rows(Context &ctx, const Layout &L, const Operator &op, double *dst,
-                               const double *src, bool accumulate);
+                               const double *src, bool accumulate, int plane_lo = -1, int plane_hi = -1);
   void launch_csr_overlay(Context &ctx, const CsrOverlay &csr, double *dst, const double *src,
                           bool accumulate);
   void launch_periodic_copy(Context &ctx, const Layout &L, const bool periodic[3], double *v);
@@ -208,6 +211,7 @@ namespace gdm
                               const bool periodic[3], double *v, double value);
   void launch_diagonal(Context &ctx, const Layout &L, const Operator &op, double *diag);
   void generic_apply(Operator &op, double *dst, const double *src, bool accumulate);
+  void launch_repack(Context &ctx, const Layout &L, double *padded, double *compact, int p0, int p1, bool to_padded);
 
   // kron3d.cu -- fused tensor-product kernel (dim == 3)
   bool fused_supported(const Operator &op);
@@ -215,6 +219,8 @@ namespace gdm
   void fused_plan_destroy(Operator &op);
   // exchange_ghosts: import the ghost planes of src inside the call, overlapped with the interior planes
   void fused_apply(Operator &op, double *dst, const double *src, bool accumulate, bool exchange_ghosts = false);
+  // output planes [z0, z1) only (local plane indices; no ghost import): building block of the pipelined host-buffer apply
+  void fused_apply_window(Operator &op, double *dst, const double *src, int z0, int z1);
 
   // blas1.cu
   enum SumSlot

@@ -7,6 +7,8 @@
 //
 // Replaces SparseMatrix::vmult on matrices assembled by the reference's cell loops
 // (include/gdm/matrix_creator.h:21-61, tests/poisson_02_gdm.cc:160-206).
+#include <algorithm>
+
 #include "gdm_internal.h"
 
 namespace gdm
@@ -319,7 +321,7 @@ namespace gdm
   } // namespace
 
   void launch_constrained_rows(Context &ctx, const Layout &L, const Operator &op, double *dst,
-                               const double *src, bool accumulate)
+                               const double *src, bool accumulate, int plane_lo, int plane_hi)
   {
     FaceK a;
     a.dst = dst;
@@ -329,8 +331,8 @@ namespace gdm
     a.has_B      = op.has_B ? 1 : 0;
     a.accumulate = accumulate ? 1 : 0;
     a.pdim       = L.pdim;
-    a.own_lo     = L.own0 - L.loc0;
-    a.own_hi     = L.own1 - L.loc0;
+    a.own_lo     = (plane_lo >= 0) ? plane_lo : L.own0 - L.loc0; // optional window in the partitioned direction
+    a.own_hi     = (plane_lo >= 0) ? plane_hi : L.own1 - L.loc0;
     // GDM_DIAG_ZERO: constrained rows are written as exact zeros (residual semantics)
     a.scale      = (op.desc.constrained_diagonal == GDM_DIAG_ASSEMBLED) ? op.desc.scale : 0.0;
     for (int d = 0; d < 3; ++d)
@@ -533,5 +535,36 @@ namespace gdm
       }
     if (op.desc.constrained_diagonal == GDM_DIAG_ASSEMBLED)
       launch_constrained_rows(ctx, L, op, dst, src, true);
+  }
+  namespace
+  {
+    // compact (host order) <-> padded device layout for a range of rows
+    __global__ void repack_kernel(double *padded, double *compact, int64_t row_len, int64_t pitch, int64_t n_rows, int to_padded)
+    {
+      const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < row_len * n_rows; i += stride)
+        {
+          const int64_t r = i / row_len, c = i - r * row_len;
+          if (to_padded)
+            padded[r * pitch + c] = compact[i];
+          else
+            compact[i] = padded[r * pitch + c];
+        }
+    }
+  } // namespace
+
+  // planes [p0, p1) of a 3D vector: padded storage <-> contiguous staging buffer (host order)
+  void launch_repack(Context &ctx, const Layout &L, double *padded, double *compact, int p0, int p1, bool to_padded)
+  {
+    const int64_t row_len = (int64_t)L.ln[0] * L.nc, n_rows = (int64_t)(p1 - p0) * L.ln[1];
+    if (n_rows <= 0)
+      return;
+    const int64_t n      = row_len * n_rows;
+    const int     th     = 256;
+    const int     blocks = (int)std::min<int64_t>((n + th - 1) / th, (int64_t)ctx.sm_count * 16);
+    repack_kernel<<<blocks, th, 0, ctx.stream>>>(padded + (int64_t)p0 * L.plane, compact + (int64_t)p0 * row_len * L.ln[1], row_len,
+                                                L.pitch, n_rows, to_padded ? 1 : 0);
+    ctx.launches++;
+    GDM_CUDA_CHECK(cudaGetLastError());
   }
 } // namespace gdm

@@ -1013,4 +1013,17 @@ namespace gdm
     // Dirichlet faces (skipped by the tiles) and deal.II's constrained diagonal
     launch_constrained_rows(ctx, L, op, dst, src, accumulate);
   }
+  void fused_apply_window(Operator &op, double *dst, const double *src, int z0, int z1)
+  {
+    FusedPlan    &plan = *static_cast<FusedPlan *>(op.fused);
+    Context      &ctx  = *op.sys->ctx;
+    const Layout &L    = op.sys->L;
+    plan.wz0           = z0;
+    plan.wz1           = z1;
+    plan.wlz           = std::max(1, std::min(plan.lz, z1 - z0));
+    with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, false); });
+    plan.wz0 = plan.wz1 = -1;
+    plan.wlz            = 0;
+    launch_constrained_rows(ctx, L, op, dst, src, false, z0, z1);
+  }
 } // namespace gdm

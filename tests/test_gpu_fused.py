@@ -95,3 +95,19 @@ def test_full_size_properties(lib, p, n):
     M = make_operator(gs2, gc2, "mass", kernel=g.capi.KERNEL_FUSED)
     M.vmult(out, one)
     assert abs(one * out - 1.0) <= 1e-12
+
+
+@pytest.mark.parametrize("p,reps,bc", [(3, [35, 30, 70], "dirichlet"), (3, [33, 20, 97], "none"), (5, [20, 21, 100], "left")])
+def test_pipelined_host_buffer_apply(lib, p, reps, bc):
+    """gdm_operator_vmult_host on a grid deep enough for the chunked H2D / apply / D2H pipeline."""
+    import gdm_b200 as g
+    gs, gc, os_, oc = make_pair(3, p, 1, reps, bc)
+    for kind in ("stiffness", "mass"):
+        A = make_operator(gs, gc, kind, kernel=g.capi.KERNEL_FUSED)
+        Ao = oracle_operator(os_, oc, kind)
+        xh = np.random.default_rng(5).uniform(-1, 1, gs.n_dofs())
+        yh = np.full_like(xh, 3.0)
+        A.vmult_host(yh, xh)
+        assert rel_err(yh, Ao @ xh) <= TOL
+        A.vmult_host(yh, -xh)  # staging buffers are reused
+        assert rel_err(yh, -(Ao @ xh)) <= TOL
