@@ -73,22 +73,23 @@ namespace gdm
     }
 
     // ------------------------------------------------------------------ configuration
-    template <int P_, int TX_, int RY_, int NRB_, int RX_, int STAGES_, int MINB_>
+    template <int P_, int TX_, int RY_, int NRB_, int RX_, int STAGES_, int MINB_, int NXW_ = 0>
     struct Cfg
     {
       static constexpr int P = P_, TX = TX_, RY = RY_, NRB = NRB_, RX = RX_, STAGES = STAGES_, MINB = MINB_;
+      static constexpr int NXW = NXW_; // > 0: warp-specialised kernel with NXW dedicated x-pass warps
       static constexpr int W       = 2 * P + 1;
       static constexpr int TY      = RY * NRB;
       static constexpr int NR      = TY + 2 * P;                         // rows of the staged tile
       static constexpr int PIN     = TX + 2 * P;                         // pitch of the staged tile (dense TMA box)
       static constexpr int PY      = ((NR / 2) & 1) ? NR : NR + 2;       // column pitch of the transposed a/b fields
-      static constexpr int THREADS = TX * NRB;
+      static constexpr int THREADS = TX * NRB + 32 * NXW_;
       static constexpr int NWARPS  = THREADS / 32;
       static constexpr int NXB     = TX / RX;
       static constexpr int NTASK   = NXB * NR;
       static constexpr int NAB     = 3;                                  // a/b buffers in flight (split barrier)
       // x pass work split: block tasks (RX outputs) on rows [0, NRM), single outputs on rows [NRM, NR)
-      static constexpr int NRM     = (NTASK <= THREADS) ? NR : (THREADS / NXB);
+      static constexpr int NRM     = (NTASK <= TX * NRB) ? NR : ((TX * NRB) / NXB);
       static constexpr int NREM    = (NR - NRM) * TX;                    // single-output tasks
       static constexpr int NBT     = 2 * (P + 1);                        // boundary (non-Toeplitz) rows per direction
       static constexpr int TB_DOUBLES = 2 * 2 * NBT * 8 * ((2 * P + 1 + 7) / 8); // [dir][field][row][taps padded]
@@ -119,7 +120,7 @@ namespace gdm
     constexpr size_t smem_bytes()
     {
       return (size_t)(C::STAGES * C::STAGE_DOUBLES + C::NAB * (HASB ? 2 : 1) * C::TX * C::PY + C::NAB * 2 * 16 + C::TB_DOUBLES) * sizeof(double) +
-             (C::STAGES + 1) * sizeof(uint64_t) + 128;
+             (2 * C::STAGES + 2 * C::NAB + 2) * sizeof(uint64_t) + 128;
     }
 
     __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -590,6 +591,338 @@ namespace gdm
         }
     }
 
+    // ------------------------------------------------------------------ warp-specialised variant
+    // NXW dedicated x-pass warps (producers) and NRB y/z warps (consumers) run concurrently: the x pass is
+    // shared-memory heavy, the y/z pass FP64 heavy, so the two pipes are busy at the same time instead of
+    // alternating.  No CTA-wide barrier: mbarrier rings full_ab/empty_ab (a/b buffers) and full_in/empty_in
+    // (TMA stages) carry the dependencies; the producers run up to NAB-1 planes ahead.
+    template <class C, bool HASB, int BSYM, bool ACCUM>
+    __global__ void __launch_bounds__(C::THREADS, 1) kron3d_ws_kernel(const __grid_constant__ CUtensorMap tmap, const KArgs<C::P> g)
+    {
+      constexpr int P = C::P, W = C::W, TX = C::TX, RY = C::RY, RX = C::RX, NR = C::NR, PIN = C::PIN, PY = C::PY;
+      constexpr int NF = HASB ? 2 : 1, NAB = C::NAB, S = C::STAGES;
+      constexpr int YZ_THREADS = TX * C::NRB, X_THREADS = 32 * C::NXW;
+      extern __shared__ __align__(128) double smem[];
+      constexpr int AB_BUF  = NF * TX * PY;
+      constexpr int OFF_AB  = S * C::STAGE_DOUBLES;
+      constexpr int OFF_ZT  = OFF_AB + NAB * AB_BUF;
+      constexpr int OFF_TB  = OFF_ZT + NAB * 2 * 16;
+      constexpr int WP      = 8 * ((W + 7) / 8);
+      constexpr int NBT     = C::NBT;
+      constexpr int OFF_BAR = OFF_TB + C::TB_DOUBLES;
+      uint64_t     *full_in  = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+      uint64_t     *empty_in = full_in + S;
+      uint64_t     *full_ab  = empty_in + S;
+      uint64_t     *empty_ab = full_ab + NAB;
+
+      const int tid = threadIdx.x;
+      int       b   = blockIdx.x;
+      const int tx  = b % g.tiles_x;
+      b /= g.tiles_x;
+      const int ty    = b % g.tiles_y;
+      const int chunk = b / g.tiles_y;
+      const int x0    = g.xorg + tx * TX;
+      const int y0    = g.cy0 + ty * C::TY;
+      const int zc0   = g.cz0 + chunk * g.lz;
+      const int zc1   = min(zc0 + g.lz, g.cz1);
+      const int kbeg = zc0 - P, kend = zc1 + P;
+      const int ncols   = min(TX, g.cx1 - x0);
+      const int nrows   = min(C::TY, g.cy1 - y0);
+      const int nr_need = nrows + 2 * P;
+      constexpr unsigned STAGE_BYTES = NR * PIN * sizeof(double);
+
+      if (tid == 0)
+        {
+          for (int s = 0; s < S; ++s)
+            {
+              mbar_init(&full_in[s], 1);
+              mbar_init(&empty_in[s], C::NXW);
+            }
+          for (int i = 0; i < NAB; ++i)
+            {
+              mbar_init(&full_ab[i], C::NXW);
+              mbar_init(&empty_ab[i], C::NRB * (TX / 32));
+            }
+          mbar_fence_init();
+        }
+      for (int e = tid; e < 2 * 2 * NBT * W; e += C::THREADS)
+        {
+          const int t = e % W, c = (e / W) % NBT, f = (e / (W * NBT)) % 2, d = e / (W * NBT * 2);
+          const int n    = d ? g.ny : g.nx;
+          const int node = (c <= P) ? c : n - P + (c - P - 1);
+          const double *tab = d ? (f ? g.tabBy : g.tabAy) : (f ? g.tabBx : g.tabAx);
+          smem[OFF_TB + ((d * 2 + f) * NBT + c) * WP + t] = (HASB || f == 0) ? __ldg(tab + node * W + t) : 0.0;
+        }
+      __syncthreads();
+
+      if (tid >= YZ_THREADS)
+        {
+          // =========================================================== producers: TMA + x pass
+          const int xt = tid - YZ_THREADS;
+          if (xt == 0)
+            for (int s = 0; s < S; ++s)
+              if (kbeg + s < kend)
+                {
+                  mbar_expect_tx(&full_in[s], STAGE_BYTES);
+                  tma_load_3d(smem + s * C::STAGE_DOUBLES, &tmap, &full_in[s], x0 - P, y0 - P, kbeg + s);
+                }
+          const int     zj = xt % W, zf = (xt / W) & 1;
+          const double *zsrc = (zf ? g.zsB : g.zsA) + zj;
+          double        znext = 0.0;
+          if (xt < 2 * W && kbeg >= 0 && kbeg < g.nz_local)
+            znext = __ldg(zsrc + (int64_t)kbeg * W);
+          int it = 0;
+          for (int k = kbeg; k < kend; ++k, ++it)
+            {
+              const int s = it % S, ab = it % NAB;
+              // refill the stage of the previous plane once every producer warp has left it
+              if (xt == 0 && it > 0)
+                {
+                  const int sp = (it - 1) % S, kp = k - 1 + S;
+                  if (kp < kend)
+                    {
+                      mbar_wait(&empty_in[sp], ((it - 1) / S) & 1);
+                      mbar_expect_tx(&full_in[sp], STAGE_BYTES);
+                      tma_load_3d(smem + sp * C::STAGE_DOUBLES, &tmap, &full_in[sp], x0 - P, y0 - P, kp);
+                    }
+                }
+              mbar_wait(&full_in[s], (it / S) & 1);
+              mbar_wait(&empty_ab[ab], ((it / NAB) & 1) ^ 1);
+              const int in_off = s * C::STAGE_DOUBLES;
+              const int a_off  = OFF_AB + ab * AB_BUF;
+              const int b_off  = a_off + (NF - 1) * TX * PY;
+              if (xt < 2 * W)
+                {
+                  smem[OFF_ZT + (ab * 2 + zf) * 16 + zj] = znext;
+                  znext = (k + 1 >= 0 && k + 1 < g.nz_local) ? __ldg(zsrc + (int64_t)(k + 1) * W) : 0.0;
+                }
+              for (int task = xt; task < C::NTASK; task += X_THREADS)
+                {
+                  const int r  = task % NR;
+                  const int xb = task / NR;
+                  if (r >= nr_need || xb * RX >= ncols)
+                    continue;
+                  double v[RX + 2 * P];
+                  {
+                    const double2 *src = reinterpret_cast<const double2 *>(smem + in_off + r * PIN + xb * RX);
+#pragma unroll
+                    for (int q = 0; q < (RX + 2 * P) / 2; ++q)
+                      {
+                        const double2 t = src[q];
+                        v[2 * q]        = t.x;
+                        v[2 * q + 1]    = t.y;
+                      }
+                  }
+                  double a[RX], bb[RX];
+#pragma unroll
+                  for (int j = 0; j < RX; ++j)
+                    {
+                      const int c   = j + P;
+                      double    ra  = g.Ax[0] * v[c];
+                      double    rbv = (HASB && BSYM > 0) ? g.Bx[0] * v[c] : 0.0;
+#pragma unroll
+                      for (int d = 1; d <= P; ++d)
+                        {
+                          const double sm = v[c - d] + v[c + d];
+                          ra              = fma(g.Ax[d], sm, ra);
+                          if (HASB)
+                            {
+                              if (BSYM > 0)
+                                rbv = fma(g.Bx[d], sm, rbv);
+                              else
+                                rbv = fma(g.Bx[d], v[c + d] - v[c - d], rbv);
+                            }
+                        }
+                      a[j]  = ra;
+                      bb[j] = rbv;
+                    }
+                  const int gx_first = x0 + xb * RX;
+                  if (gx_first <= P || gx_first + RX - 1 >= g.nx - P)
+                    {
+#pragma unroll
+                      for (int j = 0; j < RX; ++j)
+                        {
+                          const int gx = gx_first + j;
+                          if ((gx <= P || gx >= g.nx - P) && gx >= 0 && gx <= g.nx)
+                            {
+                              const int     rc = (gx <= P) ? gx : gx - (g.nx - P) + P + 1;
+                              const double *ta = smem + OFF_TB + (0 * NBT + rc) * WP;
+                              const double *tb = smem + OFF_TB + (1 * NBT + rc) * WP;
+                              double        ra = 0.0, rbv = 0.0;
+#pragma unroll
+                              for (int t = 0; t < W; ++t)
+                                {
+                                  ra = fma(ta[t], v[j + t], ra);
+                                  if (HASB)
+                                    rbv = fma(tb[t], v[j + t], rbv);
+                                }
+                              a[j]  = ra;
+                              bb[j] = rbv;
+                            }
+                        }
+                    }
+#pragma unroll
+                  for (int j = 0; j < RX; ++j)
+                    {
+                      smem[a_off + (xb * RX + j) * PY + r] = a[j];
+                      if (HASB)
+                        smem[b_off + (xb * RX + j) * PY + r] = bb[j];
+                    }
+                }
+              __syncwarp();
+              if ((xt & 31) == 0)
+                {
+                  mbar_arrive(&full_ab[ab]);
+                  mbar_arrive(&empty_in[s]);
+                }
+            }
+        }
+      else
+        {
+          // =========================================================== consumers: y pass + z pass
+          const int  lx        = tid % TX;
+          const int  rb        = tid / TX;
+          const int  gy_first  = y0 + rb * RY;
+          const bool yz_active = (lx < ncols) && (x0 + lx >= g.cx0) && (rb * RY < nrows);
+          const bool y_bnd     = (gy_first <= P) || (gy_first + RY - 1 >= g.ny - P);
+          double    *out       = g.dst + (int64_t)(kbeg - P - 1) * g.plane + (int64_t)gy_first * g.pitch + (x0 + lx);
+          double     acc[RY][2 * P];
+#pragma unroll
+          for (int i = 0; i < RY; ++i)
+#pragma unroll
+            for (int j = 0; j < 2 * P; ++j)
+              acc[i][j] = 0.0;
+          int it = 0;
+          for (int k = kbeg; k < kend; ++k, ++it)
+            {
+              const int ab = it % NAB;
+              mbar_wait(&full_ab[ab], (it / NAB) & 1);
+              out += g.plane;
+              if (yz_active)
+                {
+                  const int a_off = OFF_AB + ab * AB_BUF + lx * PY + rb * RY;
+                  const int b_off = a_off + (NF - 1) * TX * PY;
+                  double    u1[RY], u2[RY];
+                  {
+                    double aw[RY + 2 * P], bw[RY + 2 * P];
+                    if constexpr (RY % 2 == 0)
+                      {
+                        const double2 *pa = reinterpret_cast<const double2 *>(smem + a_off);
+                        const double2 *pb = reinterpret_cast<const double2 *>(smem + b_off);
+#pragma unroll
+                        for (int q = 0; q < (RY + 2 * P) / 2; ++q)
+                          {
+                            const double2 t = pa[q];
+                            aw[2 * q]       = t.x;
+                            aw[2 * q + 1]   = t.y;
+                            if (HASB)
+                              {
+                                const double2 s2 = pb[q];
+                                bw[2 * q]        = s2.x;
+                                bw[2 * q + 1]    = s2.y;
+                              }
+                          }
+                      }
+                    else
+                      {
+#pragma unroll
+                        for (int j = 0; j < RY + 2 * P; ++j)
+                          {
+                            aw[j] = smem[a_off + j];
+                            if (HASB)
+                              bw[j] = smem[b_off + j];
+                          }
+                      }
+#pragma unroll
+                    for (int i = 0; i < RY; ++i)
+                      {
+                        const int gy = min(gy_first + i, g.ny);
+                        double    t1, t2 = 0.0;
+                        if (y_bnd && (gy <= P || gy >= g.ny - P))
+                          {
+                            const int     rc = (gy <= P) ? gy : gy - (g.ny - P) + P + 1;
+                            const double *ta = smem + OFF_TB + (2 * NBT + rc) * WP;
+                            const double *tb = smem + OFF_TB + (3 * NBT + rc) * WP;
+                            t1               = 0.0;
+#pragma unroll
+                            for (int t = 0; t < W; ++t)
+                              {
+                                const double ca = ta[t];
+                                t1              = fma(ca, aw[i + t], t1);
+                                if (HASB)
+                                  {
+                                    t2 = fma(ca, bw[i + t], t2);
+                                    t2 = fma(tb[t], aw[i + t], t2);
+                                  }
+                              }
+                          }
+                        else
+                          {
+                            const int c = i + P;
+                            t1          = g.Ay[0] * aw[c];
+                            if (HASB)
+                              {
+                                t2 = g.Ay[0] * bw[c];
+                                if (BSYM > 0)
+                                  t2 = fma(g.By[0], aw[c], t2);
+                              }
+#pragma unroll
+                            for (int d = 1; d <= P; ++d)
+                              {
+                                const double sa = aw[c - d] + aw[c + d];
+                                t1              = fma(g.Ay[d], sa, t1);
+                                if (HASB)
+                                  {
+                                    const double sb = bw[c - d] + bw[c + d];
+                                    t2              = fma(g.Ay[d], sb, t2);
+                                    if (BSYM > 0)
+                                      t2 = fma(g.By[d], sa, t2);
+                                    else
+                                      t2 = fma(g.By[d], aw[c + d] - aw[c - d], t2);
+                                  }
+                              }
+                          }
+                        u1[i] = t1;
+                        u2[i] = t2;
+                      }
+                  }
+                  double res[RY];
+                  if (k >= g.kz_lo && k < g.kz_hi)
+                    z_pass<P, RY, HASB>(g.Az, g.Bz, u1, u2, acc, res);
+                  else
+                    {
+                      double zA[W], zB[W];
+#pragma unroll
+                      for (int j = 0; j < W; ++j)
+                        {
+                          zA[j] = smem[OFF_ZT + (ab * 2 + 0) * 16 + j];
+                          zB[j] = HASB ? smem[OFF_ZT + (ab * 2 + 1) * 16 + j] : 0.0;
+                        }
+                      z_pass<P, RY, HASB>(zA, zB, u1, u2, acc, res);
+                    }
+                  const int r_out = k - P;
+                  if (r_out >= zc0 && r_out < zc1)
+                    {
+#pragma unroll
+                      for (int i = 0; i < RY; ++i)
+                        if (gy_first + i < g.cy1)
+                          {
+                            double *o = out + (int64_t)i * g.pitch;
+                            double  t = res[i];
+                            if (ACCUM)
+                              t += *o;
+                            *o = t;
+                          }
+                    }
+                }
+              // this warp no longer needs the a/b buffer (and its z-table slot)
+              __syncwarp();
+              if ((tid & 31) == 0)
+                mbar_arrive(&empty_ab[ab]);
+            }
+        }
+    }
+
     // ------------------------------------------------------------------ host side
     typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -653,7 +986,20 @@ namespace gdm
   X(21, Cfg<3, 32, 2, 8, 4, 3, 3>)      \
   X(22, Cfg<3, 32, 2, 8, 8, 3, 3>)      \
   X(23, Cfg<3, 32, 2, 8, 4, 2, 4>)      \
-  X(24, Cfg<3, 64, 2, 8, 8, 3, 2>)
+  X(24, Cfg<3, 64, 2, 8, 8, 3, 2>)      \
+  X(25, Cfg<3, 32, 8, 8, 8, 3, 1>)      \
+  X(26, Cfg<3, 32, 6, 8, 8, 3, 1>)      \
+  X(27, Cfg<3, 64, 4, 8, 8, 3, 1>)      \
+  X(28, Cfg<3, 64, 4, 8, 4, 3, 1>)      \
+  X(29, Cfg<3, 32, 4, 8, 4, 3, 1>)      \
+  X(30, Cfg<3, 32, 4, 16, 4, 3, 1>)     \
+  X(31, Cfg<3, 32, 4, 12, 4, 3, 1>)     \
+  X(32, Cfg<3, 32, 4, 16, 8, 3, 1>)     \
+  X(40, Cfg<3, 32, 4, 8, 4, 3, 1, 4>)   \
+  X(41, Cfg<3, 32, 4, 8, 8, 3, 1, 4>)   \
+  X(42, Cfg<3, 32, 4, 8, 4, 4, 1, 4>)   \
+  X(43, Cfg<3, 32, 6, 8, 4, 3, 1, 4>)   \
+  X(44, Cfg<3, 32, 4, 8, 4, 3, 1, 8>)
 
     template <class F>
     void with_config(int id, F &&f)
@@ -766,7 +1112,7 @@ namespace gdm
       a.zsB        = plan.d_zsB;
       fill_interior<C>(op, a);
       a.dbg = std::getenv("GDM_FUSED_DBG") ? atoi(std::getenv("GDM_FUSED_DBG")) : 0;
-      auto         kern  = kron3d_kernel<C, HASB, BSYM, ACCUM>;
+      auto kern = (C::NXW > 0) ? kron3d_ws_kernel<C, HASB, BSYM, ACCUM> : kron3d_kernel<C, HASB, BSYM, ACCUM>;
       const size_t smem  = smem_bytes<C, HASB>();
       GDM_REQUIRE(smem <= 227 * 1024, GDM_ERR_INTERNAL, "fused kernel configuration exceeds the shared memory of an SM");
       static bool  attr_set = false;
