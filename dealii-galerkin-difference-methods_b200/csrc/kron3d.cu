@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <map>
+#include <type_traits>
 
 #include "gdm_internal.h"
 
@@ -76,6 +77,7 @@ namespace gdm
     template <int P_, int TX_, int RY_, int NRB_, int RX_, int STAGES_, int MINB_, int NXW_ = 0>
     struct Cfg
     {
+      static constexpr bool V4 = false, V5 = false, V6 = false, V7 = false;
       static constexpr int P = P_, TX = TX_, RY = RY_, NRB = NRB_, RX = RX_, STAGES = STAGES_, MINB = MINB_;
       static constexpr int NXW = NXW_; // > 0: warp-specialised kernel with NXW dedicated x-pass warps
       static constexpr int W       = 2 * P + 1;
@@ -114,6 +116,10 @@ namespace gdm
       const double *zsA, *zsB;                     // scatter rows [plane][2P+1], scale folded in
       double        Ax[P + 1], Bx[P + 1], Ay[P + 1], By[P + 1]; // interior taps by distance
       double        Az[2 * P + 1], Bz[2 * P + 1];               // interior scatter row, scale folded in
+      double        sigma;                                      // v4 tap split: sum_d alpha_d (0 without the split)
+      const double *zt;                                         // v4: scatter rows of the non-Toeplitz plane classes [class][field][W+1]
+      const int4   *segs;                                       // v5: work segments {tile x, tile y, z0, z1}
+      const int    *seg_ptr;                                    // v5: segments of CTA b are [seg_ptr[b], seg_ptr[b+1])
     };
 
     template <class C, bool HASB>
@@ -923,6 +929,11 @@ namespace gdm
         }
     }
 
+#include "kron3d_v4.cuh"
+#include "kron3d_v5.cuh"
+#include "kron3d_v6.cuh"
+#include "kron3d_v7.cuh"
+
     // ------------------------------------------------------------------ host side
     typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -951,55 +962,64 @@ namespace gdm
       int      wz0 = -1, wz1 = -1, wlz = 0; // output-plane sub-window of the next launch (-1: whole slab)
       bool     use_comm_stream = false;     // launch on the communication stream (slab faces, behind the ghost import)
       double  *d_zsA = nullptr, *d_zsB = nullptr;
+      // v4: effective B tables (B, or R = B - alpha A with the tap split), plane-class scatter table
+      bool                rsplit = false;
+      double              sigma  = 0.0;
+      int                 kz_lo = 0, kz_hi = 0;
+      std::vector<double> hBe[3];
+      double             *d_Be[2] = {nullptr, nullptr};
+      double             *d_zt    = nullptr;
+      // v5: balanced partitions per output-plane window (cz0, cz1) -> device segment lists
+      struct Partition
+      {
+        int   grid = 0;
+        int4 *d_segs = nullptr;
+        int  *d_ptr  = nullptr;
+      };
+      std::map<std::pair<int, int>, Partition> parts;
       std::map<const void *, CUtensorMap> maps;
       ~FusedPlan()
       {
         cudaFree(d_zsA);
         cudaFree(d_zsB);
+        cudaFree(d_Be[0]);
+        cudaFree(d_Be[1]);
+        cudaFree(d_zt);
+        for (auto &kv : parts)
+          {
+            cudaFree(kv.second.d_segs);
+            cudaFree(kv.second.d_ptr);
+          }
       }
     };
 
     // available tile configurations (selected per degree; GDM_FUSED_CFG=<id> overrides for tuning)
     //                      id        P  TX RY NRB RX ST MINB
 #define GDM_FUSED_CONFIGS(X)            \
+  /* v3 (split phase barrier):  P  TX RY NRB RX ST MINB [NXW] */ \
   X(0, Cfg<1, 32, 8, 4, 8, 3, 2>)       \
-  X(1, Cfg<3, 32, 7, 6, 8, 3, 2>)       \
   X(2, Cfg<5, 32, 4, 6, 8, 3, 2>)       \
-  X(3, Cfg<3, 32, 8, 4, 8, 2, 3>)       \
-  X(4, Cfg<3, 64, 7, 6, 8, 3, 1>)       \
-  X(5, Cfg<3, 32, 6, 7, 8, 3, 2>)       \
   X(6, Cfg<3, 32, 4, 8, 8, 3, 2>)       \
-  X(7, Cfg<3, 64, 4, 8, 8, 3, 1>)       \
-  X(8, Cfg<3, 32, 7, 6, 8, 2, 2>)       \
-  X(9, Cfg<3, 32, 7, 6, 8, 4, 2>)       \
-  X(10, Cfg<3, 32, 5, 8, 8, 3, 2>)      \
-  X(11, Cfg<3, 32, 8, 4, 8, 3, 2>)      \
-  X(12, Cfg<3, 32, 4, 8, 8, 2, 2>)      \
-  X(13, Cfg<3, 64, 8, 4, 8, 2, 1>)      \
   X(14, Cfg<3, 32, 4, 8, 4, 3, 2>)      \
   X(15, Cfg<5, 32, 4, 8, 8, 3, 1>)      \
-  X(16, Cfg<5, 32, 4, 8, 8, 3, 2>)      \
-  X(17, Cfg<3, 32, 4, 8, 4, 2, 2>)      \
-  X(18, Cfg<3, 32, 4, 8, 4, 4, 2>)      \
-  X(19, Cfg<3, 32, 6, 4, 8, 3, 3>)      \
-  X(20, Cfg<3, 32, 4, 4, 4, 3, 4>)      \
-  X(21, Cfg<3, 32, 2, 8, 4, 3, 3>)      \
-  X(22, Cfg<3, 32, 2, 8, 8, 3, 3>)      \
-  X(23, Cfg<3, 32, 2, 8, 4, 2, 4>)      \
-  X(24, Cfg<3, 64, 2, 8, 8, 3, 2>)      \
-  X(25, Cfg<3, 32, 8, 8, 8, 3, 1>)      \
-  X(26, Cfg<3, 32, 6, 8, 8, 3, 1>)      \
-  X(27, Cfg<3, 64, 4, 8, 8, 3, 1>)      \
-  X(28, Cfg<3, 64, 4, 8, 4, 3, 1>)      \
-  X(29, Cfg<3, 32, 4, 8, 4, 3, 1>)      \
-  X(30, Cfg<3, 32, 4, 16, 4, 3, 1>)     \
-  X(31, Cfg<3, 32, 4, 12, 4, 3, 1>)     \
-  X(32, Cfg<3, 32, 4, 16, 8, 3, 1>)     \
   X(40, Cfg<3, 32, 4, 8, 4, 3, 1, 4>)   \
-  X(41, Cfg<3, 32, 4, 8, 8, 3, 1, 4>)   \
-  X(42, Cfg<3, 32, 4, 8, 4, 4, 1, 4>)   \
-  X(43, Cfg<3, 32, 6, 8, 4, 3, 1, 4>)   \
-  X(44, Cfg<3, 32, 4, 8, 4, 3, 1, 8>)
+  /* v4 (lean, one CTA barrier per plane, tap split): P RY NRB RX ST MINB */ \
+  X(100, Cfg4<3, 4, 8, 4, 3, 2>)        \
+  X(101, Cfg4<1, 4, 8, 4, 3, 2>)        \
+  X(102, Cfg4<5, 4, 8, 4, 3, 2>)        \
+  X(103, Cfg4<3, 4, 8, 8, 3, 2>)        \
+  X(109, Cfg4<1, 8, 4, 4, 3, 2>)        \
+  /* v5 (mbarrier rings, tile-major balanced partition) */ \
+  X(200, Cfg5<3, 4, 8, 4, 3, 2>)        \
+  /* v6 (register resident, warps independent):  P RY NW ST MINB */ \
+  X(300, Cfg6<3, 8, 4, 4, 3>)           \
+  X(301, Cfg6<1, 8, 4, 4, 4>)           \
+  X(304, Cfg6<3, 8, 4, 4, 2>)           \
+  X(312, Cfg6<3, 8, 4, 8, 2>)           \
+  /* v7 (v4 + aligned balanced partition): P RY NRB RX ST MINB */ \
+  X(400, Cfg7<3, 4, 8, 4, 3, 2>)        \
+  X(401, Cfg7<1, 4, 8, 4, 3, 2>)        \
+  X(402, Cfg7<5, 4, 8, 4, 3, 2>)
 
     template <class F>
     void with_config(int id, F &&f)
@@ -1019,7 +1039,20 @@ namespace gdm
 
     int default_config(int p)
     {
-      int id = (p == 1) ? 0 : (p == 3 ? 14 : 2);
+      // defaults by measurement on B200 (profiles/r1/ops_families.log): p=1 -> v4, p=3 and p=5 -> v3.
+      // GDM_FUSED_FAMILY=3|4|6|7 selects a kernel family for every degree, GDM_FUSED_CFG=<id> one configuration.
+      int id = (p == 1) ? 101 : (p == 3 ? 14 : 15);
+      if (const char *fam = std::getenv("GDM_FUSED_FAMILY"))
+        {
+          if (fam[0] == '3')
+            id = (p == 1) ? 0 : (p == 3 ? 14 : 15);
+          else if (fam[0] == '4')
+            id = (p == 1) ? 101 : (p == 3 ? 100 : 102);
+          else if (fam[0] == '6' && p != 5)
+            id = (p == 1) ? 301 : 304;
+          else if (fam[0] == '7')
+            id = (p == 1) ? 401 : (p == 3 ? 400 : 402);
+        }
       if (const char *env = std::getenv("GDM_FUSED_CFG"))
         {
           const int e = atoi(env);
@@ -1037,18 +1070,20 @@ namespace gdm
     }
 
     template <class C>
-    void fill_interior(const Operator &op, KArgs<C::P> &a)
+    void fill_interior(const Operator &op, const FusedPlan &plan, KArgs<C::P> &a)
     {
       constexpr int P = C::P, W = C::W;
       const Layout &L = op.sys->L;
+      // B tables seen by the kernel: the v4 kernels may run on R = B - alpha A (tap split)
+      const std::vector<double> *hB = C::V4 ? plan.hBe : op.hB;
       // any interior (Toeplitz) row: P+1 is interior because N >= 2P+2 is required
       const int ix = P + 1, iy = P + 1;
       for (int d = 0; d <= P; ++d)
         {
           a.Ax[d] = op.hA[0][(size_t)ix * W + P + d];
           a.Ay[d] = op.hA[1][(size_t)iy * W + P + d];
-          a.Bx[d] = op.has_B ? op.hB[0][(size_t)ix * W + P + d] : 0.0;
-          a.By[d] = op.has_B ? op.hB[1][(size_t)iy * W + P + d] : 0.0;
+          a.Bx[d] = op.has_B ? hB[0][(size_t)ix * W + P + d] : 0.0;
+          a.By[d] = op.has_B ? hB[1][(size_t)iy * W + P + d] : 0.0;
         }
       // interior scatter row of z: zs[k][j] = scale * T_z[k - P + j][2P - j] with all rows Toeplitz,
       // valid for input planes whose 2P+1 target rows are interior: P < k - P and k + P < N_z - P (global)
@@ -1070,7 +1105,7 @@ namespace gdm
               for (int j = 0; j < W; ++j)
                 {
                   a.Az[j] = op.desc.scale * op.hA[2][(size_t)local_interior * W + (2 * P - j)];
-                  a.Bz[j] = op.has_B ? op.desc.scale * op.hB[2][(size_t)local_interior * W + (2 * P - j)] : 0.0;
+                  a.Bz[j] = op.has_B ? op.desc.scale * hB[2][(size_t)local_interior * W + (2 * P - j)] : 0.0;
                 }
               a.kz_lo = std::max(0, 2 * P + 1 - L.loc0);
               a.kz_hi = std::min(L.ln[2], L.N[2] - 2 * P - L.loc0);
@@ -1079,6 +1114,159 @@ namespace gdm
             }
         }
       (void)iz;
+    }
+
+    // Static partition of the (tile, plane) work of the output window [cz0, cz1) into at most `slots` CTAs.
+    // A CTA costs its planes plus 2P ramp planes per segment.
+    //  * linear sweep (v5, and the rest of v7): contiguous shares of the tile-major work list; a share that would end
+    //    within min_seg planes of a tile column's end is snapped to it;
+    //  * aligned part (v7): m = slots / tiles full segments per tile column, every column cut at the same planes so
+    //    that neighbouring tiles stream through the same planes at the same time (their halos meet in L2); the planes
+    //    above m L are shared among the spare slots by the sweep.  L is chosen by direct search: minimise the cost of
+    //    the most expensive CTA.
+    struct PartitionPlan
+    {
+      std::vector<int4> segs;
+      std::vector<int>  ptr;
+      int64_t           max_cost = 0;
+      int               zl       = 0;
+    };
+
+    // sweep planes [zl, cz1) of all tiles over at most `slots` CTAs, appending to pp; returns false if it does not fit
+    inline void sweep_partition(PartitionPlan &pp, int tiles, int tiles_x, int zl, int cz1, int slots, int P)
+    {
+      const int     min_seg = 2 * P;
+      const int     nz      = cz1 - zl;
+      if (nz <= 0)
+        return;
+      const int64_t work = (int64_t)tiles * nz;
+      const int     G    = (int)std::max<int64_t>(1, std::min<int64_t>(slots, work / (2 * P)));
+      int64_t       T    = std::max<int64_t>((work + (int64_t)2 * P * (G + tiles) + G - 1) / G, 4 * P);
+      const size_t  segs_fixed = pp.segs.size(), ptr_fixed = pp.ptr.size();
+      for (int attempt = 0;; ++attempt)
+        {
+          pp.segs.resize(segs_fixed);
+          pp.ptr.resize(ptr_fixed);
+          int64_t c = 0, cmax = 0;
+          for (int t = 0; t < tiles; ++t)
+            {
+              int z = zl;
+              while (z < cz1)
+                {
+                  const int64_t room = T - c - 2 * P;
+                  if (room < std::min(min_seg, cz1 - z) && c > 0)
+                    {
+                      pp.ptr.push_back((int)pp.segs.size());
+                      cmax = std::max(cmax, c);
+                      c    = 0;
+                      continue;
+                    }
+                  int       take = (int)std::min<int64_t>(cz1 - z, std::max<int64_t>(room, 1));
+                  const int rem  = cz1 - z - take;
+                  if (rem > 0 && rem < min_seg)
+                    take = (take - (min_seg - rem) >= min_seg) ? take - (min_seg - rem) : cz1 - z;
+                  pp.segs.push_back(make_int4(t % tiles_x, t / tiles_x, z, z + take));
+                  c += take + 2 * P;
+                  z += take;
+                }
+            }
+          if (c > 0)
+            {
+              pp.ptr.push_back((int)pp.segs.size());
+              cmax = std::max(cmax, c);
+            }
+          if ((int)(pp.ptr.size() - ptr_fixed) <= slots || attempt > 400)
+            {
+              pp.max_cost = std::max(pp.max_cost, cmax);
+              return;
+            }
+          T += std::max<int64_t>(1, T / 64);
+        }
+    }
+
+    inline PartitionPlan make_partition(bool aligned, int tiles, int tiles_x, int cz0, int cz1, int slots, int P, int forced_L)
+    {
+      const int min_seg = 2 * P;
+      const int nzw     = cz1 - cz0;
+      auto      build   = [&](int L) {
+        PartitionPlan pp;
+        pp.ptr.assign(1, 0);
+        pp.zl     = cz0;
+        int spare = slots;
+        if (L > 0)
+          {
+            const int m = slots / tiles;
+            for (int c = 0; c < m; ++c)
+              {
+                const int z0 = cz0 + c * L, z1 = std::min(cz1, z0 + L);
+                if (z0 >= z1)
+                  break;
+                for (int t = 0; t < tiles; ++t)
+                  {
+                    pp.segs.push_back(make_int4(t % tiles_x, t / tiles_x, z0, z1));
+                    pp.ptr.push_back((int)pp.segs.size());
+                  }
+                pp.max_cost = std::max<int64_t>(pp.max_cost, z1 - z0 + 2 * P);
+                pp.zl       = z1;
+              }
+            spare = std::max(1, slots - (int)pp.ptr.size() + 1);
+          }
+        sweep_partition(pp, tiles, tiles_x, pp.zl, cz1, spare, P);
+        return pp;
+      };
+      if (!aligned || slots < tiles || nzw < 4 * min_seg)
+        return build(0);
+      const int m    = slots / tiles;
+      const int Lmax = (nzw + m - 1) / m;
+      if (forced_L > 0)
+        return build(std::min(std::max(forced_L, min_seg), Lmax));
+      PartitionPlan best = build(Lmax);
+      if (slots - m * tiles > 0)
+        for (int L = Lmax - 1; L >= std::max(min_seg, Lmax / 2); --L)
+          {
+            if (nzw - m * L < min_seg)
+              continue;
+            PartitionPlan pp = build(L);
+            if ((int)pp.ptr.size() - 1 <= slots && pp.max_cost < best.max_cost)
+              best = std::move(pp);
+          }
+      return best;
+    }
+
+    template <class C>
+    const FusedPlan::Partition &get_partition(Context &ctx, FusedPlan &plan, int cz0, int cz1)
+    {
+      const auto key = std::make_pair(cz0, cz1);
+      auto       it  = plan.parts.find(key);
+      if (it != plan.parts.end())
+        return it->second;
+      if (plan.parts.size() > 256)
+        {
+          GDM_CUDA_CHECK(cudaDeviceSynchronize());
+          for (auto &kv : plan.parts)
+            {
+              cudaFree(kv.second.d_segs);
+              cudaFree(kv.second.d_ptr);
+            }
+          plan.parts.clear();
+        }
+      const int tiles = std::max(1, plan.tiles_x * plan.tiles_y);
+      int       slots = ctx.sm_count * C::MINB;
+      if (const char *env = std::getenv("GDM_FUSED_SLOTS"))
+        slots = std::max(1, atoi(env));
+      const char         *envL = std::getenv("GDM_FUSED_L");
+      const PartitionPlan pp   = make_partition(C::V7, tiles, plan.tiles_x, cz0, cz1, slots, C::P, envL ? atoi(envL) : 0);
+      FusedPlan::Partition part;
+      part.grid = (int)pp.ptr.size() - 1;
+      GDM_CUDA_CHECK(cudaMalloc(&part.d_segs, std::max<size_t>(1, pp.segs.size()) * sizeof(int4)));
+      GDM_CUDA_CHECK(cudaMalloc(&part.d_ptr, pp.ptr.size() * sizeof(int)));
+      GDM_CUDA_CHECK(cudaMemcpy(part.d_segs, pp.segs.data(), pp.segs.size() * sizeof(int4), cudaMemcpyHostToDevice));
+      GDM_CUDA_CHECK(cudaMemcpy(part.d_ptr, pp.ptr.data(), pp.ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+      GDM_CUDA_CHECK(cudaDeviceSynchronize());
+      if (std::getenv("GDM_FUSED_VERBOSE"))
+        fprintf(stderr, "[gdm] fused partition: planes [%d, %d) (aligned up to %d), %d tiles -> %d CTAs, %zu segments, longest CTA %lld planes\n",
+                cz0, cz1, pp.zl, tiles, part.grid, pp.segs.size(), (long long)pp.max_cost);
+      return plan.parts.emplace(key, part).first->second;
     }
 
     template <class C, bool HASB, int BSYM, bool ACCUM>
@@ -1105,26 +1293,86 @@ namespace gdm
       a.lz         = (plan.wz0 >= 0 && plan.wlz > 0) ? plan.wlz : plan.lz;
       a.nz_local   = L.ln[2];
       a.tabAx      = op.dA[0];
-      a.tabBx      = op.dB[0];
+      a.tabBx      = (C::V4 && op.has_B) ? plan.d_Be[0] : op.dB[0];
       a.tabAy      = op.dA[1];
-      a.tabBy      = op.dB[1];
+      a.tabBy      = (C::V4 && op.has_B) ? plan.d_Be[1] : op.dB[1];
       a.zsA        = plan.d_zsA;
       a.zsB        = plan.d_zsB;
-      fill_interior<C>(op, a);
+      a.sigma      = plan.sigma;
+      a.zt         = plan.d_zt;
+      a.segs       = nullptr;
+      a.seg_ptr    = nullptr;
+      fill_interior<C>(op, plan, a);
       a.dbg = std::getenv("GDM_FUSED_DBG") ? atoi(std::getenv("GDM_FUSED_DBG")) : 0;
-      auto kern = (C::NXW > 0) ? kron3d_ws_kernel<C, HASB, BSYM, ACCUM> : kron3d_kernel<C, HASB, BSYM, ACCUM>;
-      const size_t smem  = smem_bytes<C, HASB>();
+      void (*kern)(const CUtensorMap, const KArgs<C::P>) = nullptr;
+      size_t smem = 0;
+      int v5_grid = -1;
+      if constexpr (C::V7)
+        {
+          constexpr int MODE = !HASB ? 0 : (BSYM > 0 ? 1 : 2);
+          if constexpr (MODE == 1)
+            kern = plan.rsplit ? kron3d_v7_kernel<C, 1, true, ACCUM> : kron3d_v7_kernel<C, 1, false, ACCUM>;
+          else
+            kern = kron3d_v7_kernel<C, MODE, false, ACCUM>;
+          smem = smem_bytes_v7<C, HASB>();
+          if (a.cz1 > a.cz0)
+            {
+              const FusedPlan::Partition &part = get_partition<C>(ctx, plan, a.cz0, a.cz1);
+              a.segs                           = part.d_segs;
+              a.seg_ptr                        = part.d_ptr;
+              v5_grid                          = part.grid;
+            }
+        }
+      else if constexpr (C::V6)
+        {
+          constexpr int MODE = !HASB ? 0 : (BSYM > 0 ? 1 : 2);
+          if constexpr (MODE == 1)
+            kern = plan.rsplit ? kron3d_v6_kernel<C, 1, true, ACCUM> : kron3d_v6_kernel<C, 1, false, ACCUM>;
+          else
+            kern = kron3d_v6_kernel<C, MODE, false, ACCUM>;
+          smem = smem_bytes_v6<C>();
+        }
+      else if constexpr (C::V5)
+        {
+          constexpr int MODE = !HASB ? 0 : (BSYM > 0 ? 1 : 2);
+          if constexpr (MODE == 1)
+            kern = plan.rsplit ? kron3d_v5_kernel<C, 1, true, ACCUM> : kron3d_v5_kernel<C, 1, false, ACCUM>;
+          else
+            kern = kron3d_v5_kernel<C, MODE, false, ACCUM>;
+          smem = smem_bytes_v5<C, HASB>();
+          if (a.cz1 > a.cz0)
+            {
+              const FusedPlan::Partition &part = get_partition<C>(ctx, plan, a.cz0, a.cz1);
+              a.segs                           = part.d_segs;
+              a.seg_ptr                        = part.d_ptr;
+              v5_grid                          = part.grid;
+            }
+        }
+      else if constexpr (C::V4)
+        {
+          constexpr int MODE = !HASB ? 0 : (BSYM > 0 ? 1 : 2);
+          if constexpr (MODE == 1)
+            kern = plan.rsplit ? kron3d_v4_kernel<C, 1, true, ACCUM> : kron3d_v4_kernel<C, 1, false, ACCUM>;
+          else
+            kern = kron3d_v4_kernel<C, MODE, false, ACCUM>;
+          smem = smem_bytes_v4<C, HASB>();
+        }
+      else
+        {
+          kern = (C::NXW > 0) ? kron3d_ws_kernel<C, HASB, BSYM, ACCUM> : kron3d_kernel<C, HASB, BSYM, ACCUM>;
+          smem = smem_bytes<C, HASB>();
+        }
       GDM_REQUIRE(smem <= 227 * 1024, GDM_ERR_INTERNAL, "fused kernel configuration exceeds the shared memory of an SM");
-      static bool  attr_set = false;
-      if (!attr_set)
+      static std::map<const void *, bool> attr_set;
+      if (!attr_set[(const void *)kern])
         {
           GDM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          attr_set = true;
+          attr_set[(const void *)kern] = true;
         }
       if (a.cz1 <= a.cz0)
         return;
       const int n_chunks = (a.cz1 - a.cz0 + a.lz - 1) / a.lz;
-      const int grid     = plan.tiles_x * plan.tiles_y * n_chunks;
+      const int grid     = (C::V5 || C::V7) ? v5_grid : plan.tiles_x * plan.tiles_y * n_chunks;
       if (grid <= 0)
         return;
       kern<<<grid, C::THREADS, smem, plan.use_comm_stream ? ctx.comm_stream : ctx.stream>>>(map, a);
@@ -1238,6 +1486,96 @@ namespace gdm
     GDM_CUDA_CHECK(cudaMalloc(&plan->d_zsB, zsB.size() * sizeof(double)));
     GDM_CUDA_CHECK(cudaMemcpy(plan->d_zsA, zsA.data(), zsA.size() * sizeof(double), cudaMemcpyHostToDevice));
     GDM_CUDA_CHECK(cudaMemcpy(plan->d_zsB, zsB.data(), zsB.size() * sizeof(double), cudaMemcpyHostToDevice));
+
+    // ---- v4 kernels: effective B tables (tap split), plane-class scatter table
+    bool is_v4 = false;
+    with_config(plan->cfg, [&](auto c) { is_v4 = decltype(c)::V4; });
+    if (!is_v4)
+      return;
+    // Toeplitz z planes [kz_lo, kz_hi) (same rule as fill_interior) and one local interior row of direction 2
+    int local_interior = -1;
+    for (int r = 0; r < L.ln[2]; ++r)
+      if (r + L.loc0 > P && r + L.loc0 < L.N[2] - P)
+        {
+          local_interior = r;
+          break;
+        }
+    plan->kz_lo = plan->kz_hi = 0;
+    if (L.N[2] >= 4 * P + 2 && local_interior >= 0)
+      {
+        plan->kz_lo = std::max(0, 2 * P + 1 - L.loc0);
+        plan->kz_hi = std::max(plan->kz_lo, std::min(L.ln[2], L.N[2] - 2 * P - L.loc0));
+      }
+    const int zrows = 2 * W;
+    GDM_REQUIRE(plan->kz_lo + (L.ln[2] - plan->kz_hi) <= zrows, GDM_ERR_INTERNAL, "fused v4: too many non-Toeplitz planes");
+    for (int d = 0; d < 3; ++d)
+      plan->hBe[d] = op.hB[d];
+    plan->rsplit = false;
+    plan->sigma  = 0.0;
+    const char *env_split = std::getenv("GDM_FUSED_RSPLIT");
+    if (op.has_B && op.b_symmetry > 0 && !(env_split && env_split[0] == '0'))
+      {
+        // K_d = alpha_d M_d + R_d with alpha_d = (outer tap of K_d) / (outer tap of M_d): R_d has zero outer taps on
+        // Toeplitz rows; the identity holds row by row, so the one-sided and masked rows need no special treatment
+        double alpha[3] = {0, 0, 0};
+        bool   ok       = true;
+        for (int d = 0; d < 3 && ok; ++d)
+          {
+            const int row = (d == 2) ? local_interior : P + 1;
+            if (row < 0 || L.N[d] < 2 * P + 2)
+              {
+                ok = false;
+                break;
+              }
+            const double m = op.hA[d][(size_t)row * W + 2 * P], k = op.hB[d][(size_t)row * W + 2 * P];
+            if (m == 0.0 || op.hA[d][(size_t)row * W] != m || op.hB[d][(size_t)row * W] != k)
+              ok = false;
+            alpha[d] = ok ? k / m : 0.0;
+          }
+        if (ok)
+          {
+            for (int d = 0; d < 3; ++d)
+              {
+                const int rows = (int)(op.hB[d].size() / W);
+                for (int r = 0; r < rows; ++r)
+                  {
+                    for (int t = 0; t < W; ++t)
+                      plan->hBe[d][(size_t)r * W + t] = op.hB[d][(size_t)r * W + t] - alpha[d] * op.hA[d][(size_t)r * W + t];
+                    const int gr = r + (d == 2 ? L.loc0 : 0); // global row
+                    if (gr > P && gr < L.N[d] - P)
+                      plan->hBe[d][(size_t)r * W] = plan->hBe[d][(size_t)r * W + 2 * P] = 0.0;
+                  }
+              }
+            plan->rsplit = true;
+            plan->sigma  = alpha[0] + alpha[1] + alpha[2];
+          }
+      }
+    if (op.has_B)
+      for (int d = 0; d < 2; ++d)
+        {
+          GDM_CUDA_CHECK(cudaMalloc(&plan->d_Be[d], plan->hBe[d].size() * sizeof(double)));
+          GDM_CUDA_CHECK(
+            cudaMemcpy(plan->d_Be[d], plan->hBe[d].data(), plan->hBe[d].size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    const int           wz = W + 1;
+    std::vector<double> zt((size_t)zrows * 2 * wz, 0.0);
+    for (int c = 0; c < zrows; ++c)
+      {
+        const int k = (c < plan->kz_lo) ? c : plan->kz_hi + (c - plan->kz_lo);
+        if (k < 0 || k >= L.ln[2])
+          continue;
+        for (int j = 0; j < W; ++j)
+          {
+            const int r = k - P + j;
+            if (r < 0 || r >= L.ln[2])
+              continue;
+            zt[(size_t)(c * 2 + 0) * wz + j] = op.desc.scale * op.hA[2][(size_t)r * W + (2 * P - j)];
+            if (op.has_B)
+              zt[(size_t)(c * 2 + 1) * wz + j] = op.desc.scale * plan->hBe[2][(size_t)r * W + (2 * P - j)];
+          }
+      }
+    GDM_CUDA_CHECK(cudaMalloc(&plan->d_zt, zt.size() * sizeof(double)));
+    GDM_CUDA_CHECK(cudaMemcpy(plan->d_zt, zt.data(), zt.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
 
   void fused_plan_destroy(Operator &op)
@@ -1263,6 +1601,10 @@ namespace gdm
     FusedPlan    &plan = *static_cast<FusedPlan *>(op.fused);
     Context      &ctx  = *op.sys->ctx;
     const Layout &L    = op.sys->L;
+    bool is_v5 = false;
+    with_config(plan.cfg, [&](auto c) { is_v5 = decltype(c)::V5 || decltype(c)::V7; });
+    if (is_v5)
+      plan.tune = false; // v5 partitions the work statically, there is no chunk length to tune
     if (plan.tune)
       {
         // FFTW-style plan refinement: time a few chunk counts around one/two/three CTAs per slot on
