@@ -252,10 +252,24 @@ def run_ours(args):
         return
     peak, which = peaks()
     achieved = ALG_BYTES_PER_DOF * (total_dofs / world) / (ms / args.steps * 1e-3) / 1e9
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+    # (profiles/r1/traffic.json; only valid for the BASELINE grid on one GPU)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1", "traffic.json")
+    if os.path.exists(tpath) and world == 1 and n == 256 and p == 3:
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    # second roof: FP64 pipe.  43 FP64 instructions per DoF in sum-factorised form (x 11, y 18, z 14);
+    # peak = measured DFMA issue rate (profiles/microbench/microbench2.json: 33.8 TFLOP/s = 16.9 T instr-lanes/s)
+    fp64_ops_per_dof, fp64_peak = 43.0, 16.9e12
+    fp64 = {"bound": "fp64", "achieved": fp64_ops_per_dof * (total_dofs / world) / (ms / args.steps * 1e-3) / 1e12,
+            "peak": fp64_peak / 1e12, "unit": "T FP64 instr-lanes/s", "ops_per_dof": fp64_ops_per_dof}
+    fp64["frac"] = fp64["achieved"] / fp64["peak"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)",
                 "kernel": "kron3d_kernel (fused TMA-staged tensor-product apply)" if A.kernel_used() == 2 else "generic band passes",
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_DOF * total_dofs / world,
+                "second_roof": fp64,
                 "note": "duration = CUDA-event time of the timed region / steps (includes the constrained-face kernels)"}
     base = cpu_csr_sample(args.cpu_cells, p, 10, 2) if world == 1 or True else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -670,6 +670,25 @@ int gdm_system_halo_plan(gdm_system_t sys, int32_t *plan10)
   GDM_CATCH
 }
 
+int gdm_fused_partition(int aligned, int tiles_x, int tiles_y, int z0, int z1, int slots, int fe_degree, int32_t *seg_ptr,
+                        int32_t cap_ptr, int32_t *segs4, int32_t cap_segs, int32_t *n_ctas, int32_t *n_segs)
+{
+  GDM_TRY
+  GDM_ARG(n_ctas);
+  GDM_ARG(n_segs);
+  std::vector<int> ptr, segs;
+  fused_partition_host(aligned != 0, tiles_x, tiles_y, z0, z1, slots, fe_degree, ptr, segs);
+  *n_ctas = (int32_t)ptr.size() - 1;
+  *n_segs = (int32_t)(segs.size() / 4);
+  GDM_REQUIRE(seg_ptr != nullptr && segs4 != nullptr && cap_ptr >= (int32_t)ptr.size() && cap_segs >= *n_segs,
+              GDM_ERR_INVALID, "partition buffers too small");
+  for (size_t i = 0; i < ptr.size(); ++i)
+    seg_ptr[i] = ptr[i];
+  for (size_t i = 0; i < segs.size(); ++i)
+    segs4[i] = segs[i];
+  GDM_CATCH
+}
+
 // -------------------------------------------------------------- constraints
 int gdm_constraints_create(gdm_system_t sys, gdm_constraints_t *out)
 {

@@ -221,6 +221,10 @@ namespace gdm
   void fused_apply(Operator &op, double *dst, const double *src, bool accumulate, bool exchange_ghosts = false);
   // output planes [z0, z1) only (local plane indices; no ghost import): building block of the pipelined host-buffer apply
   void fused_apply_window(Operator &op, double *dst, const double *src, int z0, int z1);
+  // host logic of the static work partition of the fused kernels (v5/v7): CTA b runs segments
+  // [seg_ptr[b], seg_ptr[b+1]) of segs4 = {tile x, tile y, z0, z1} x n
+  void fused_partition_host(bool aligned, int tiles_x, int tiles_y, int z0, int z1, int slots, int p, std::vector<int> &seg_ptr,
+                            std::vector<int> &segs4);
 
   // blas1.cu
   enum SumSlot

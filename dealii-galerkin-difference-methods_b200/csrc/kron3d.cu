@@ -1402,6 +1402,22 @@ namespace gdm
     }
   } // namespace
 
+  void fused_partition_host(bool aligned, int tiles_x, int tiles_y, int z0, int z1, int slots, int p, std::vector<int> &seg_ptr,
+                            std::vector<int> &segs4)
+  {
+    GDM_REQUIRE(tiles_x > 0 && tiles_y > 0 && z1 >= z0 && slots > 0 && p > 0, GDM_ERR_INVALID, "invalid partition request");
+    const PartitionPlan pp = make_partition(aligned, tiles_x * tiles_y, tiles_x, z0, z1, slots, p, 0);
+    seg_ptr                = pp.ptr;
+    segs4.clear();
+    for (const int4 &s : pp.segs)
+      {
+        segs4.push_back(s.x);
+        segs4.push_back(s.y);
+        segs4.push_back(s.z);
+        segs4.push_back(s.w);
+      }
+  }
+
   bool fused_supported(const Operator &op)
   {
     const Layout &L = op.sys->L;

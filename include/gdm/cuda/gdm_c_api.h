@@ -125,6 +125,15 @@ int      gdm_system_layout(gdm_system_t sys, gdm_layout_info *info);
  * direction): plan10 = {prev_rank, next_rank, send_lo_plane, send_lo_count, recv_lo_plane, recv_lo_count,
  * send_hi_plane, send_hi_count, recv_hi_plane, recv_hi_count}; ranks are -1 where there is no neighbour. */
 int      gdm_system_halo_plan(gdm_system_t sys, int32_t *plan10);
+/* Host logic of the fused kernels' static work partition (no device needed; exposed for tests and tools):
+ * the (tile, plane) work of output planes [z0, z1) of a tiles_x x tiles_y tile grid is split into at most `slots`
+ * CTAs; CTA b runs segments [seg_ptr[b], seg_ptr[b+1]) of segs4 = {tile x, tile y, z_begin, z_end} per segment.
+ * aligned != 0: every tile column is cut at the same planes (kron3d_v7), else tile-major linear sweep (kron3d_v5).
+ * Replaces the per-rank slab loop of the reference's cell iteration (system.h:703-761) inside one GPU.
+ * Returns GDM_ERR_INVALID if the capacities are too small; *n_ctas / *n_segs are always set. */
+int      gdm_fused_partition(int aligned, int tiles_x, int tiles_y, int z0, int z1, int slots, int fe_degree,
+                             int32_t *seg_ptr, int32_t cap_ptr, int32_t *segs4, int32_t cap_segs, int32_t *n_ctas,
+                             int32_t *n_segs);
 
 /* ----------------------------------------------------------- constraints */
 int gdm_constraints_create(gdm_system_t sys, gdm_constraints_t *c);

@@ -118,7 +118,10 @@ def test_cg_iteration_parity_with_oracle(lib, dim, p, reps, bc, pre):
     slack = max(1, octl.last_step() // 100)
     assert abs(ctl.last_step() - octl.last_step()) <= slack
     assert abs(ctl.initial_value() - octl.initial_value()) <= 1e-13 * octl.initial_value()
-    assert rel_err(sol.numpy(), xo) <= 1e-9
+    # Both iterates satisfy ||r|| < 1e-9 ||r0||; when the stopping iteration moves by one (see above) they differ by
+    # one CG update, i.e. by O(reduction * cond(P^-1 A)) relative -- 1e-9 only holds for identical counts.
+    tol = 1e-9 if ctl.last_step() == octl.last_step() else 1e-7
+    assert rel_err(sol.numpy(), xo) <= tol
 
 
 def test_advection_rk4_matches_oracle(lib):

@@ -7,7 +7,7 @@ timeout 200 python -m pytest tests/test_gpu_solvers.py -m gpu -q -k test_cg_iter
 grep -E "assert|last_step|passed|failed" gpurun_out/pytest_cgpar.log | head -20
 run() { r=$(env "$@" GDM_FUSED_VERBOSE=1 timeout 120 python bench.py --steps 50 --warmup 5 --quick 2>&1 | grep -E "gdm\]|value|rror" | tr '\n' ' '); echo "$* :: $r"; }
 {
-run GDM_FUSED_V4=0
+run GDM_FUSED_FAMILY=3
 run GDM_FUSED_CFG=100
 run GDM_FUSED_CFG=100 GDM_FUSED_RSPLIT=0
 run GDM_FUSED_CFG=103
