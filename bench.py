@@ -95,7 +95,8 @@ def cpu_csr_sample(n_cells, p, steps, warmup):
     """The reference's CPU path on a bounded sample: assembled CSR SpMV, all host cores."""
     import numpy as np
     import oracle as O
-    from oracle.csr_baseline import CsrOperator, num_threads
+    from oracle.csr_baseline import CsrOperator, num_threads, set_num_threads
+    set_num_threads(os.cpu_count() or 1)  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     s = O.System(3, p)
     s.subdivided_hyper_cube(n_cells)
     c = O.Constraints()
@@ -132,7 +133,7 @@ def run_reference(args):
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -203,8 +204,8 @@ def run_ours(args):
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "quick": True,
-                              "frac_of_hbm_roofline": ALG_BYTES_PER_DOF * value / world / peaks()[0], "n_gpus": world}))
+            emit({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "quick": True,
+                  "frac_of_hbm_roofline": ALG_BYTES_PER_DOF * value / world / peaks()[0], "n_gpus": world})
         return
     # ---- end to end through the host-buffer entry point (pinned host memory)
     e2e_steps = max(3, min(args.steps, 10))
@@ -235,6 +236,13 @@ def run_ours(args):
         b.set(1.0)
         con.set_zero(b)
         u = g.Vector(sys_)
+        # untimed warm-up solve: the first ncclAllReduce sets up its channels lazily (milliseconds)
+        wctl = g.ReductionControl(3, 1e-30, 1e-30)
+        try:
+            g.SolverCG(wctl).solve(A, u, b, g.PreconditionIdentity())
+        except g.NoConvergence:
+            pass
+        u.set(0.0)
         ctl = g.ReductionControl(args.cg_steps, 1e-30, 1e-30)
         barrier()
         e0.record()
@@ -283,10 +291,25 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_owned * 8, "d2h_bytes_per_step": n_owned * 8,
                     "steps": e2e_steps, "api": "gdm_operator_vmult_host (pinned host buffers)"},
             "gpu_launches": int(launches), "clocks": clocks, "cg": cg}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Print the one JSON line on the process's original stdout."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # native libraries (NCCL's version banner) write to fd 1: keep fd 1 for the JSON line only
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

@@ -1713,7 +1713,19 @@ namespace gdm
           }
       }
     else
-      with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
+      {
+        // Dirichlet faces (skipped by the tiles) and deal.II's constrained diagonal: disjoint outputs, so the small
+        // face kernel runs beside the tile kernel on the high-priority stream instead of after it (8 of 155 us)
+        GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_a, ctx.stream));
+        GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.comm_stream, ctx.ev_a, 0));
+        std::swap(ctx.stream, ctx.comm_stream);
+        launch_constrained_rows(ctx, L, op, dst, src, accumulate);
+        std::swap(ctx.stream, ctx.comm_stream);
+        GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_b, ctx.comm_stream));
+        with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
+        GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, ctx.ev_b, 0));
+        return;
+      }
     // Dirichlet faces (skipped by the tiles) and deal.II's constrained diagonal
     launch_constrained_rows(ctx, L, op, dst, src, accumulate);
   }

@@ -19,6 +19,13 @@
 #include <omp.h>
 #endif
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline uses all host cores explicitly */
+void gdm_oracle_set_num_threads(int n)
+{
+  if (n > 0)
+    omp_set_num_threads(n);
+}
+
 int gdm_oracle_num_threads(void)
 {
 #ifdef _OPENMP

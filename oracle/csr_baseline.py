@@ -103,3 +103,11 @@ class CsrOperator:
 
 def num_threads():
     return load().gdm_oracle_num_threads()
+
+
+def set_num_threads(n):
+    """Use n OpenMP threads (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib = load()
+    lib.gdm_oracle_set_num_threads.argtypes = [C.c_int]
+    lib.gdm_oracle_set_num_threads.restype = None
+    lib.gdm_oracle_set_num_threads(int(n))
