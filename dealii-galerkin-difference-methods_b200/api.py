@@ -418,6 +418,13 @@ class SparseMatrix:
     def vmult_add(self, dst, src):
         capi.check(self.lib.gdm_operator_vmult_add(self.h, dst.h, src.h))
 
+    def vmult_dot(self, dst, src):
+        """dst = A src; returns <src, dst> (all ranks).  Fused path: the dot product rides in the store epilogue."""
+        import ctypes as C
+        out = C.c_double()
+        capi.check(self.lib.gdm_operator_vmult_dot(self.h, dst.h, src.h, C.byref(out)))
+        return out.value
+
     Tvmult = vmult  # mass/stiffness are symmetric; advection operators expose the transpose as a separate kind
 
     def vmult_host(self, dst, src):

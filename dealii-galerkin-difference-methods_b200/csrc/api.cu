@@ -1090,6 +1090,28 @@ int gdm_operator_vmult(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src)
   GDM_CATCH
 }
 
+int gdm_operator_vmult_dot(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src, double *src_dot_dst)
+{
+  GDM_TRY
+  GDM_ARG(op);
+  GDM_ARG(dst);
+  GDM_ARG(src);
+  GDM_ARG(src_dot_dst);
+  Operator &o   = op->impl;
+  Context  &ctx = *o.sys->ctx;
+  GDM_REQUIRE(dst->impl.sys == o.sys && src->impl.sys == o.sys, GDM_ERR_INVALID, "vector/operator system mismatch");
+  GDM_REQUIRE(dst->impl.d != src->impl.d, GDM_ERR_INVALID, "vmult: dst and src must not alias");
+  if (o.kernel_used == GDM_KERNEL_FUSED && !o.csr && fused_supports_dot(o))
+    fused_apply(o, dst->impl.d, src->impl.d, false, true, SUM_DOT); // dot product in the store epilogue
+  else
+    {
+      operator_apply(o, dst->impl, src->impl, false);
+      blas_dot(ctx, src->impl.d + o.sys->L.own_off, dst->impl.d + o.sys->L.own_off, o.sys->L.own_len, SUM_DOT);
+    }
+  *src_dot_dst = read_sum(ctx, SUM_DOT, true);
+  GDM_CATCH
+}
+
 int gdm_operator_vmult_add(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src)
 {
   GDM_TRY

@@ -249,6 +249,35 @@ namespace gdm
     GDM_CUDA_CHECK(cudaGetLastError());
   }
 
+  namespace
+  {
+    // fixed-order sum of n partials: thread t adds elements t, t+1024, ...; then a fixed binary tree
+    __global__ void sum_partials_kernel(const double *__restrict__ partials, int n, double *__restrict__ out)
+    {
+      __shared__ double sh[1024];
+      double            t = 0.0;
+      for (int i = threadIdx.x; i < n; i += 1024)
+        t += partials[i];
+      sh[threadIdx.x] = t;
+      __syncthreads();
+      for (int o = 512; o > 0; o >>= 1)
+        {
+          if ((int)threadIdx.x < o)
+            sh[threadIdx.x] += sh[threadIdx.x + o];
+          __syncthreads();
+        }
+      if (threadIdx.x == 0)
+        *out = sh[0];
+    }
+  } // namespace
+
+  void blas_sum_partials(Context &ctx, const double *partials, int n, int slot)
+  {
+    sum_partials_kernel<<<1, 1024, 0, ctx.stream>>>(partials, n, ctx.d_sums + slot);
+    ctx.launches++;
+    GDM_CUDA_CHECK(cudaGetLastError());
+  }
+
   void blas_absmax(Context &ctx, const double *a, int64_t n, int slot)
   {
     const int grid = reduce_grid(ctx, std::max<int64_t>(n, 1));

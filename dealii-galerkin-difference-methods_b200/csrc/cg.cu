@@ -10,6 +10,7 @@
 // every few iterations, so the stream never drains inside a batch.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "gdm_internal.h"
 
@@ -118,6 +119,9 @@ namespace gdm
     pv.d    = w.p;
     pv.owns = false;
 
+    // p . A p inside the store epilogue of the tile kernel (no separate 16 B/DoF pass); GDM_CG_FUSED_DOT=0 disables
+    const char *env_fd    = std::getenv("GDM_CG_FUSED_DOT");
+    const bool  fused_dot = A.kernel_used == GDM_KERNEL_FUSED && !A.csr && fused_supports_dot(A) && !(env_fd && env_fd[0] == '0');
     unsigned it    = 0;
     unsigned batch = 4;
     while (done == 0)
@@ -128,8 +132,13 @@ namespace gdm
         while (it < end)
           {
             ++it;
-            apply(A, w.q, w.p);
-            blas_dot(ctx, w.p + off, w.q + off, n, SUM_PQ);
+            if (fused_dot)
+              fused_apply(A, w.q, w.p, false, true, SUM_PQ); // q = A p and p.q in one pass over p and q
+            else
+              {
+                apply(A, w.q, w.p);
+                blas_dot(ctx, w.p + off, w.q + off, n, SUM_PQ);
+              }
             allreduce(SUM_PQ, 1);
             cg_launch_update(ctx, x.d + off, w.r + off, w.p + off, w.q + off, dinv, n, status.p, cg_rz_slot(it - 1),
                              cg_rr_slot(it), cg_rz_slot(it));

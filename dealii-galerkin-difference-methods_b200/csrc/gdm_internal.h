@@ -202,8 +202,13 @@ namespace gdm
     bool          owned_only = false; // restrict to owned planes of pdim
   };
   void launch_band_pass(Context &ctx, const Layout &L, const bool periodic[3], const BandPassArgs &a);
-  void launch_constrained_rows(Context &ctx, const Layout &L, const Operator &op, double *dst,
-                               const double *src, bool accumulate, int plane_lo = -1, int plane_hi = -1);
+  // returns the number of thread blocks launched; dot_partials != nullptr: block b also writes the sum of
+  // src * dst over its rows to dot_partials[b] (fused dot product of the apply)
+  int  launch_constrained_rows(Context &ctx, const Layout &L, const Operator &op, double *dst,
+                               const double *src, bool accumulate, int plane_lo = -1, int plane_hi = -1,
+                               double *dot_partials = nullptr);
+  // upper bound of the blocks launch_constrained_rows uses (to size partial buffers)
+  int  constrained_rows_max_blocks(const Layout &L);
   void launch_csr_overlay(Context &ctx, const CsrOverlay &csr, double *dst, const double *src,
                           bool accumulate);
   void launch_periodic_copy(Context &ctx, const Layout &L, const bool periodic[3], double *v);
@@ -218,7 +223,11 @@ namespace gdm
   void fused_plan_create(Operator &op);
   void fused_plan_destroy(Operator &op);
   // exchange_ghosts: import the ghost planes of src inside the call, overlapped with the interior planes
-  void fused_apply(Operator &op, double *dst, const double *src, bool accumulate, bool exchange_ghosts = false);
+  // dot_slot >= 0: additionally leaves <src, A src> over the owned DoFs of this rank in ctx.d_sums[dot_slot]
+  // (fused into the store epilogue of the tile kernels; deterministic two-stage sum).  Check fused_supports_dot.
+  void fused_apply(Operator &op, double *dst, const double *src, bool accumulate, bool exchange_ghosts = false,
+                   int dot_slot = -1);
+  bool fused_supports_dot(const Operator &op);
   // output planes [z0, z1) only (local plane indices; no ghost import): building block of the pipelined host-buffer apply
   void fused_apply_window(Operator &op, double *dst, const double *src, int z0, int z1);
   // host logic of the static work partition of the fused kernels (v5/v7): CTA b runs segments
@@ -246,6 +255,8 @@ namespace gdm
   void blas_invert(Context &ctx, double *v, int64_t n);
   // result lands in ctx.d_sums[slot] (device); max variant for linfty
   void blas_dot(Context &ctx, const double *a, const double *b, int64_t n, int slot);
+  // ctx.d_sums[slot] = sum of partials[0..n) in a fixed order (one block)
+  void blas_sum_partials(Context &ctx, const double *partials, int n, int slot);
   void blas_absmax(Context &ctx, const double *a, int64_t n, int slot);
   double read_sum(Context &ctx, int slot, bool allreduce_sum, bool is_max = false);
 

@@ -78,6 +78,7 @@ namespace gdm
       int           own_lo, own_hi, pdim; // owned window (local indices) in pdim
       int64_t       stride[3];
       double        scale;
+      double       *dot_partials; // optional: per-block partial sums of src * dst
     };
 
     __device__ __forceinline__ void face_index(int dim, int d, const int *ln, int64_t tid, int node,
@@ -103,11 +104,11 @@ namespace gdm
         idx[e1] = (int)(tid / n0);
     }
 
-    __global__ void constrained_rows_kernel(const FaceK a)
+    // value written on a constrained (Dirichlet face) row: deal.II's diagonal convention, |scale * diag|
+    __device__ __forceinline__ bool constrained_row(const FaceK &a, int64_t tid, int64_t &off, double &val)
     {
-      int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
       if (tid >= a.face_off[a.n_faces])
-        return;
+        return false;
       int f = 0;
       while (tid >= a.face_off[f + 1])
         ++f;
@@ -117,13 +118,12 @@ namespace gdm
       bool      valid;
       face_index(a.dim, fd, a.ln, tid, a.face_node[f], idx, valid);
       if (!valid)
-        return;
+        return false;
       if (idx[a.pdim] < a.own_lo || idx[a.pdim] >= a.own_hi)
-        return;
+        return false;
       for (int e = 0; e < fd; ++e) // the lowest constrained direction handles the node
         if (idx[e] == a.con_lo[e] || idx[e] == a.con_hi[e])
-          return;
-      double val;
+          return false;
       if (a.has_B)
         {
           val = 0.0;
@@ -142,16 +142,44 @@ namespace gdm
           for (int d = 0; d < a.dim; ++d)
             val *= a.diagA[d][idx[d]];
         }
-      val         = fabs(val * a.scale);
-      int64_t off = 0;
+      val = fabs(val * a.scale);
+      off = 0;
       for (int d = 0; d < a.dim; ++d)
         off += idx[d] * a.stride[d];
-      for (int c = 0; c < a.nc; ++c)
+      return true;
+    }
+
+    __global__ void constrained_rows_kernel(const FaceK a)
+    {
+      const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      int64_t       off = 0;
+      double        val = 0.0, dsum = 0.0;
+      if (constrained_row(a, tid, off, val))
+        for (int c = 0; c < a.nc; ++c)
+          {
+            const double x = a.src[off + c];
+            double       r = val * x;
+            dsum           = fma(x, r, dsum); // fused dot <src, A src> over the constrained rows
+            if (a.accumulate)
+              r += a.dst[off + c];
+            a.dst[off + c] = r;
+          }
+      if (a.dot_partials) // block sum in a fixed order (deterministic)
         {
-          double r = val * a.src[off + c];
-          if (a.accumulate)
-            r += a.dst[off + c];
-          a.dst[off + c] = r;
+          __shared__ double wsum[32];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+            dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+          if ((threadIdx.x & 31) == 0)
+            wsum[threadIdx.x >> 5] = dsum;
+          __syncthreads();
+          if (threadIdx.x == 0)
+            {
+              double t = 0.0;
+              for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+                t += wsum[w];
+              a.dot_partials[blockIdx.x] = t;
+            }
         }
     }
 
@@ -320,8 +348,8 @@ namespace gdm
     }
   } // namespace
 
-  void launch_constrained_rows(Context &ctx, const Layout &L, const Operator &op, double *dst,
-                               const double *src, bool accumulate, int plane_lo, int plane_hi)
+  int launch_constrained_rows(Context &ctx, const Layout &L, const Operator &op, double *dst,
+                              const double *src, bool accumulate, int plane_lo, int plane_hi, double *dot_partials)
   {
     FaceK a;
     a.dst = dst;
@@ -357,12 +385,23 @@ namespace gdm
           ++a.n_faces;
         }
     if (a.n_faces == 0)
-      return;
+      return 0;
     const int64_t n  = a.face_off[a.n_faces];
     const int     th = 128;
-    constrained_rows_kernel<<<(unsigned)((n + th - 1) / th), th, 0, ctx.stream>>>(a);
+    a.dot_partials = dot_partials;
+    const unsigned blocks = (unsigned)((n + th - 1) / th);
+    constrained_rows_kernel<<<blocks, th, 0, ctx.stream>>>(a);
     ctx.launches++;
     GDM_CUDA_CHECK(cudaGetLastError());
+    return (int)blocks;
+  }
+
+  int constrained_rows_max_blocks(const Layout &L)
+  {
+    int64_t n = 0;
+    for (int d = 0; d < L.dim; ++d)
+      n += 2 * face_points(L, d);
+    return (int)((n + 127) / 128) + 1;
   }
 
   void launch_csr_overlay(Context &ctx, const CsrOverlay &csr, double *dst, const double *src,

@@ -120,7 +120,31 @@ namespace gdm
       const double *zt;                                         // v4: scatter rows of the non-Toeplitz plane classes [class][field][W+1]
       const int4   *segs;                                       // v5: work segments {tile x, tile y, z0, z1}
       const int    *seg_ptr;                                    // v5: segments of CTA b are [seg_ptr[b], seg_ptr[b+1])
+      // fused dot product <src, A src> (CG: p . A p): every CTA writes the sum over the points it stored to
+      // dot_partials[blockIdx.x]; null = disabled.  dot_src has the layout of dst.
+      const double *dot_src;
+      double       *dot_partials;
     };
+
+    // sum of `v` over the CTA in a fixed order (warp shuffles, then the warp sums in index order): deterministic
+    template <int NWARPS>
+    __device__ __forceinline__ void block_dot_store(double v, double *scratch, double *dst_partial)
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_down_sync(0xffffffffu, v, o);
+      __syncthreads(); // the scratch area (a TMA stage) is no longer read by anyone
+      if ((threadIdx.x & 31) == 0)
+        scratch[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x == 0)
+        {
+          double t = 0.0;
+          for (int w = 0; w < NWARPS; ++w)
+            t += scratch[w];
+          *dst_partial = t;
+        }
+    }
 
     template <class C, bool HASB>
     constexpr size_t smem_bytes()
@@ -164,7 +188,7 @@ namespace gdm
     }
 
     // ------------------------------------------------------------------ the kernel
-    template <class C, bool HASB, int BSYM, bool ACCUM>
+    template <class C, bool HASB, int BSYM, bool ACCUM, bool DOT = false>
     __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_kernel(const __grid_constant__ CUtensorMap tmap, const KArgs<C::P> g)
     {
       constexpr int P = C::P, W = C::W, TX = C::TX, RY = C::RY, RX = C::RX, NR = C::NR, PIN = C::PIN, PY = C::PY;
@@ -405,6 +429,7 @@ namespace gdm
       if (stage == 0)
         parity ^= 1;
 
+      [[maybe_unused]] double dsum = 0.0; // fused dot product (DOT): sum of src * (A src) over the points this thread stores
       for (int k = kbeg; k < kend; ++k)
         {
           const int abn = (abk + 1 == NAB) ? 0 : abk + 1;
@@ -573,6 +598,8 @@ namespace gdm
                       {
                         double *o = out + (int64_t)i * g.pitch;
                         double  t = res[i];
+                        if constexpr (DOT)
+                          dsum = fma(__ldg(g.dot_src + (o - g.dst)), t, dsum);
                         if (ACCUM)
                           t += *o;
                         *o = t;
@@ -595,6 +622,8 @@ namespace gdm
             }
           abk = abn;
         }
+      if constexpr (DOT)
+        block_dot_store<C::NWARPS>(dsum, smem, g.dot_partials + blockIdx.x);
     }
 
     // ------------------------------------------------------------------ warp-specialised variant
@@ -977,6 +1006,11 @@ namespace gdm
         int  *d_ptr  = nullptr;
       };
       std::map<std::pair<int, int>, Partition> parts;
+      // fused dot product: per-CTA partial sums of the launches of one apply (tile kernels, then the face kernel)
+      double *d_dot      = nullptr;
+      size_t  dot_cap    = 0;
+      int     dot_cursor = -1; // >= 0 while an apply with a fused dot is being enqueued
+      const double *dot_src = nullptr;
       std::map<const void *, CUtensorMap> maps;
       ~FusedPlan()
       {
@@ -985,6 +1019,7 @@ namespace gdm
         cudaFree(d_Be[0]);
         cudaFree(d_Be[1]);
         cudaFree(d_zt);
+        cudaFree(d_dot);
         for (auto &kv : parts)
           {
             cudaFree(kv.second.d_segs);
@@ -1302,6 +1337,8 @@ namespace gdm
       a.zt         = plan.d_zt;
       a.segs       = nullptr;
       a.seg_ptr    = nullptr;
+      a.dot_src    = nullptr;
+      a.dot_partials = nullptr;
       fill_interior<C>(op, plan, a);
       a.dbg = std::getenv("GDM_FUSED_DBG") ? atoi(std::getenv("GDM_FUSED_DBG")) : 0;
       void (*kern)(const CUtensorMap, const KArgs<C::P>) = nullptr;
@@ -1355,11 +1392,22 @@ namespace gdm
             kern = plan.rsplit ? kron3d_v4_kernel<C, 1, true, ACCUM> : kron3d_v4_kernel<C, 1, false, ACCUM>;
           else
             kern = kron3d_v4_kernel<C, MODE, false, ACCUM>;
+          if constexpr (!ACCUM)
+            if (plan.dot_cursor >= 0) // store epilogue with the fused dot product
+              {
+                if constexpr (MODE == 1)
+                  kern = plan.rsplit ? kron3d_v4_kernel<C, 1, true, false, true> : kron3d_v4_kernel<C, 1, false, false, true>;
+                else
+                  kern = kron3d_v4_kernel<C, MODE, false, false, true>;
+              }
           smem = smem_bytes_v4<C, HASB>();
         }
       else
         {
           kern = (C::NXW > 0) ? kron3d_ws_kernel<C, HASB, BSYM, ACCUM> : kron3d_kernel<C, HASB, BSYM, ACCUM>;
+          if constexpr (!ACCUM && C::NXW == 0)
+            if (plan.dot_cursor >= 0)
+              kern = kron3d_kernel<C, HASB, BSYM, false, true>;
           smem = smem_bytes<C, HASB>();
         }
       GDM_REQUIRE(smem <= 227 * 1024, GDM_ERR_INTERNAL, "fused kernel configuration exceeds the shared memory of an SM");
@@ -1375,6 +1423,13 @@ namespace gdm
       const int grid     = (C::V5 || C::V7) ? v5_grid : plan.tiles_x * plan.tiles_y * n_chunks;
       if (grid <= 0)
         return;
+      if (plan.dot_cursor >= 0)
+        {
+          GDM_REQUIRE(!ACCUM && (size_t)(plan.dot_cursor + grid) <= plan.dot_cap, GDM_ERR_INTERNAL, "fused dot: partial buffer too small");
+          a.dot_src      = plan.dot_src;
+          a.dot_partials = plan.d_dot + plan.dot_cursor;
+          plan.dot_cursor += grid;
+        }
       kern<<<grid, C::THREADS, smem, plan.use_comm_stream ? ctx.comm_stream : ctx.stream>>>(map, a);
       ctx.launches++;
       GDM_CUDA_CHECK(cudaGetLastError());
@@ -1612,7 +1667,21 @@ namespace gdm
       accumulate ? launch_variant<C, true, -1, true>(op, plan, map, dst) : launch_variant<C, true, -1, false>(op, plan, map, dst);
   }
 
-  void fused_apply(Operator &op, double *dst, const double *src, bool accumulate, bool exchange_ghosts)
+  bool fused_supports_dot(const Operator &op)
+  {
+    if (!op.fused)
+      return false;
+    const FusedPlan &plan = *static_cast<const FusedPlan *>(op.fused);
+    bool             ok   = false;
+    // the store epilogue with the dot product exists in the v3 tile kernel and in v4
+    with_config(plan.cfg, [&](auto c) {
+      using C = decltype(c);
+      ok      = (!C::V4 && C::NXW == 0) || (C::V4 && !C::V5 && !C::V6 && !C::V7);
+    });
+    return ok;
+  }
+
+  void fused_apply(Operator &op, double *dst, const double *src, bool accumulate, bool exchange_ghosts, int dot_slot)
   {
     FusedPlan    &plan = *static_cast<FusedPlan *>(op.fused);
     Context      &ctx  = *op.sys->ctx;
@@ -1677,6 +1746,42 @@ namespace gdm
                   plan.tiles_y, plan.lz, plan.n_chunks, best_ms);
       }
     const int P = L.p;
+    const bool want_dot = dot_slot >= 0;
+    double    *face_partials = nullptr; // where the face kernel puts its partial sums (set below)
+    if (want_dot)
+      {
+        GDM_REQUIRE(!accumulate && fused_supports_dot(op), GDM_ERR_INTERNAL, "fused dot product not available for this configuration");
+        // partial sums: one per CTA of the (up to three) tile launches, then one per block of the face kernel
+        const int    tiles   = std::max(1, plan.tiles_x * plan.tiles_y);
+        const int    nzw     = std::max(1, plan.cz1 - plan.cz0);
+        const int    lz_min  = std::max(1, std::min(plan.lz, P));
+        const size_t need    = (size_t)tiles * (nzw / lz_min + 4) + (size_t)constrained_rows_max_blocks(L) + 64;
+        if (need > plan.dot_cap)
+          {
+            GDM_CUDA_CHECK(cudaDeviceSynchronize());
+            cudaFree(plan.d_dot);
+            plan.d_dot = nullptr;
+            GDM_CUDA_CHECK(cudaMalloc(&plan.d_dot, need * sizeof(double)));
+            plan.dot_cap = need;
+          }
+        plan.dot_src    = src;
+        plan.dot_cursor = 0;
+        // the face kernel may run concurrently with the tile kernels: give it the tail of the buffer
+        face_partials = plan.d_dot + (plan.dot_cap - (size_t)constrained_rows_max_blocks(L));
+      }
+    int  face_blocks = 0;
+    auto finish_dot  = [&]() {
+      if (!want_dot)
+        return;
+      // compact: [tile partials | face partials] are summed separately in a fixed order into the slot
+      const int n_tile = plan.dot_cursor;
+      plan.dot_cursor  = -1;
+      plan.dot_src     = nullptr;
+      if (face_blocks > 0) // move the face partials behind the tile partials (device-side copy, same stream)
+        GDM_CUDA_CHECK(cudaMemcpyAsync(plan.d_dot + n_tile, face_partials, (size_t)face_blocks * sizeof(double),
+                                       cudaMemcpyDeviceToDevice, ctx.stream));
+      blas_sum_partials(ctx, plan.d_dot, n_tile + face_blocks, dot_slot);
+    };
     if (L.n_ranks > 1 && exchange_ghosts)
       {
         // overlap the ghost import (NCCL on the comm stream) with the planes that do not need it
@@ -1719,15 +1824,17 @@ namespace gdm
         GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_a, ctx.stream));
         GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.comm_stream, ctx.ev_a, 0));
         std::swap(ctx.stream, ctx.comm_stream);
-        launch_constrained_rows(ctx, L, op, dst, src, accumulate);
+        face_blocks = launch_constrained_rows(ctx, L, op, dst, src, accumulate, -1, -1, face_partials);
         std::swap(ctx.stream, ctx.comm_stream);
         GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_b, ctx.comm_stream));
         with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
         GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, ctx.ev_b, 0));
+        finish_dot();
         return;
       }
     // Dirichlet faces (skipped by the tiles) and deal.II's constrained diagonal
-    launch_constrained_rows(ctx, L, op, dst, src, accumulate);
+    face_blocks = launch_constrained_rows(ctx, L, op, dst, src, accumulate, -1, -1, face_partials);
+    finish_dot();
   }
   void fused_apply_window(Operator &op, double *dst, const double *src, int z0, int z1)
   {

@@ -120,7 +120,7 @@ __device__ __forceinline__ void z_pass_v4(const double (&zA)[2 * P + 1], const d
     }
 }
 
-template <class C, int MODE, bool RSPLIT, bool ACCUM>
+template <class C, int MODE, bool RSPLIT, bool ACCUM, bool DOT = false>
 __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v4_kernel(const __grid_constant__ CUtensorMap tmap, const KArgs<C::P> g)
 {
   constexpr int  P = C::P, W = C::W, TX = C::TX, RY = C::RY, RX = C::RX, NR = C::NR, PIN = C::PIN, PY = C::PY;
@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v4_kernel(const __
 #pragma unroll
     for (int j = 0; j < 2 * P; ++j)
       acc[i][j] = 0.0;
+  [[maybe_unused]] double dsum = 0.0; // fused dot product (DOT): sum of src * (A src) over the points this thread stores
 
   // ---- x pass of one plane: staged tile at in_off -> a/b buffer at a_off (doubles)
   auto x_pass = [&](const int in_off, const int a_off) {
@@ -441,6 +442,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v4_kernel(const __
             {
               double *o = out + (int64_t)i * g.pitch;
               double  t = res[i];
+              if constexpr (DOT)
+                dsum = fma(__ldg(g.dot_src + (o - g.dst)), t, dsum);
               if (ACCUM)
                 t += *o;
               *o = t;
@@ -487,4 +490,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v4_kernel(const __
       ab_nxt      = t;
       out += g.plane;
     }
+  if constexpr (DOT)
+    block_dot_store<C::NWARPS>(dsum, smem, g.dot_partials + blockIdx.x);
 }

@@ -202,6 +202,9 @@ int gdm_operator_vmult(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src);  
 int gdm_operator_vmult_add(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src);
 /* Host-buffer form of vmult (the call a deal.II user makes with host vectors):
  * copies src to the device, applies, copies dst back; synchronises. */
+/* dst = A src and *src_dot_dst = <src, dst> over all ranks (the q = A p, p.q pair of SolverCG): on the fused path the
+ * dot product is accumulated in the store epilogue of the tile kernel, so p and q are not read again. */
+int gdm_operator_vmult_dot(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src, double *src_dot_dst);
 int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *src_host);
 int gdm_operator_diagonal(gdm_operator_t op, gdm_vector_t diag);   /* matrix diagonal (Jacobi) */
 /* 1 / (row sums of the mass operator): matrix_creator.h:64-117; op must be MASS */

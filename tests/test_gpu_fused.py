@@ -111,3 +111,42 @@ def test_pipelined_host_buffer_apply(lib, p, reps, bc):
         assert rel_err(yh, Ao @ xh) <= TOL
         A.vmult_host(yh, -xh)  # staging buffers are reused
         assert rel_err(yh, -(Ao @ xh)) <= TOL
+
+
+@pytest.mark.parametrize("p,reps,bc", FUSED_CASES)
+@pytest.mark.parametrize("kind", ["mass", "stiffness"])
+def test_fused_dot_product(lib, p, reps, bc, kind):
+    """gdm_operator_vmult_dot: y = A x and <x, y> from the store epilogue of the tile kernel (CG's q = A p, p.q)."""
+    import gdm_b200 as g
+    gs, gc, os_, oc = make_pair(3, p, 1, reps, bc)
+    A = make_operator(gs, gc, kind, kernel=g.capi.KERNEL_FUSED)
+    Ao = oracle_operator(os_, oc, kind)
+    xh = np.random.default_rng(3).uniform(-1, 1, gs.n_dofs())
+    x, y = g.Vector(gs, xh), g.Vector(gs)
+    d = A.vmult_dot(y, x)
+    ref = Ao @ xh
+    assert rel_err(y.numpy(), ref) <= TOL
+    # relative to sum |x_i y_i| (the condition of the sum), tolerance of one FP64 summation of n terms
+    assert abs(d - xh @ ref) <= 1e-13 * np.abs(xh * ref).sum()
+    # deterministic: the same call gives the same bits
+    assert A.vmult_dot(y, x) == d
+
+
+def test_cg_with_fused_dot_matches_separate_dot(lib, monkeypatch):
+    """The fused p.Ap must not change what CG computes beyond the summation order of one dot product."""
+    import gdm_b200 as g
+    gs, gc, os_, oc = make_pair(3, 3, 1, [20, 18, 33], "dirichlet")
+    A = make_operator(gs, gc, "stiffness", kernel=g.capi.KERNEL_FUSED)
+    rhs = g.Vector(gs)
+    rhs.set(1.0)
+    gc.set_zero(rhs)
+    sols, steps = [], []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("GDM_CG_FUSED_DOT", flag)
+        u = g.Vector(gs)
+        ctl = g.ReductionControl(500, 1e-12, 1e-8)
+        g.SolverCG(ctl).solve(A, u, rhs, g.PreconditionIdentity())
+        sols.append(u.numpy())
+        steps.append(ctl.last_step())
+    assert abs(steps[0] - steps[1]) <= 1
+    assert rel_err(sols[0], sols[1]) <= 1e-6 if steps[0] != steps[1] else rel_err(sols[0], sols[1]) <= 1e-9
