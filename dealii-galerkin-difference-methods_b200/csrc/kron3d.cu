@@ -1030,18 +1030,22 @@ namespace gdm
 
     // available tile configurations (selected per degree; GDM_FUSED_CFG=<id> overrides for tuning)
     //                      id        P  TX RY NRB RX ST MINB
-#define GDM_FUSED_CONFIGS(X)            \
+    // Production configurations (defaults per degree) and, with -DGDM_FUSED_EXPERIMENTAL (build.py:
+    // GDM_BUILD_EXPERIMENTAL=1), the control-structure experiments of round 1 (v5/v6/v7).
+#define GDM_FUSED_CONFIGS_CORE(X)       \
   /* v3 (split phase barrier):  P  TX RY NRB RX ST MINB [NXW] */ \
   X(0, Cfg<1, 32, 8, 4, 8, 3, 2>)       \
   X(2, Cfg<5, 32, 4, 6, 8, 3, 2>)       \
-  X(6, Cfg<3, 32, 4, 8, 8, 3, 2>)       \
   X(14, Cfg<3, 32, 4, 8, 4, 3, 2>)      \
   X(15, Cfg<5, 32, 4, 8, 8, 3, 1>)      \
-  X(40, Cfg<3, 32, 4, 8, 4, 3, 1, 4>)   \
   /* v4 (lean, one CTA barrier per plane, tap split): P RY NRB RX ST MINB */ \
   X(100, Cfg4<3, 4, 8, 4, 3, 2>)        \
   X(101, Cfg4<1, 4, 8, 4, 3, 2>)        \
-  X(102, Cfg4<5, 4, 8, 4, 3, 2>)        \
+  X(102, Cfg4<5, 4, 8, 4, 3, 2>)
+#ifdef GDM_FUSED_EXPERIMENTAL
+#define GDM_FUSED_CONFIGS_EXP(X)        \
+  X(6, Cfg<3, 32, 4, 8, 8, 3, 2>)       \
+  X(40, Cfg<3, 32, 4, 8, 4, 3, 1, 4>)   \
   X(103, Cfg4<3, 4, 8, 8, 3, 2>)        \
   X(109, Cfg4<1, 8, 4, 4, 3, 2>)        \
   /* v5 (mbarrier rings, tile-major balanced partition) */ \
@@ -1055,6 +1059,10 @@ namespace gdm
   X(400, Cfg7<3, 4, 8, 4, 3, 2>)        \
   X(401, Cfg7<1, 4, 8, 4, 3, 2>)        \
   X(402, Cfg7<5, 4, 8, 4, 3, 2>)
+#else
+#define GDM_FUSED_CONFIGS_EXP(X)
+#endif
+#define GDM_FUSED_CONFIGS(X) GDM_FUSED_CONFIGS_CORE(X) GDM_FUSED_CONFIGS_EXP(X)
 
     template <class F>
     void with_config(int id, F &&f)
@@ -1068,7 +1076,8 @@ namespace gdm
           GDM_FUSED_CONFIGS(GDM_CASE)
 #undef GDM_CASE
           default:
-            throw Error(GDM_ERR_INTERNAL, "unknown fused kernel configuration");
+            throw Error(GDM_ERR_INVALID, "fused kernel configuration " + std::to_string(id) +
+                        " is not in this build (experimental families need GDM_BUILD_EXPERIMENTAL=1 at build time)");
         }
     }
 
