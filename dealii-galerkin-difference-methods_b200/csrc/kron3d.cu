@@ -1048,6 +1048,8 @@ namespace gdm
   X(40, Cfg<3, 32, 4, 8, 4, 3, 1, 4>)   \
   X(103, Cfg4<3, 4, 8, 8, 3, 2>)        \
   X(109, Cfg4<1, 8, 4, 4, 3, 2>)        \
+  X(121, Cfg4<1, 8, 4, 4, 3, 4>)        \
+  X(124, Cfg4<1, 4, 8, 4, 3, 3>)        \
   /* v5 (mbarrier rings, tile-major balanced partition) */ \
   X(200, Cfg5<3, 4, 8, 4, 3, 2>)        \
   /* v6 (register resident, warps independent):  P RY NW ST MINB */ \
