@@ -1048,6 +1048,8 @@ namespace gdm
   X(40, Cfg<3, 32, 4, 8, 4, 3, 1, 4>)   \
   X(103, Cfg4<3, 4, 8, 8, 3, 2>)        \
   X(109, Cfg4<1, 8, 4, 4, 3, 2>)        \
+  X(130, Cfg4<3, 4, 4, 4, 3, 4>)        \
+  X(133, Cfg4<3, 4, 6, 4, 3, 2>)        \
   X(121, Cfg4<1, 8, 4, 4, 3, 4>)        \
   X(124, Cfg4<1, 4, 8, 4, 3, 3>)        \
   /* v5 (mbarrier rings, tile-major balanced partition) */ \
@@ -1403,6 +1405,11 @@ namespace gdm
             kern = plan.rsplit ? kron3d_v4_kernel<C, 1, true, ACCUM> : kron3d_v4_kernel<C, 1, false, ACCUM>;
           else
             kern = kron3d_v4_kernel<C, MODE, false, ACCUM>;
+#ifdef GDM_FUSED_EXPERIMENTAL
+          if constexpr (!ACCUM && MODE == 1)
+            if (a.dbg & 32) // diagnostic: LSU + synchronisation skeleton without the FP64 arithmetic
+              kern = kron3d_v4_kernel<C, 1, true, false, false, true>;
+#endif
           if constexpr (!ACCUM)
             if (plan.dot_cursor >= 0) // store epilogue with the fused dot product
               {

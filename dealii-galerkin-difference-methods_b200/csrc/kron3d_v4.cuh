@@ -120,7 +120,9 @@ __device__ __forceinline__ void z_pass_v4(const double (&zA)[2 * P + 1], const d
     }
 }
 
-template <class C, int MODE, bool RSPLIT, bool ACCUM, bool DOT = false>
+// NOFP (diagnostic, experimental build only): keep every shared-memory / TMA / global access and barrier of the kernel but
+// replace the FP64 arithmetic by one addition per value -- measures the LSU + synchronisation skeleton (profiles/r1).
+template <class C, int MODE, bool RSPLIT, bool ACCUM, bool DOT = false, bool NOFP = false>
 __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v4_kernel(const __grid_constant__ CUtensorMap tmap, const KArgs<C::P> g)
 {
   constexpr int  P = C::P, W = C::W, TX = C::TX, RY = C::RY, RX = C::RX, NR = C::NR, PIN = C::PIN, PY = C::PY;
@@ -222,6 +224,12 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v4_kernel(const __
         for (int j = 0; j < RX; ++j)
           {
             const int c   = j + P;
+            if constexpr (NOFP)
+              {
+                a[j]  = v[c] + v[c - P];
+                bb[j] = v[c + P];
+                continue;
+              }
             double    ra  = g.Ax[0] * v[c];
             double    rbv = (HASB && SYM) ? g.Bx[0] * v[c] : 0.0;
 #pragma unroll
@@ -307,6 +315,14 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v4_kernel(const __
                       rbv = fma(tb[t], v[t], rbv);
                   }
               }
+            else if constexpr (NOFP)
+              {
+                ra = v[0];
+#pragma unroll
+                for (int t = 1; t < W - 1; ++t)
+                  ra += v[t];
+                rbv = v[W - 1];
+              }
             else
               {
                 ra = g.Ax[0] * v[P];
@@ -360,6 +376,12 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v4_kernel(const __
       for (int i = 0; i < RY; ++i)
         {
           const int c  = i + P;
+          if constexpr (NOFP)
+            {
+              u1[i] = aw[i] + aw[i + 2 * P];
+              u2[i] = HASB ? bw[i] + bw[i + 2 * P] : 0.0;
+              continue;
+            }
           double    t1 = g.Ay[0] * aw[c], t2 = 0.0;
           if (HASB)
             {
@@ -418,7 +440,13 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v4_kernel(const __
         }
     }
     double res[RY];
-    if (k >= g.kz_lo && k < g.kz_hi)
+    if constexpr (NOFP)
+      {
+#pragma unroll
+        for (int i = 0; i < RY; ++i)
+          res[i] = u1[i] + u2[i] + acc[i][0];
+      }
+    else if (k >= g.kz_lo && k < g.kz_hi)
       z_pass_v4<P, RY, MODE, RSPLIT, true>(g.Az, g.Bz, g.sigma, u1, u2, acc, res);
     else
       {
