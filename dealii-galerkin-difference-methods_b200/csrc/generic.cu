@@ -8,6 +8,8 @@
 // Replaces SparseMatrix::vmult on matrices assembled by the reference's cell loops
 // (include/gdm/matrix_creator.h:21-61, tests/poisson_02_gdm.cc:160-206).
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 
 #include "gdm_internal.h"
 
@@ -62,6 +64,178 @@ namespace gdm
       if (a.accumulate)
         acc += a.dst[base];
       a.dst[base] = acc;
+    }
+
+    // ---- fused band pass: both chains of the sum factorisation in one launch
+    //     oS = (S ? A S : 0) + B P   (scaled / accumulated on the last direction),   oP = A P   (optional)
+    // dir == 0: one thread per output, neighbours along x come from the same cache lines;
+    // dir >= 1: a thread marches along `dir` over RJ outputs with the 2p+1 window of P (and S) in registers, so
+    // every input value is read once per (RJ + 2p)/RJ instead of 2p+1 times through L2.
+    struct BandK2
+    {
+      const double *S, *P, *tabA, *tabB;
+      double       *oS, *oP;
+      int           dir, nc;
+      int           n_dir, wrap;
+      int64_t       pitch, plane, stride;
+      int           lo[3], hi[3];
+      int           accumulate;
+      double        scale;
+    };
+    constexpr int BAND_RJ = 32;
+
+    // column index of tap t of row r (periodic fold: rows below `wrap` wrap around, the duplicate last row does not)
+    __device__ __forceinline__ int band_col(int r, int t, int p, int wrap)
+    {
+      int c = r + t - p;
+      if (wrap > 0)
+        {
+          if (c < 0)
+            c += wrap;
+          else if (c >= wrap && r < wrap)
+            c -= wrap;
+        }
+      return c;
+    }
+
+    template <int P>
+    __global__ void band_x_kernel(const BandK2 a)
+    {
+      constexpr int W  = 2 * P + 1;
+      const int64_t ex = (int64_t)a.lo[0] * a.nc + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (ex >= (int64_t)a.hi[0] * a.nc)
+        return;
+      const int     j    = a.lo[1] + blockIdx.y;
+      const int     k    = a.lo[2] + blockIdx.z;
+      const int     r    = (int)(ex / a.nc);
+      const int64_t base = (int64_t)k * a.plane + (int64_t)j * a.pitch + ex;
+      const double *tA = a.tabA + (int64_t)r * W, *tB = a.tabB + (int64_t)r * W;
+      double        s = 0.0, q = 0.0;
+#pragma unroll
+      for (int t = 0; t < W; ++t)
+        {
+          const int c = band_col(r, t, P, a.wrap);
+          if (c < 0 || c >= a.n_dir)
+            continue;
+          const int64_t off = base + (int64_t)(c - r) * a.stride;
+          const double  pv  = __ldg(a.P + off);
+          const double  ca = __ldg(tA + t), cb = __ldg(tB + t);
+          s                 = fma(cb, pv, s);
+          if (a.S)
+            s = fma(ca, __ldg(a.S + off), s);
+          q = fma(ca, pv, q);
+        }
+      s *= a.scale;
+      if (a.accumulate)
+        s += a.oS[base];
+      a.oS[base] = s;
+      if (a.oP)
+        a.oP[base] = q;
+    }
+
+    template <int P>
+    __global__ void band_march_kernel(const BandK2 a)
+    {
+      constexpr int W  = 2 * P + 1;
+      const int64_t ex = (int64_t)a.lo[0] * a.nc + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (ex >= (int64_t)a.hi[0] * a.nc)
+        return;
+      int     r0, r1;
+      int64_t base0; // offset of marching index 0
+      if (a.dir == 1)
+        {
+          r0    = a.lo[1] + blockIdx.y * BAND_RJ;
+          r1    = min(r0 + BAND_RJ, a.hi[1]);
+          base0 = (int64_t)(a.lo[2] + blockIdx.z) * a.plane + ex;
+        }
+      else
+        {
+          r0    = a.lo[2] + blockIdx.z * BAND_RJ;
+          r1    = min(r0 + BAND_RJ, a.hi[2]);
+          base0 = (int64_t)(a.lo[1] + blockIdx.y) * a.pitch + ex;
+        }
+      const bool has_S = a.S != nullptr, has_oP = a.oP != nullptr;
+      // value at logical column c of the sliding window (rows below the periodic seam)
+      auto ld = [&](const double *f, int c) -> double {
+        if (a.wrap > 0)
+          {
+            if (c < 0)
+              c += a.wrap;
+            else if (c >= a.wrap)
+              c -= a.wrap;
+          }
+        return (c < 0 || c >= a.n_dir) ? 0.0 : __ldg(f + base0 + (int64_t)c * a.stride);
+      };
+      double wP[W], wS[W];
+#pragma unroll
+      for (int t = 1; t < W; ++t)
+        {
+          wP[t] = ld(a.P, r0 - P + t - 1);
+          wS[t] = has_S ? ld(a.S, r0 - P + t - 1) : 0.0;
+        }
+      constexpr int U = 4; // rows per trip: their new window values are requested together
+      for (int rb = r0; rb < r1; rb += U)
+        {
+          double nP[U], nS[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            {
+              nP[u] = ld(a.P, rb + u + P);
+              nS[u] = has_S ? ld(a.S, rb + u + P) : 0.0;
+            }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            {
+              const int r = rb + u;
+#pragma unroll
+              for (int t = 0; t < W - 1; ++t)
+                {
+                  wP[t] = wP[t + 1];
+                  wS[t] = wS[t + 1];
+                }
+              wP[W - 1] = nP[u];
+              wS[W - 1] = nS[u];
+              if (r >= r1)
+                continue;
+              const double *tA = a.tabA + (int64_t)r * W, *tB = a.tabB + (int64_t)r * W;
+              double        s = 0.0, q = 0.0;
+              if (a.wrap > 0 && r >= a.wrap)
+                {
+                  // the duplicate last row of a periodic direction does not wrap: gather it directly
+#pragma unroll
+                  for (int t = 0; t < W; ++t)
+                    {
+                      const int c = r + t - P;
+                      if (c < 0 || c >= a.n_dir)
+                        continue;
+                      const double pv = __ldg(a.P + base0 + (int64_t)c * a.stride);
+                      s               = fma(__ldg(tB + t), pv, s);
+                      if (has_S)
+                        s = fma(__ldg(tA + t), __ldg(a.S + base0 + (int64_t)c * a.stride), s);
+                      q = fma(__ldg(tA + t), pv, q);
+                    }
+                }
+              else
+                {
+#pragma unroll
+                  for (int t = 0; t < W; ++t)
+                    {
+                      const double ca = __ldg(tA + t), cb = __ldg(tB + t);
+                      s               = fma(cb, wP[t], s);
+                      if (has_S)
+                        s = fma(ca, wS[t], s);
+                      q = fma(ca, wP[t], q);
+                    }
+                }
+              const int64_t o = base0 + (int64_t)r * a.stride;
+              s *= a.scale;
+              if (a.accumulate)
+                s += a.oS[o];
+              a.oS[o] = s;
+              if (has_oP)
+                a.oP[o] = q;
+            }
+        }
     }
 
     struct FaceK
@@ -283,6 +457,55 @@ namespace gdm
         }
     }
   } // namespace
+
+  // fused pass of direction `dir`: oS = (S ? A S : 0) + B P (scaled / accumulated), oP = A P (optional).
+  // Returns false when the degree has no instantiation (the caller falls back to the one-output passes).
+  bool launch_band_pass2(Context &ctx, const Layout &L, const bool periodic[3], int dir, bool owned_only, const double *S,
+                         const double *P, const double *tabA, const double *tabB, double *oS, double *oP, double scale,
+                         bool accumulate)
+  {
+    BandK2 a;
+    a.S = S, a.P = P, a.tabA = tabA, a.tabB = tabB, a.oS = oS, a.oP = oP;
+    a.dir        = dir;
+    a.nc         = L.nc;
+    a.n_dir      = L.ln[dir];
+    a.wrap       = periodic[dir] ? L.N[dir] : 0;
+    a.pitch      = L.pitch;
+    a.plane      = L.plane;
+    a.stride     = L.stride[dir];
+    a.accumulate = accumulate ? 1 : 0;
+    a.scale      = scale;
+    window(L, owned_only, a.lo, a.hi);
+    const int64_t x_elems = (int64_t)(a.hi[0] - a.lo[0]) * L.nc;
+    if (x_elems <= 0 || a.hi[1] <= a.lo[1] || a.hi[2] <= a.lo[2])
+      return true;
+    const int threads = 128;
+    unsigned  gy = (unsigned)(a.hi[1] - a.lo[1]), gz = (unsigned)(a.hi[2] - a.lo[2]);
+    if (dir == 1)
+      gy = (gy + BAND_RJ - 1) / BAND_RJ;
+    else if (dir == 2)
+      gz = (gz + BAND_RJ - 1) / BAND_RJ;
+    const dim3 grid((unsigned)((x_elems + threads - 1) / threads), gy, gz);
+    auto       launch = [&](auto pc) {
+      constexpr int PP = decltype(pc)::value;
+      if (dir == 0)
+        band_x_kernel<PP><<<grid, threads, 0, ctx.stream>>>(a);
+      else
+        band_march_kernel<PP><<<grid, threads, 0, ctx.stream>>>(a);
+    };
+    switch (L.p)
+      {
+        case 1: launch(std::integral_constant<int, 1>{}); break;
+        case 3: launch(std::integral_constant<int, 3>{}); break;
+        case 5: launch(std::integral_constant<int, 5>{}); break;
+        case 7: launch(std::integral_constant<int, 7>{}); break;
+        case 9: launch(std::integral_constant<int, 9>{}); break;
+        default: return false;
+      }
+    ctx.launches++;
+    GDM_CUDA_CHECK(cudaGetLastError());
+    return true;
+  }
 
   void launch_band_pass(Context &ctx, const Layout &L, const bool periodic[3], const BandPassArgs &in)
   {
@@ -518,10 +741,29 @@ namespace gdm
     ctx.ensure_scratch((size_t)L.size);
     const double *P = src, *S = nullptr;
     int           next = 0;
+    const char   *env_f = std::getenv("GDM_GENERIC_FUSED");
+    const bool    fused_passes = !(env_f && env_f[0] == '0') && (L.p == 1 || L.p == 3 || L.p == 5 || L.p == 7 || L.p == 9);
     for (int d = 0; d < dim; ++d)
       {
         const bool last       = (d == dim - 1);
         const bool owned_only = (d == L.pdim);
+        if (fused_passes)
+          {
+            // one launch per direction: S_d = A_d S_{d-1} + B_d P_{d-1} and P_d = A_d P_{d-1} (mass: P_d only)
+            double *oS = last ? dst : ctx.scratch[next++ & 3];
+            double *oP = (op.has_B && !last) ? ctx.scratch[next++ & 3] : nullptr;
+            launch_band_pass2(ctx, L, op.periodic, d, owned_only, op.has_B ? S : nullptr, P, op.dA[d], op.has_B ? op.dB[d] : op.dA[d], oS,
+                              oP, last ? op.desc.scale : 1.0, last && accumulate);
+            if (op.has_B)
+              {
+                S = oS;
+                if (oP)
+                  P = oP;
+              }
+            else
+              P = oS;
+            continue;
+          }
         if (op.has_B)
           {
             double      *Sn = last ? dst : ctx.scratch[next++ & 3];
