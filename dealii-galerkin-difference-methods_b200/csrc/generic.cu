@@ -98,14 +98,18 @@ namespace gdm
       return c;
     }
 
+    // Thread indices are flattened over (x element, row): a row of 257 nodes would otherwise leave the third 128-thread
+    // block of every row with one active lane.
     template <int P>
     __global__ void band_x_kernel(const BandK2 a)
     {
-      constexpr int W  = 2 * P + 1;
-      const int64_t ex = (int64_t)a.lo[0] * a.nc + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-      if (ex >= (int64_t)a.hi[0] * a.nc)
+      constexpr int W      = 2 * P + 1;
+      const int64_t row_el = (int64_t)(a.hi[0] - a.lo[0]) * a.nc; // computed elements of a row
+      const int64_t idx    = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (idx >= row_el * (a.hi[1] - a.lo[1]))
         return;
-      const int     j    = a.lo[1] + blockIdx.y;
+      const int     j    = a.lo[1] + (int)(idx / row_el);
+      const int64_t ex   = (int64_t)a.lo[0] * a.nc + idx % row_el;
       const int     k    = a.lo[2] + blockIdx.z;
       const int     r    = (int)(ex / a.nc);
       const int64_t base = (int64_t)k * a.plane + (int64_t)j * a.pitch + ex;
@@ -136,23 +140,28 @@ namespace gdm
     template <int P>
     __global__ void band_march_kernel(const BandK2 a)
     {
-      constexpr int W  = 2 * P + 1;
-      const int64_t ex = (int64_t)a.lo[0] * a.nc + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-      if (ex >= (int64_t)a.hi[0] * a.nc)
+      constexpr int W      = 2 * P + 1;
+      const int64_t row_el = (int64_t)(a.hi[0] - a.lo[0]) * a.nc; // computed elements of a row
+      // independent columns (x element, the index that is not marched) flattened over blockIdx.x; blockIdx.y: march chunk
+      const int     n_other = (a.dir == 1) ? (a.hi[2] - a.lo[2]) : (a.hi[1] - a.lo[1]);
+      const int64_t col     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (col >= row_el * n_other)
         return;
-      int     r0, r1;
-      int64_t base0; // offset of marching index 0
+      const int64_t ex    = (int64_t)a.lo[0] * a.nc + col % row_el;
+      const int     other = (int)(col / row_el);
+      int           r0, r1;
+      int64_t       base0; // offset of marching index 0
       if (a.dir == 1)
         {
           r0    = a.lo[1] + blockIdx.y * BAND_RJ;
           r1    = min(r0 + BAND_RJ, a.hi[1]);
-          base0 = (int64_t)(a.lo[2] + blockIdx.z) * a.plane + ex;
+          base0 = (int64_t)(a.lo[2] + other) * a.plane + ex;
         }
       else
         {
-          r0    = a.lo[2] + blockIdx.z * BAND_RJ;
+          r0    = a.lo[2] + blockIdx.y * BAND_RJ;
           r1    = min(r0 + BAND_RJ, a.hi[2]);
-          base0 = (int64_t)(a.lo[1] + blockIdx.y) * a.pitch + ex;
+          base0 = (int64_t)(a.lo[1] + other) * a.pitch + ex;
         }
       const bool has_S = a.S != nullptr, has_oP = a.oP != nullptr;
       // value at logical column c of the sliding window (rows below the periodic seam)
@@ -479,14 +488,16 @@ namespace gdm
     const int64_t x_elems = (int64_t)(a.hi[0] - a.lo[0]) * L.nc;
     if (x_elems <= 0 || a.hi[1] <= a.lo[1] || a.hi[2] <= a.lo[2])
       return true;
-    const int threads = 128;
-    unsigned  gy = (unsigned)(a.hi[1] - a.lo[1]), gz = (unsigned)(a.hi[2] - a.lo[2]);
-    if (dir == 1)
-      gy = (gy + BAND_RJ - 1) / BAND_RJ;
-    else if (dir == 2)
-      gz = (gz + BAND_RJ - 1) / BAND_RJ;
-    const dim3 grid((unsigned)((x_elems + threads - 1) / threads), gy, gz);
-    auto       launch = [&](auto pc) {
+    const int     threads = 128;
+    const int     ny = a.hi[1] - a.lo[1], nz = a.hi[2] - a.lo[2];
+    dim3          grid;
+    if (dir == 0) // all outputs of a plane flattened; one plane per blockIdx.z
+      grid = dim3((unsigned)((x_elems * ny + threads - 1) / threads), 1, (unsigned)nz);
+    else if (dir == 1) // columns (x element, plane) flattened; chunks of BAND_RJ rows
+      grid = dim3((unsigned)((x_elems * nz + threads - 1) / threads), (unsigned)((ny + BAND_RJ - 1) / BAND_RJ), 1);
+    else // columns (x element, row) flattened; chunks of BAND_RJ planes
+      grid = dim3((unsigned)((x_elems * ny + threads - 1) / threads), (unsigned)((nz + BAND_RJ - 1) / BAND_RJ), 1);
+    auto launch = [&](auto pc) {
       constexpr int PP = decltype(pc)::value;
       if (dir == 0)
         band_x_kernel<PP><<<grid, threads, 0, ctx.stream>>>(a);
