@@ -34,6 +34,14 @@ namespace gdm
 {
   namespace
   {
+    // Diagnostic switches of the kernels (GDM_FUSED_DBG: ablations used for profiles/r1) exist only in the experimental
+    // build; the production kernels carry no debug branches.
+#ifdef GDM_FUSED_EXPERIMENTAL
+#define GDM_DBG(g, bit) (((g).dbg & (bit)) != 0)
+#else
+#define GDM_DBG(g, bit) false
+#endif
+
     // ------------------------------------------------------------------ PTX helpers
     __device__ __forceinline__ uint32_t smem_u32(const void *p)
     {
@@ -436,9 +444,9 @@ namespace gdm
           // ---- x pass of plane k+1 (its buffer was last read by the y/z pass of plane k-2)
           if (k + 1 < kend)
             {
-              if (!(g.dbg & 32) || tid < 32)
+              if (!GDM_DBG(g, 32) || tid < 32)
                 mbar_wait(&bars[stage], parity);
-              if (!(g.dbg & 4))
+              if (!GDM_DBG(g, 4))
                 x_pass(stage, abn);
               if (tid < 2 * W)
                 {
@@ -447,12 +455,12 @@ namespace gdm
                 }
             }
           __syncwarp();
-          if ((tid & 31) == 0 && !(g.dbg & 16))
+          if ((tid & 31) == 0 && !GDM_DBG(g, 16))
             mbar_arrive(xbar);
 
           // ---- y pass + z pass of plane k (overlaps the other warps' x pass of plane k+1)
           out += g.plane;
-          if (yz_active && !(g.dbg & 8))
+          if (yz_active && !GDM_DBG(g, 8))
             {
               const int a_off = OFF_AB + abk * AB_BUF + lx * PY + rb * RY;
               const int b_off = a_off + (NF - 1) * TX * PY;
@@ -590,7 +598,7 @@ namespace gdm
                   z_pass<P, RY, HASB>(zA, zB, u1, u2, acc, res);
                 }
               const int r_out = k - P; // output plane completed by this input plane
-              if (r_out >= zc0 && r_out < zc1 && !(g.dbg & 1))
+              if (r_out >= zc0 && r_out < zc1 && !GDM_DBG(g, 1))
                 {
 #pragma unroll
                   for (int i = 0; i < RY; ++i)
@@ -607,7 +615,7 @@ namespace gdm
                 }
             }
           // ---- every warp has finished the x pass of plane k+1: its stage can be refilled
-          if (!(g.dbg & 16))
+          if (!GDM_DBG(g, 16))
             mbar_wait(xbar, xphase);
           xphase ^= 1;
           if (tid == 0 && k + 1 + C::STAGES < kend)

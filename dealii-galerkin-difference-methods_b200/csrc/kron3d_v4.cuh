@@ -497,11 +497,11 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v4_kernel(const __
       if (k + 1 < kend)
         {
           mbar_wait_a(bar0 + 8 * stage, parity);
-          if (!(g.dbg & 4))
+          if (!GDM_DBG(g, 4))
             x_pass(stage * C::STAGE_DOUBLES, ab_nxt);
         }
-      if (!(g.dbg & 8))
-        yz_pass(k, ab_cur, (k - P >= zc0) && !(g.dbg & 1));
+      if (!GDM_DBG(g, 8))
+        yz_pass(k, ab_cur, (k - P >= zc0) && !GDM_DBG(g, 1));
       __syncthreads();
       if (tid == 0 && k + 1 + C::STAGES < kend)
         {

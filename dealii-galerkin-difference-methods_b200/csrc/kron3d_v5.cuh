@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v5_kernel(const __
   auto x_step = [&]() {
     mbar_wait_a(bar0 + 8 * xs, xs_par);           // TMA stage landed
     mbar_wait_a(bar_ae + 8 * xb_, xb_par ^ 1u);   // a/b buffer released by the y pass that read it last
-    if (!(g.dbg & 4))
+    if (!GDM_DBG(g, 4))
       x_pass(xs * C::STAGE_DOUBLES, OFF_AB + xb_ * AB_BUF);
     __syncwarp();
     if (lane == 0)
@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v5_kernel(const __
           if (k + 1 < kend)
             x_step();
           mbar_wait_a(bar_af + 8 * yb_, yb_par); // every warp has written its part of plane k
-          if (!(g.dbg & 8))
-            yz_pass(k, OFF_AB + yb_ * AB_BUF, (k - P >= zc0) && !(g.dbg & 1));
+          if (!GDM_DBG(g, 8))
+            yz_pass(k, OFF_AB + yb_ * AB_BUF, (k - P >= zc0) && !GDM_DBG(g, 1));
           __syncwarp();
           if (lane == 0)
             mbar_arrive_a(bar_ae + 8 * yb_);

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v6_kernel(const __
   double   *out      = g.dst + (int64_t)(kbeg - P) * g.plane + (int64_t)gy_first * g.pitch + gx;
   const int in_off   = warp * RY * PIN + lane; // this thread's first input value inside a stage
   // non-Toeplitz rows: x (per lane), y (per output row, warp uniform)
-  const bool x_bnd   = (gx <= P || gx >= g.nx - P) && gx >= 0 && gx <= g.nx && !(g.dbg & 16);
+  const bool x_bnd   = (gx <= P || gx >= g.nx - P) && gx >= 0 && gx <= g.nx && !GDM_DBG(g, 16);
   const int  xrc     = (gx <= P) ? gx : gx - (g.nx - P) + P + 1;
   const int  xta_off = OFF_TB + (0 * NBT + (x_bnd ? xrc : 0)) * WP;
   const bool any_fix = (x0 <= P) || (x0 + TX - 1 >= g.nx - P) || (gy_first <= P) || (gy_first + RY - 1 >= g.ny - P);
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v6_kernel(const __
             try_refill();
         }
       mbar_wait_a(bar_f + 8 * st, par);
-      const int  nstore = (k - P >= zc0 && !(g.dbg & 1)) ? nst : 0;
+      const int  nstore = (k - P >= zc0 && !GDM_DBG(g, 1)) ? nst : 0;
       const bool toep   = (k >= g.kz_lo && k < g.kz_hi);
       int        zc     = 0;
       if (!toep)
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_v6_kernel(const __
           const int kk = min(max(k, 0), g.nz_local - 1);
           zc           = (kk < g.kz_lo) ? kk : g.kz_lo + (kk - g.kz_hi);
         }
-      if (!(g.dbg & 8))
+      if (!GDM_DBG(g, 8))
         {
           if (!any_fix)
             {
