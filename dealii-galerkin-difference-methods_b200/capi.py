@@ -94,6 +94,8 @@ SIGNATURES = {
     "gdm_system_halo_plan": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "gdm_fused_partition": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "gdm_pers_partition": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gdm_constraints_create": (C.c_int, [_H, _PH]),
     "gdm_constraints_destroy": (C.c_int, [_H]),
     "gdm_constraints_make_zero_boundary": (C.c_int, [_H, C.c_int]),

@@ -689,6 +689,25 @@ int gdm_fused_partition(int aligned, int tiles_x, int tiles_y, int z0, int z1, i
   GDM_CATCH
 }
 
+int gdm_pers_partition(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, int aligned, int32_t *job_ptr,
+                       int32_t cap_ptr, int32_t *jobs6, int32_t cap_jobs, int32_t *n_shares, int32_t *n_jobs)
+{
+  GDM_TRY
+  GDM_ARG(n_shares);
+  GDM_ARG(n_jobs);
+  std::vector<int> ptr, jobs;
+  pers_partition_host(tiles_x, tiles_y, k0, k1, slots, min_len, aligned != 0, 0, ptr, jobs);
+  *n_shares = (int32_t)ptr.size() - 1;
+  *n_jobs   = (int32_t)(jobs.size() / 6);
+  GDM_REQUIRE(job_ptr != nullptr && jobs6 != nullptr && cap_ptr >= (int32_t)ptr.size() && cap_jobs >= *n_jobs, GDM_ERR_INVALID,
+              "partition buffers too small");
+  for (size_t i = 0; i < ptr.size(); ++i)
+    job_ptr[i] = ptr[i];
+  for (size_t i = 0; i < jobs.size(); ++i)
+    jobs6[i] = jobs[i];
+  GDM_CATCH
+}
+
 // -------------------------------------------------------------- constraints
 int gdm_constraints_create(gdm_system_t sys, gdm_constraints_t *out)
 {

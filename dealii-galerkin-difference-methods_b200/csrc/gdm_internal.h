@@ -235,6 +235,19 @@ namespace gdm
   void fused_partition_host(bool aligned, int tiles_x, int tiles_y, int z0, int z1, int slots, int p, std::vector<int> &seg_ptr,
                             std::vector<int> &segs4);
 
+  // kron3d_pers.cu -- persistent ramp-free fused kernel (default for dim == 3, scalar, non-periodic)
+  bool  pers_supported(const Operator &op);
+  void *pers_plan_create(Operator &op); // nullptr: not applicable to this operator
+  void  pers_plan_destroy(void *plan);
+  int   pers_max_grid(const Operator &op, const void *plan);
+  // output planes [oz0, oz1) (local indices); dot_partials != nullptr: CTA w leaves its share of <dot_src, A src> in
+  // dot_partials[w]; returns the number of CTAs launched
+  int   pers_launch(Operator &op, void *plan, double *dst, const double *src, bool accumulate, int oz0, int oz1, cudaStream_t stream,
+                    const double *dot_src, double *dot_partials);
+  int   pers_error_flag(void *plan);
+  void  pers_partition_host(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, bool aligned, int forced_L,
+                            std::vector<int> &job_ptr, std::vector<int> &jobs6);
+
   // blas1.cu
   enum SumSlot
   {

@@ -992,6 +992,7 @@ namespace gdm
 
     struct FusedPlan
     {
+      void    *pers = nullptr; // persistent ramp-free kernel (kron3d_pers.cu); used for every launch when set
       int      cfg = 0;     // index into GDM_FUSED_CONFIGS
       int      tiles_x = 0, tiles_y = 0, n_chunks = 0, lz = 0;
       int      cx0, cx1, cy0, cy1, cz0, cz1, xorg;
@@ -1022,6 +1023,8 @@ namespace gdm
       std::map<const void *, CUtensorMap> maps;
       ~FusedPlan()
       {
+        if (pers)
+          pers_plan_destroy(pers);
         cudaFree(d_zsA);
         cudaFree(d_zsB);
         cudaFree(d_Be[0]);
@@ -1536,6 +1539,12 @@ namespace gdm
       z1 = std::min(z1, L.nn[2] - 1);
     plan->cz0 = z0 - L.loc0;
     plan->cz1 = std::max(z1 - L.loc0, plan->cz0);
+    {
+      // default family: the persistent ramp-free kernel; GDM_FUSED_FAMILY=3|4 selects the round-1 tile kernels
+      const char *fam = std::getenv("GDM_FUSED_FAMILY");
+      if ((!fam || fam[0] == '8') && !std::getenv("GDM_FUSED_CFG") && pers_supported(op))
+        plan->pers = pers_plan_create(op);
+    }
     int tx = 32, ty = 32, min_blocks = 2;
     plan->cfg = default_config(P);
     with_config(plan->cfg, [&](auto c) {
@@ -1566,7 +1575,7 @@ namespace gdm
     lz             = std::max(lz, 1);
     plan->lz       = lz;
     plan->n_chunks = (nz + lz - 1) / lz;
-    plan->tune     = !lz_forced && (int64_t)nz * (plan->cx1 - plan->cx0) * (plan->cy1 - plan->cy0) > (int64_t)(1 << 21);
+    plan->tune     = !plan->pers && !lz_forced && (int64_t)nz * (plan->cx1 - plan->cx0) * (plan->cy1 - plan->cy0) > (int64_t)(1 << 21);
     // scatter rows: zs[k][j] = scale * T_z[k - P + j][2P - j]
     std::vector<double> zsA((size_t)L.ln[2] * W, 0.0), zsB((size_t)L.ln[2] * W, 0.0);
     for (int k = 0; k < L.ln[2]; ++k)
@@ -1681,9 +1690,33 @@ namespace gdm
     op.fused = nullptr;
   }
 
+  // one launch of the persistent kernel over the current output window of the plan
+  static void dispatch_pers(Operator &op, FusedPlan &plan, double *dst, const double *src, bool accumulate)
+  {
+    Context  &ctx = *op.sys->ctx;
+    const int z0  = (plan.wz0 >= 0) ? plan.wz0 : plan.cz0;
+    const int z1  = (plan.wz0 >= 0) ? plan.wz1 : plan.cz1;
+    double   *dp  = nullptr;
+    if (plan.dot_cursor >= 0)
+      {
+        GDM_REQUIRE(!accumulate && (size_t)(plan.dot_cursor + pers_max_grid(op, plan.pers)) <= plan.dot_cap, GDM_ERR_INTERNAL,
+                    "fused dot: partial buffer too small");
+        dp = plan.d_dot + plan.dot_cursor;
+      }
+    const int grid = pers_launch(op, plan.pers, dst, src, accumulate, z0, z1, plan.use_comm_stream ? ctx.comm_stream : ctx.stream,
+                                 dp ? plan.dot_src : nullptr, dp);
+    if (dp)
+      plan.dot_cursor += grid;
+  }
+
   template <class C>
   static void dispatch(Operator &op, FusedPlan &plan, double *dst, const double *src, bool accumulate)
   {
+    if (plan.pers)
+      {
+        dispatch_pers(op, plan, dst, src, accumulate);
+        return;
+      }
     const CUtensorMap &map = get_map<C>(op, plan, src);
     if (!op.has_B)
       accumulate ? launch_variant<C, false, +1, true>(op, plan, map, dst) : launch_variant<C, false, +1, false>(op, plan, map, dst);
@@ -1698,6 +1731,8 @@ namespace gdm
     if (!op.fused)
       return false;
     const FusedPlan &plan = *static_cast<const FusedPlan *>(op.fused);
+    if (plan.pers)
+      return true;
     bool             ok   = false;
     // the store epilogue with the dot product exists in the v3 tile kernel and in v4
     with_config(plan.cfg, [&](auto c) {
@@ -1781,7 +1816,9 @@ namespace gdm
         const int    tiles   = std::max(1, plan.tiles_x * plan.tiles_y);
         const int    nzw     = std::max(1, plan.cz1 - plan.cz0);
         const int    lz_min  = std::max(1, std::min(plan.lz, P));
-        const size_t need    = (size_t)tiles * (nzw / lz_min + 4) + (size_t)constrained_rows_max_blocks(L) + 64;
+        size_t       need    = (size_t)tiles * (nzw / lz_min + 4) + (size_t)constrained_rows_max_blocks(L) + 64;
+        if (plan.pers)
+          need = (size_t)3 * pers_max_grid(op, plan.pers) + (size_t)constrained_rows_max_blocks(L) + 64;
         if (need > plan.dot_cap)
           {
             GDM_CUDA_CHECK(cudaDeviceSynchronize());

@@ -1,0 +1,1425 @@
+// kron3d_pers -- persistent, ramp-free fused 3D tensor-product apply (sm_100a).
+//
+//     y = scale * ( B_x (x) A_y (x) A_z  +  A_x (x) B_y (x) A_z  +  A_x (x) A_y (x) B_z ) x      (stiffness / advection)
+//     y = scale * ( A_x (x) A_y (x) A_z ) x                                                      (mass)
+//
+// Replaces SparseMatrix::vmult of the assembled operator (reference: tests/poisson_02_gdm.cc:215,
+// prototypes/advection_01_gdm.cc:216, applications/wave/include/gdm/wave/problem.h:486-488).
+//
+// Same arithmetic as the round-1 tile kernels (TMA-staged (TX+2P) x (TY+2P) tile per plane, x pass -> transposed a/r
+// fields in shared memory -> y pass -> z pass in registers in scatter form, tap split K_d = alpha_d M_d + R_d), but
+// the work decomposition is new:
+//   * one CTA per resident slot (grid = SMs x CTAs/SM), every CTA streams an equal share of the (tile, plane) work list;
+//   * a CTA only processes the input planes of its own share: there is NO z ramp.  At a seam between two shares of one
+//     tile column the upper share writes its first 2P emitted (partial) planes to a small scratch area and raises a
+//     flag; the lower share adds them to its 2P running accumulators when it flushes, so every output plane is
+//     written exactly once, by one CTA, in a fixed order (bitwise reproducible, no atomics on data);
+//   * work is handed out by a ticket (atomicAdd) in descending share order, so a CTA only ever waits for a share that
+//     was started before it: no deadlock even if the grid is not fully resident;
+//   * the planes of consecutive jobs of a CTA form one sequence for the TMA pipeline (no refill bubble at a job switch);
+//   * planes that cannot contribute (Dirichlet planes, zero fill outside the slab) are never staged.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <type_traits>
+
+#include "gdm_internal.h"
+
+namespace gdm
+{
+  namespace
+  {
+    // ------------------------------------------------------------------ PTX helpers
+    __device__ __forceinline__ uint32_t smem_u32(const void *p)
+    {
+      return (uint32_t)__cvta_generic_to_shared(p);
+    }
+    __device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count)
+    {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    }
+    __device__ __forceinline__ void mbar_fence_init()
+    {
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes)
+    {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    }
+    __device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity)
+    {
+      asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+    }
+    __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+    {
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                   "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                   : "memory");
+    }
+    __device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+    {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+      return v;
+    }
+    __device__ __forceinline__ void st_release(unsigned *p, unsigned v)
+    {
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    }
+
+    // ------------------------------------------------------------------ configuration
+    template <int P_, int RY_, int NW_, int RX_, int STAGES_, int MINB_>
+    struct CfgP
+    {
+      static constexpr int  P = P_, TX = 32, RY = RY_, NW = NW_, RX = RX_, STAGES = STAGES_, MINB = MINB_;
+      static constexpr int  W       = 2 * P + 1;
+      static constexpr int  TY      = RY * NW;
+      static constexpr int  NR      = TY + 2 * P;                   // rows of the staged tile
+      static constexpr int  PIN     = TX + 2 * P;                   // pitch of the staged tile (dense TMA box)
+      static constexpr int  PY      = ((NR / 2) & 1) ? NR : NR + 2; // column pitch of the transposed a/r fields
+      static constexpr int  THREADS = 32 * NW;
+      static constexpr int  NXB     = TX / RX;
+      // x pass: warp tasks (x block, group of 32 rows); the NR % 32 rows left over are block tasks packed densely
+      // (lane <-> (x block, row)) into NLW more warp tasks; the task -> warp map rotates with the plane counter so that
+      // no scheduler owns the extra tasks permanently
+      static constexpr int  NG_FULL  = NR / 32;
+      static constexpr int  REM      = NR % 32;
+      static constexpr int  NWT_FULL = NXB * NG_FULL;
+      static constexpr int  NLT      = REM * NXB; // left-over thread tasks
+      static constexpr int  NLW      = (NLT + 31) / 32;
+      static constexpr int  NWT      = NWT_FULL + NLW;
+      static constexpr int  ROUNDS   = (NWT + NW - 1) / NW;
+      static constexpr int  NBT        = 2 * (P + 1);
+      static constexpr int  WP         = 8 * ((W + 7) / 8);
+      static constexpr int  TB_DOUBLES = 2 * 2 * NBT * WP;
+      static constexpr int  ZROWS      = 2 * W; // non-Toeplitz plane classes: 2P+1 at either end
+      static constexpr int  WZ         = W + 1;
+      static constexpr int  ZT_DOUBLES = ZROWS * 2 * WZ;
+      static constexpr int  STAGE_DOUBLES = (NR * PIN + 15) / 16 * 16;
+      static_assert(TX % RX == 0 && RX % 2 == 0 && NR % 2 == 0 && RY % 2 == 0, "tile shape");
+      static_assert(((PIN / 2) & 1) == 1 && ((PY / 2) & 1) == 1, "16-byte pitches must be odd for conflict-free LDS.128");
+    };
+
+    struct JobP // one contiguous run of input planes of one tile column
+    {
+      int x0, y0;   // first output column / row of the tile
+      int k0, k1;   // input planes [k0, k1) (local plane indices)
+      int seam_lo;  // >= 0: the first 2P emitted planes are partial sums owned by the job below: scratch slot
+      int seam_hi;  // >= 0: the job above left its partial sums for the 2P planes this job flushes in this slot
+      int pad0, pad1;
+    };
+
+    template <int P>
+    struct ArgsP
+    {
+      double       *dst;
+      int64_t       pitch, plane;
+      int           cx0, cx1, cy0, cy1, cz0, cz1; // output window (local node indices)
+      int           nx, ny;                       // cells per direction (boundary rows: <= P or >= N-P)
+      int           nz_local;
+      int           kz_lo, kz_hi;                 // input planes [kz_lo, kz_hi) only touch Toeplitz z rows
+      int           grid;                         // number of shares
+      unsigned      ticket_base, epoch;
+      const double *tabAx, *tabBx, *tabAy, *tabBy; // row tables [node][2P+1]
+      double        Ax[P + 1], Bx[P + 1], Ay[P + 1], By[P + 1]; // interior taps by distance
+      double        Az[2 * P + 1], Bz[2 * P + 1];               // interior scatter row, scale folded in
+      double        sigma;                                      // tap split: sum_d alpha_d
+      const double *zt;                                         // scatter rows of the non-Toeplitz plane classes [class][field][W+1]
+      const JobP   *jobs;
+      const int    *job_ptr; // jobs of share w: [job_ptr[w], job_ptr[w+1])
+      unsigned     *ticket;  // work counter (monotone; ticket_base = its value before this launch)
+      unsigned     *flags;   // [job]: == epoch once the job's first 2P partial planes are in scratch
+      double       *scratch; // [job][2P][TY][TX]
+      int          *error;   // set if a seam wait timed out
+      long long    *trace;   // diagnostic (GDM_PERS_TRACE): per share {clock cycles, SM id}
+      const double *dot_src; // fused dot product <src, A src>: every CTA writes its sum to dot_partials[share]
+      double       *dot_partials;
+    };
+
+    template <class C, bool HASB>
+    constexpr size_t smem_bytes_p()
+    {
+      return (size_t)(C::STAGES * C::STAGE_DOUBLES + 2 * (HASB ? 2 : 1) * C::TX * C::PY + C::ZT_DOUBLES + C::TB_DOUBLES) * sizeof(double) +
+             (size_t)C::STAGES * sizeof(uint64_t) + 64 + 128;
+    }
+
+    // MODE 0: mass; MODE 1: B symmetric with the tap split (B tables hold R = B - alpha A); MODE 2: B antisymmetric.
+    // The per-thread state of the kernel lives in one object whose members stay in registers (everything is inlined and
+    // every array index is a compile-time constant after unrolling).
+    template <class C, int MODE, bool ACCUM, bool DOT>
+    struct PersWorker
+    {
+      static constexpr int  P = C::P, W = C::W, TX = C::TX, TY = C::TY, RY = C::RY, RX = C::RX, NR = C::NR, PIN = C::PIN, PY = C::PY;
+      static constexpr bool HASB = MODE != 0, SYM = MODE == 1;
+      static constexpr int  NF = HASB ? 2 : 1;
+      static constexpr int  PB = SYM ? P - 1 : P; // outermost tap of the interior B rows in x and y
+      static constexpr int  S  = C::STAGES;
+      static constexpr int  AB_BUF   = NF * TX * PY; // [field][x][PY] (y contiguous)
+      static constexpr int  OFF_AB   = S * C::STAGE_DOUBLES;
+      static constexpr int  OFF_ZT   = OFF_AB + 2 * AB_BUF;
+      static constexpr int  OFF_TB   = OFF_ZT + C::ZT_DOUBLES;
+      static constexpr int  OFF_BAR  = OFF_TB + C::TB_DOUBLES;
+      static constexpr int  OFF_MISC = OFF_BAR + S;
+      static constexpr int  WP = C::WP, NBT = C::NBT, WZ = C::WZ;
+      static constexpr unsigned STAGE_BYTES = NR * PIN * sizeof(double);
+      static constexpr int  FULL_ROUNDS = C::NWT / C::NW, EXTRA = C::NWT % C::NW;
+      static_assert(sizeof(JobP) == 2 * sizeof(int4), "job size");
+      static_assert(EXTRA == 0 || C::NW > 1, "x pass task map");
+
+      const ArgsP<P>    &g;
+      const CUtensorMap *tmap;
+      double            *smem;
+      uint32_t           sb, bar0;
+      int                tid, lane, warp, yz_off;
+      double             acc[RY][2 * P];
+      double             dsum; // fused dot product (DOT): sum of src * (A src) over the points this thread stores
+      // pipeline state: seq = number of planes whose x pass is done; everything else is derived from it
+      int seq;
+      int njobs, jb;
+      // (the TMA issue cursor of thread 0 -- job index, job, next plane -- lives in shared memory: smisc[4..12))
+
+      struct JobCtx // per-thread view of the current job
+      {
+        JobP    J;
+        bool    more;      // another job follows in this share
+        int     gy_first;  // first row of this thread
+        int     nst;       // rows i < nst of this thread are stored
+        double *out;       // output plane k - P at (gy_first, gx)
+        double *sp;        // scratch slot position of this thread
+        int     k_scr;     // planes k < k_scr emit into the scratch slot
+        int     x0_next;   // x origin of the job that follows
+      };
+
+      __device__ __forceinline__ PersWorker(const ArgsP<P> &g_, const CUtensorMap *tmap_, double *smem_)
+        : g(g_)
+        , tmap(tmap_)
+        , smem(smem_)
+      {}
+
+      __device__ __forceinline__ JobP load_job(const int j) const
+      {
+        const int4 *q = reinterpret_cast<const int4 *>(g.jobs + j);
+        const int4  a = __ldg(q), b = __ldg(q + 1);
+        JobP        J;
+        J.x0 = a.x, J.y0 = a.y, J.k0 = a.z, J.k1 = a.w, J.seam_lo = b.x, J.seam_hi = b.y, J.pad0 = 0, J.pad1 = 0;
+        return J;
+      }
+
+      // thread 0: request the next plane of the share's plane sequence into stage st
+      __device__ __forceinline__ void issue(const int st)
+      {
+        int *cur = reinterpret_cast<int *>(smem + OFF_MISC) + 4; // {ij, ik, x0 - P, y0 - P, k1}
+        const int ij = cur[0];
+        if (ij >= njobs)
+          return;
+        const int ik = cur[1];
+        mbar_expect_tx(bar0 + 8 * st, STAGE_BYTES);
+        tma_load_3d(sb + st * C::STAGE_DOUBLES * 8, tmap, bar0 + 8 * st, cur[2], cur[3], ik);
+        if (ik + 1 >= cur[4])
+          {
+            cur[0] = ij + 1;
+            if (ij + 1 < njobs)
+              {
+                const JobP Jn = load_job(jb + ij + 1);
+                cur[1]        = Jn.k0;
+                cur[2]        = Jn.x0 - P;
+                cur[3]        = Jn.y0 - P;
+                cur[4]        = Jn.k1;
+              }
+          }
+        else
+          cur[1] = ik + 1;
+      }
+      // stage / parity of the TMA ring and a/r buffers of plane sequence number q
+      __device__ __forceinline__ int      stage_of(const int q) const { return q % S; }
+      __device__ __forceinline__ unsigned parity_of(const int q) const { return (unsigned)(q / S) & 1u; }
+      __device__ __forceinline__ int      ab_of(const int q) const { return OFF_AB + (q & 1) * AB_BUF; }
+
+      // ---- x pass of one plane: staged tile at in_off -> a/r buffer at a_off (doubles); x0 = first output column.
+      // FIX: the tile touches one-sided rows of A_x/B_x (recomputed from the row tables by the threads that own them).
+      template <bool FIX>
+      __device__ __forceinline__ void x_task(const int wt, const int in_off, const int a_off, const int x0)
+      {
+        const int      b_off = a_off + (NF - 1) * TX * PY;
+        int            xb, r;
+        if (wt < C::NWT_FULL)
+          {
+            xb = wt % C::NXB;
+            r  = (wt / C::NXB) * 32 + lane;
+          }
+        else
+          {
+            const int idx = (wt - C::NWT_FULL) * 32 + lane;
+            if (idx >= C::NLT)
+              return;
+            xb = idx / C::REM;
+            r  = C::NG_FULL * 32 + idx % C::REM;
+          }
+        double v[RX + 2 * P];
+        {
+          const double2 *src = reinterpret_cast<const double2 *>(smem + in_off + r * PIN + xb * RX);
+#pragma unroll
+          for (int q = 0; q < (RX + 2 * P) / 2; ++q)
+            {
+              const double2 t = src[q];
+              v[2 * q]        = t.x;
+              v[2 * q + 1]    = t.y;
+            }
+        }
+        double a[RX], bb[RX];
+#pragma unroll
+        for (int j = 0; j < RX; ++j)
+          {
+            const int c   = j + P;
+            double    ra  = g.Ax[0] * v[c];
+            double    rbv = (HASB && SYM) ? g.Bx[0] * v[c] : 0.0;
+#pragma unroll
+            for (int d = 1; d <= P; ++d)
+              {
+                const double s = v[c - d] + v[c + d];
+                ra             = fma(g.Ax[d], s, ra);
+                if (HASB)
+                  {
+                    if (SYM)
+                      {
+                        if (d <= PB)
+                          rbv = fma(g.Bx[d], s, rbv);
+                      }
+                    else
+                      rbv = fma(g.Bx[d], v[c + d] - v[c - d], rbv);
+                  }
+              }
+            a[j]  = ra;
+            bb[j] = rbv;
+          }
+        if constexpr (FIX)
+          {
+            const int gx_first = x0 + xb * RX;
+            if (gx_first <= P || gx_first + RX - 1 >= g.nx - P)
+              {
+#pragma unroll
+                for (int j = 0; j < RX; ++j)
+                  {
+                    const int gxx = gx_first + j;
+                    if ((gxx <= P || gxx >= g.nx - P) && gxx >= 0 && gxx <= g.nx)
+                      {
+                        const int     rc = (gxx <= P) ? gxx : gxx - (g.nx - P) + P + 1;
+                        const double *ta = smem + OFF_TB + (0 * NBT + rc) * WP;
+                        const double *tb = smem + OFF_TB + (1 * NBT + rc) * WP;
+                        double        ra = 0.0, rbv = 0.0;
+#pragma unroll
+                        for (int t = 0; t < W; ++t)
+                          {
+                            ra = fma(ta[t], v[j + t], ra);
+                            if (HASB)
+                              rbv = fma(tb[t], v[j + t], rbv);
+                          }
+                        a[j]  = ra;
+                        bb[j] = rbv;
+                      }
+                  }
+              }
+          }
+        // transposed store: [x][row], consecutive lanes -> consecutive rows
+#pragma unroll
+        for (int j = 0; j < RX; ++j)
+          {
+            smem[a_off + (xb * RX + j) * PY + r] = a[j];
+            if (HASB)
+              smem[b_off + (xb * RX + j) * PY + r] = bb[j];
+          }
+      }
+
+      // Task -> warp map: full rounds warp + rd NW; the NWT % NW tasks left over rotate over warps 1..NW-1 with the plane
+      // counter (warp 0 issues the TMA loads instead)
+      // x pass of plane sequence number q (waits for its TMA stage)
+      template <bool FIX>
+      __device__ __forceinline__ void x_pass(const int q, const int x0)
+      {
+        const int st = stage_of(q);
+        mbar_wait(bar0 + 8 * st, parity_of(q));
+        const int in_off = st * C::STAGE_DOUBLES, a_off = ab_of(q);
+#pragma unroll
+        for (int rd = 0; rd < FULL_ROUNDS; ++rd)
+          x_task<FIX>(warp + rd * C::NW, in_off, a_off, x0);
+        if constexpr (EXTRA > 0)
+          {
+            const int e = (warp - 1 + q) % (C::NW - 1);
+            if (warp != 0 && e < EXTRA)
+              x_task<FIX>(FULL_ROUNDS * C::NW + e, in_off, a_off, x0);
+          }
+      }
+
+      // ---- y pass + z pass of input plane k from the a/r buffer at ab_off: res = emitted plane k - P.
+      // FIX: the tile touches one-sided rows of A_y/B_y; TOEP: plane k only touches Toeplitz rows of A_z/B_z.
+      // Row by row: the y result of a row goes straight into the z accumulators (few values live at a time).
+      template <bool FIX, bool TOEP>
+      __device__ __forceinline__ void yz_rows(const double (&zA)[W], const double (&zB)[W], const int ab_off, const int gy_first,
+                                              double (&res)[RY])
+      {
+        constexpr bool OUTER = HASB && !(SYM && TOEP); // outer taps of the B chain present in z
+        double         aw[RY + 2 * P], bw[RY + 2 * P];
+        const double2 *pa = reinterpret_cast<const double2 *>(smem + ab_off + yz_off);
+        const double2 *pb = reinterpret_cast<const double2 *>(smem + ab_off + (NF - 1) * TX * PY + yz_off);
+#pragma unroll
+        for (int q = 0; q < (RY + 2 * P) / 2; ++q)
+          {
+            const double2 t = pa[q];
+            aw[2 * q]       = t.x;
+            aw[2 * q + 1]   = t.y;
+            if (HASB)
+              {
+                const double2 s = pb[q];
+                bw[2 * q]       = s.x;
+                bw[2 * q + 1]   = s.y;
+              }
+          }
+        [[maybe_unused]] const bool y_edge = FIX && (gy_first <= P || gy_first + RY - 1 >= g.ny - P);
+#pragma unroll
+        for (int i = 0; i < RY; ++i)
+          {
+            const int c  = i + P;
+            double    t1 = g.Ay[0] * aw[c], t2 = 0.0;
+            if (HASB)
+              {
+                t2 = g.Ay[0] * bw[c];
+                if (SYM)
+                  t2 = fma(g.By[0], aw[c], t2);
+              }
+#pragma unroll
+            for (int d = 1; d <= P; ++d)
+              {
+                const double sa = aw[c - d] + aw[c + d];
+                t1              = fma(g.Ay[d], sa, t1);
+                if (HASB)
+                  {
+                    const double sbv = bw[c - d] + bw[c + d];
+                    t2               = fma(g.Ay[d], sbv, t2);
+                    if (SYM)
+                      {
+                        if (d <= PB)
+                          t2 = fma(g.By[d], sa, t2);
+                      }
+                    else
+                      t2 = fma(g.By[d], aw[c + d] - aw[c - d], t2);
+                  }
+              }
+            if constexpr (FIX)
+              if (y_edge)
+                {
+                  const int gy = gy_first + i;
+                  if ((gy <= P || gy >= g.ny - P) && gy <= g.ny)
+                    {
+                      const int     rc = (gy <= P) ? gy : gy - (g.ny - P) + P + 1;
+                      const double *ta = smem + OFF_TB + (2 * NBT + rc) * WP;
+                      const double *tb = smem + OFF_TB + (3 * NBT + rc) * WP;
+                      t1               = 0.0;
+                      t2               = 0.0;
+#pragma unroll
+                      for (int t = 0; t < W; ++t)
+                        {
+                          const double ca = ta[t];
+                          t1              = fma(ca, aw[i + t], t1);
+                          if (HASB)
+                            {
+                              t2 = fma(ca, bw[i + t], t2);
+                              t2 = fma(tb[t], aw[i + t], t2);
+                            }
+                        }
+                    }
+                }
+            // z pass, scatter form: y_r += A_z[r][k] ua + R_z[r][k] t1 for the 2P+1 rows r around input plane k; the
+            // accumulators shift by one plane through the FMAs themselves.  Tap split (SYM): the A chain runs on
+            // ua = t2 + sigma t1 and the R chain has no outer taps on Toeplitz planes.
+            double ua = t1;
+            if (HASB)
+              ua = SYM ? fma(g.sigma, t1, t2) : t2;
+            double r0 = fma(zA[0], ua, acc[i][0]);
+            if (OUTER)
+              r0 = fma(zB[0], t1, r0);
+            res[i] = r0;
+#pragma unroll
+            for (int j = 1; j < 2 * P; ++j)
+              {
+                double s = fma(zA[j], ua, acc[i][j]);
+                if (HASB)
+                  s = fma(zB[j], t1, s);
+                acc[i][j - 1] = s;
+              }
+            double s = zA[2 * P] * ua;
+            if (OUTER)
+              s = fma(zB[2 * P], t1, s);
+            acc[i][2 * P - 1] = s;
+          }
+      }
+
+      template <bool FIX>
+      __device__ __forceinline__ void yz_pass(const bool toep, const int k, const int ab_off, const int gy_first, double (&res)[RY])
+      {
+        if (toep)
+          yz_rows<FIX, true>(g.Az, g.Bz, ab_off, gy_first, res);
+        else
+          {
+            // plane class: planes below kz_lo by index, planes from kz_hi on after them
+            const int kk = min(max(k, 0), g.nz_local - 1);
+            const int c  = (kk < g.kz_lo) ? kk : g.kz_lo + (kk - g.kz_hi);
+            double    zA[W], zB[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+              {
+                zA[j] = smem[OFF_ZT + (c * 2 + 0) * WZ + j];
+                zB[j] = HASB ? smem[OFF_ZT + (c * 2 + 1) * WZ + j] : 0.0;
+              }
+            yz_rows<FIX, false>(zA, zB, ab_off, gy_first, res);
+          }
+      }
+
+      // store RY values of an output plane (rows gy_first + i, column gx); FULL: every row and column of the tile is valid
+      template <bool FULL>
+      __device__ __forceinline__ void store_rows(double *o, const double (&val)[RY], const int nst)
+      {
+#pragma unroll
+        for (int i = 0; i < RY; ++i)
+          if (FULL || i < nst)
+            {
+              double *q = o + (int64_t)i * g.pitch;
+              double  t = val[i];
+              if constexpr (DOT)
+                dsum = fma(__ldg(g.dot_src + (q - g.dst)), t, dsum);
+              if (ACCUM)
+                t += *q;
+              *q = t;
+            }
+      }
+
+      // general planes [ka, kb) of the job: every flag is evaluated per plane
+      __device__ __forceinline__ void slow_planes(JobCtx &c, const int ka, const int kb)
+      {
+        for (int k = ka; k < kb; ++k)
+          {
+            const bool last = (k + 1 == c.J.k1);
+            if (!last || c.more)
+              x_pass<true>(seq, last ? c.x0_next : c.J.x0);
+            double res[RY];
+            yz_pass<true>(k >= g.kz_lo && k < g.kz_hi, k, ab_of(seq - 1), c.gy_first, res);
+            if (k < c.k_scr)
+              {
+#pragma unroll
+                for (int i = 0; i < RY; ++i)
+                  __stcg(c.sp + i * TX, res[i]);
+                c.sp += TY * TX;
+              }
+            else if (k - P >= g.cz0)
+              store_rows<false>(c.out, res, c.nst);
+            __syncthreads();
+            if (tid == 0)
+              {
+                issue(stage_of(seq));
+                if (k + 1 == c.k_scr && c.J.seam_lo >= 0)
+                  {
+                    __threadfence();
+                    st_release(g.flags + c.J.seam_lo, g.epoch);
+                  }
+              }
+            ++seq;
+            c.out += g.plane;
+          }
+      }
+
+      // fast planes [ka, kb): stored to dst, Toeplitz in z, followed by another plane of this job; INNER tiles touch no
+      // one-sided row in x or y and store every row and column: their plane body has no data-dependent branch
+      template <bool INNER>
+      __device__ __forceinline__ void fast_planes(JobCtx &c, const int ka, const int kb)
+      {
+        for (int k = ka; k < kb; ++k)
+          {
+            x_pass<!INNER>(seq, c.J.x0);
+            double res[RY];
+            yz_rows<!INNER, true>(g.Az, g.Bz, ab_of(seq - 1), c.gy_first, res);
+            store_rows<INNER>(c.out, res, c.nst);
+            __syncthreads();
+            if (tid == 0)
+              issue(stage_of(seq));
+            ++seq;
+            c.out += g.plane;
+          }
+      }
+
+      __device__ __forceinline__ void run()
+      {
+        sb   = smem_u32(smem);
+        bar0 = sb + OFF_BAR * 8;
+        tid  = threadIdx.x;
+        lane = tid & 31;
+        warp = tid >> 5;
+        const long long t_start = clock64();
+        int            *smisc   = reinterpret_cast<int *>(smem + OFF_MISC);
+
+        if (tid == 0)
+          {
+            for (int s = 0; s < S; ++s)
+              mbar_init(bar0 + 8 * s, 1);
+            mbar_fence_init();
+            const unsigned t = atomicAdd(g.ticket, 1u) - g.ticket_base;
+            smisc[0]         = g.grid - 1 - (int)t; // descending: a share only waits for shares with a larger index
+          }
+        // one-sided rows of A/B in x and y (row class c: node c for c <= P, node N-P+(c-P-1) above)
+        for (int e = tid; e < 2 * 2 * NBT * W; e += C::THREADS)
+          {
+            const int     t = e % W, c = (e / W) % NBT, f = (e / (W * NBT)) % 2, d = e / (W * NBT * 2);
+            const int     n    = d ? g.ny : g.nx;
+            const int     node = (c <= P) ? c : n - P + (c - P - 1);
+            const double *tab  = d ? (f ? g.tabBy : g.tabAy) : (f ? g.tabBx : g.tabAx);
+            smem[OFF_TB + ((d * 2 + f) * NBT + c) * WP + t] = (HASB || f == 0) ? __ldg(tab + node * W + t) : 0.0;
+          }
+        for (int e = tid; e < C::ZT_DOUBLES; e += C::THREADS)
+          smem[OFF_ZT + e] = __ldg(g.zt + e);
+        __syncthreads();
+        const int share = smisc[0];
+        jb              = __ldg(g.job_ptr + share);
+        njobs           = __ldg(g.job_ptr + share + 1) - jb;
+        if (njobs <= 0)
+          {
+            if constexpr (DOT)
+              if (tid == 0)
+                g.dot_partials[share] = 0.0;
+            return;
+          }
+        JobP Jn = load_job(jb); // next job of the compute loop (every thread); the issuer keeps its own cursor
+        if (tid == 0)
+          {
+            int *cur = smisc + 4;
+            cur[0]   = 0;
+            cur[1]   = Jn.k0;
+            cur[2]   = Jn.x0 - P;
+            cur[3]   = Jn.y0 - P;
+            cur[4]   = Jn.k1;
+            for (int s = 0; s < S; ++s)
+              issue(s);
+          }
+
+        // y/z pass ownership: lane -> x, warp -> RY consecutive rows
+        yz_off = lane * PY + warp * RY; // start of this thread's window in an a/r buffer
+#pragma unroll
+        for (int i = 0; i < RY; ++i)
+#pragma unroll
+          for (int j = 0; j < 2 * P; ++j)
+            acc[i][j] = 0.0;
+        dsum = 0.0;
+
+        // prologue: x pass of the first plane of the first job
+        seq = 0;
+        x_pass<true>(0, Jn.x0);
+        __syncthreads();
+        if (tid == 0)
+          issue(0);
+        seq = 1;
+
+        for (int j = 0; j < njobs; ++j)
+          {
+            JobCtx c;
+            c.J    = Jn;
+            c.more = j + 1 < njobs;
+            if (c.more)
+              Jn = load_job(jb + j + 1);
+            const int gx = c.J.x0 + lane;
+            c.gy_first   = c.J.y0 + warp * RY;
+            c.nst        = (gx >= g.cx0 && gx < g.cx1) ? (g.cy1 - c.gy_first) : 0;
+            c.out        = g.dst + (int64_t)(c.J.k0 - P) * g.plane + (int64_t)c.gy_first * g.pitch + gx;
+            c.sp         = g.scratch + ((int64_t)max(c.J.seam_lo, 0) * (2 * P)) * (TY * TX) + (warp * RY) * TX + lane;
+            c.k_scr      = (c.J.seam_lo >= 0) ? c.J.k0 + 2 * P : c.J.k0;
+            c.x0_next    = Jn.x0;
+            const bool inner = c.J.x0 > P && c.J.x0 + TX - 1 < g.nx - P && c.J.y0 > P && c.J.y0 + TY - 1 < g.ny - P &&
+                               c.J.x0 >= g.cx0 && c.J.x0 + TX <= g.cx1 && c.J.y0 >= g.cy0 && c.J.y0 + TY <= g.cy1;
+            const int fa = max(max(c.J.k0, c.k_scr), max(g.cz0 + P, g.kz_lo));
+            const int fb = min(c.J.k1 - 1, g.kz_hi);
+            if (fb > fa)
+              {
+                slow_planes(c, c.J.k0, fa);
+                if (inner)
+                  fast_planes<true>(c, fa, fb);
+                else
+                  fast_planes<false>(c, fa, fb);
+                slow_planes(c, fb, c.J.k1);
+              }
+            else
+              slow_planes(c, c.J.k0, c.J.k1);
+            // ---- flush: output planes k1-P .. k1+P-1 hold the sums of this job's planes; the job above adds the rest
+            const double *sq = nullptr;
+            if (c.J.seam_hi >= 0)
+              {
+                if (tid == 0)
+                  {
+                    const unsigned *f  = g.flags + c.J.seam_hi;
+                    const long long t0 = clock64();
+                    while (ld_acquire(f) != g.epoch)
+                      {
+                        __nanosleep(64);
+                        if (clock64() - t0 > (1ll << 32))
+                          {
+                            *g.error = 1;
+                            break;
+                          }
+                      }
+                  }
+                __syncthreads();
+                sq = g.scratch + ((int64_t)c.J.seam_hi * (2 * P)) * (TY * TX) + (warp * RY) * TX + lane;
+              }
+#pragma unroll
+            for (int jz = 0; jz < 2 * P; ++jz)
+              {
+                const int o = c.J.k1 - P + jz;
+                double    val[RY];
+#pragma unroll
+                for (int i = 0; i < RY; ++i)
+                  {
+                    val[i]     = acc[i][jz];
+                    acc[i][jz] = 0.0;
+                  }
+                if (sq != nullptr)
+                  {
+#pragma unroll
+                    for (int i = 0; i < RY; ++i)
+                      val[i] += __ldcg(sq + (int64_t)jz * (TY * TX) + i * TX);
+                  }
+                if (o >= g.cz0 && o < g.cz1)
+                  store_rows<false>(c.out, val, c.nst);
+                c.out += g.plane;
+              }
+          }
+        if (g.trace != nullptr && tid == 0)
+          {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g.trace[2 * share]     = clock64() - t_start;
+            g.trace[2 * share + 1] = (long long)smid;
+          }
+        if constexpr (DOT)
+          {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+              dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+            __syncthreads(); // shared memory is no longer read by anyone
+            if (lane == 0)
+              smem[warp] = dsum;
+            __syncthreads();
+            if (tid == 0)
+              {
+                double t = 0.0;
+                for (int w = 0; w < C::NW; ++w)
+                  t += smem[w];
+                g.dot_partials[share] = t;
+              }
+          }
+      }
+    };
+
+    template <class C, int MODE, bool ACCUM, bool DOT>
+    __global__ void __launch_bounds__(C::THREADS, C::MINB) kron3d_pers_kernel(const __grid_constant__ CUtensorMap tmap, const ArgsP<C::P> g)
+    {
+      extern __shared__ __align__(128) double smem[];
+      PersWorker<C, MODE, ACCUM, DOT> w(g, &tmap, smem);
+      w.run();
+    }
+
+    // ------------------------------------------------------------------ host side
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+    EncodeTiledFn encode_fn()
+    {
+      static EncodeTiledFn fn = nullptr;
+      if (!fn)
+        {
+          void                           *p = nullptr;
+          cudaDriverEntryPointQueryResult qres;
+          GDM_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+          GDM_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, GDM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+          fn = reinterpret_cast<EncodeTiledFn>(p);
+        }
+      return fn;
+    }
+
+    struct PartitionP // work partition of one output-plane window
+    {
+      int       grid = 0, n_jobs = 0, n_seams = 0;
+      JobP     *d_jobs = nullptr;
+      int      *d_ptr  = nullptr;
+      unsigned *d_sync = nullptr; // [0] ticket, [1] error, [2 ...] flags per job
+      double   *d_scratch = nullptr;
+      long long *d_trace  = nullptr;
+      std::vector<JobP> h_jobs;
+      std::vector<int>  h_ptr;
+      unsigned  ticket_base = 0, epoch = 0;
+      int64_t   max_planes = 0;
+    };
+
+    struct PersPlan
+    {
+      int      cfg = 0;
+      int      tiles_x = 0, tiles_y = 0;
+      int      cx0, cx1, cy0, cy1, cz0, cz1, xorg;
+      int      in_lo = 0, in_hi = 0; // stored input planes that can contribute (local indices)
+      int      mode = 0;
+      double   sigma = 0.0;
+      int      kz_lo = 0, kz_hi = 0;
+      std::vector<double> hBe[3];
+      double  *d_Be[2] = {nullptr, nullptr};
+      double  *d_zt    = nullptr;
+      std::map<std::pair<int, int>, PartitionP> parts;
+      std::map<const void *, CUtensorMap>        maps;
+      std::map<std::pair<int, const void *>, bool> attr_set; // (device, kernel)
+      ~PersPlan()
+      {
+        cudaFree(d_Be[0]);
+        cudaFree(d_Be[1]);
+        cudaFree(d_zt);
+        for (auto &kv : parts)
+          free_part(kv.second);
+      }
+      static void free_part(PartitionP &p)
+      {
+        cudaFree(p.d_jobs);
+        cudaFree(p.d_ptr);
+        cudaFree(p.d_sync);
+        cudaFree(p.d_scratch);
+        cudaFree(p.d_trace);
+      }
+    };
+
+    //                    id   P  RY NW RX ST MINB
+#define GDM_PERS_CONFIGS_CORE(X)      \
+  X(800, CfgP<3, 4, 8, 4, 3, 2>)      \
+  X(801, CfgP<1, 4, 8, 4, 3, 2>)      \
+  X(802, CfgP<5, 4, 8, 4, 3, 2>)
+#ifdef GDM_FUSED_EXPERIMENTAL
+#define GDM_PERS_CONFIGS_EXP(X)       \
+  X(810, CfgP<3, 4, 8, 8, 3, 2>)      \
+  X(811, CfgP<3, 4, 8, 4, 4, 2>)      \
+  X(812, CfgP<3, 8, 4, 8, 3, 2>)      \
+  X(813, CfgP<3, 8, 4, 8, 4, 3>)      \
+  X(814, CfgP<3, 8, 8, 8, 3, 1>)      \
+  X(815, CfgP<3, 2, 16, 4, 3, 1>)      \
+  X(820, CfgP<3, 4, 7, 4, 3, 2>)      \
+  X(821, CfgP<3, 4, 6, 4, 3, 2>)      \
+  X(822, CfgP<3, 4, 7, 4, 4, 2>)      \
+  X(823, CfgP<3, 6, 5, 4, 3, 2>)      \
+  X(824, CfgP<3, 4, 6, 8, 3, 2>)      \
+  X(825, CfgP<3, 4, 6, 4, 4, 2>)
+#else
+#define GDM_PERS_CONFIGS_EXP(X)
+#endif
+#define GDM_PERS_CONFIGS(X) GDM_PERS_CONFIGS_CORE(X) GDM_PERS_CONFIGS_EXP(X)
+
+    template <class F>
+    void with_config(int id, F &&f)
+    {
+      switch (id)
+        {
+#define GDM_CASE(ID, ...) \
+  case ID:                \
+    f(__VA_ARGS__{});     \
+    break;
+          GDM_PERS_CONFIGS(GDM_CASE)
+#undef GDM_CASE
+          default:
+            throw Error(GDM_ERR_INVALID, "persistent fused kernel configuration " + std::to_string(id) + " is not in this build");
+        }
+    }
+
+    int default_config(int p)
+    {
+      int id = (p == 1) ? 801 : (p == 3 ? 800 : 802);
+      if (const char *env = std::getenv("GDM_PERS_CFG"))
+        {
+          const int e  = atoi(env);
+          int       ep = -1;
+          try
+            {
+              with_config(e, [&](auto c) { ep = decltype(c)::P; });
+            }
+          catch (...)
+            {}
+          if (ep == p)
+            id = e;
+        }
+      return id;
+    }
+  } // namespace
+
+  // Work partition of the persistent kernel (host logic, also exported for the CPU tests).
+  //   tiles_x x tiles_y tile columns, input planes [k0, k1), at most `slots` shares, shares cut no closer than min_len
+  //   planes to a column end or to each other.  aligned: m = slots / tiles equal chunks per column cut at the same planes
+  //   (neighbouring tiles stream the same planes at the same time, their halos meet in L2), the planes above them are
+  //   swept tile-major over the spare shares.
+  // Output: job_ptr (size grid+1) and jobs as 6 ints {tile x, tile y, k0, k1, seam_lo, seam_hi}; seam ids are job indices.
+  void pers_partition_host(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, bool aligned, int forced_L,
+                           std::vector<int> &job_ptr, std::vector<int> &jobs6)
+  {
+    GDM_REQUIRE(tiles_x > 0 && tiles_y > 0 && k1 >= k0 && slots > 0 && min_len > 0, GDM_ERR_INVALID, "invalid partition request");
+    struct Piece
+    {
+      int tile, a, b;
+    };
+    typedef std::vector<std::vector<Piece>> Shares;
+    const int tiles = tiles_x * tiles_y;
+    const int nz    = k1 - k0;
+    job_ptr.assign(1, 0);
+    jobs6.clear();
+    if (nz == 0)
+      return;
+    // tile-major sweep of planes [za, zb) of every tile over at most n shares: ideal cuts every total/G planes, each moved
+    // to the nearest position that leaves no piece shorter than min_len
+    auto sweep = [&](Shares &shares, int za, int zb, int n) {
+      const int len = zb - za;
+      if (len <= 0 || n <= 0)
+        return;
+      const int64_t total = (int64_t)tiles * len;
+      int64_t       G     = std::min<int64_t>(n, std::max<int64_t>(1, total / (2 * (int64_t)min_len)));
+      if (len < 2 * min_len) // columns are not cut
+        G = std::min<int64_t>(G, tiles);
+      std::vector<int64_t> cuts;
+      for (int64_t j = 0; j <= G; ++j)
+        {
+          int64_t c = (total * j + G / 2) / G;
+          if (len < 2 * min_len)
+            c = ((c + len / 2) / len) * len;
+          else
+            {
+              const int64_t off = c % len, base = c - off;
+              if (off != 0 && off < min_len)
+                c = base + ((2 * off < min_len) ? 0 : min_len);
+              else if (off != 0 && len - off < min_len)
+                c = base + ((2 * (len - off) < min_len) ? len : len - min_len);
+            }
+          if (cuts.empty() || c > cuts.back())
+            cuts.push_back(c);
+        }
+      for (size_t j = 0; j + 1 < cuts.size(); ++j)
+        {
+          std::vector<Piece> sh;
+          int64_t            c = cuts[j];
+          while (c < cuts[j + 1])
+            {
+              const int     t   = (int)(c / len);
+              const int64_t end = std::min<int64_t>(cuts[j + 1], (int64_t)(t + 1) * len);
+              sh.push_back({t, za + (int)(c - (int64_t)t * len), za + (int)(end - (int64_t)t * len)});
+              c = end;
+            }
+          shares.push_back(sh);
+        }
+    };
+    // m aligned chunks of L planes per column, the planes above them swept over the spare shares
+    auto build = [&](int L) {
+      Shares shares;
+      if (L <= 0)
+        {
+          sweep(shares, k0, k1, slots);
+          return shares;
+        }
+      const int m  = std::min(slots / tiles, std::max(1, nz / (2 * min_len)));
+      int       zl = k0;
+      for (int c = 0; c < m; ++c)
+        {
+          const int a = k0 + c * L, b = std::min(k1, a + L);
+          if (a >= b)
+            break;
+          int bb = b;
+          if (k1 - b > 0 && k1 - b < min_len)
+            bb = k1;
+          for (int t = 0; t < tiles; ++t)
+            shares.push_back({{t, a, bb}});
+          zl = bb;
+          if (bb == k1)
+            break;
+        }
+      sweep(shares, zl, k1, std::max(1, slots - (int)shares.size()));
+      return shares;
+    };
+    auto longest = [&](const Shares &shares) {
+      int64_t mx = 0;
+      for (auto &sh : shares)
+        {
+          int64_t n = 0;
+          for (auto &p : sh)
+            n += p.b - p.a;
+          mx = std::max(mx, n);
+        }
+      return mx;
+    };
+    Shares shares;
+    // (no aligned part if the spare shares would each have to visit many tile columns)
+    if (aligned && slots >= tiles && nz >= 4 * min_len && (slots % tiles == 0 || tiles / (slots % tiles) <= 3))
+      {
+        const int m     = std::min(slots / tiles, std::max(1, nz / (2 * min_len)));
+        const int spare = (m == slots / tiles) ? slots - m * tiles : 0;
+        const int Lmax  = (nz + m - 1) / m;
+        if (forced_L > 0)
+          shares = build(std::min(std::max(forced_L, min_len), Lmax));
+        else if (spare == 0)
+          shares = build(Lmax);
+        else
+          {
+            // equal shares: m L + R = nz with L = tiles R / spare; search around it for the shortest longest share
+            const int Lbal = (int)((double)nz / ((double)m + (double)spare / tiles) + 0.5);
+            int64_t   best = -1;
+            for (int L = std::min(Lmax, Lbal + 6); L >= std::max(min_len, Lbal - 6); --L)
+              {
+                if ((int64_t)m * L < nz && nz - m * L < min_len)
+                  continue;
+                Shares        cand = build(L);
+                const int64_t mx   = longest(cand);
+                if ((int)cand.size() <= slots && (best < 0 || mx < best))
+                  {
+                    best   = mx;
+                    shares = std::move(cand);
+                  }
+              }
+            if (best < 0)
+              shares = build(0);
+          }
+      }
+    else
+      shares = build(0);
+    // jobs in share order; seams: the job that starts at plane b of tile t is the upper neighbour of the job ending at b
+    std::map<std::pair<int, int>, int> starts; // (tile, first plane) -> job index
+    int                                nj = 0;
+    for (auto &sh : shares)
+      for (auto &p : sh)
+        starts[{p.tile, p.a}] = nj++;
+    for (auto &sh : shares)
+      {
+        for (auto &p : sh)
+          {
+            const int self = starts[{p.tile, p.a}];
+            int       hi   = -1;
+            auto      it   = starts.find({p.tile, p.b});
+            if (p.b < k1 && it != starts.end())
+              hi = it->second;
+            jobs6.push_back(p.tile % tiles_x);
+            jobs6.push_back(p.tile / tiles_x);
+            jobs6.push_back(p.a);
+            jobs6.push_back(p.b);
+            jobs6.push_back(p.a > k0 ? self : -1);
+            jobs6.push_back(hi);
+          }
+        job_ptr.push_back((int)(jobs6.size() / 6));
+      }
+  }
+
+  namespace
+  {
+    template <class C>
+    PartitionP &get_partition(Context &ctx, PersPlan &plan, int oz0, int oz1)
+    {
+      const auto key = std::make_pair(oz0, oz1);
+      auto       it  = plan.parts.find(key);
+      if (it != plan.parts.end())
+        return it->second;
+      if (plan.parts.size() > 256)
+        {
+          GDM_CUDA_CHECK(cudaDeviceSynchronize());
+          for (auto &kv : plan.parts)
+            PersPlan::free_part(kv.second);
+          plan.parts.clear();
+        }
+      constexpr int P = C::P;
+      const int     k0 = std::max(oz0 - P, plan.in_lo), k1 = std::min(oz1 + P, plan.in_hi);
+      int           slots = ctx.sm_count * C::MINB;
+      if (const char *env = std::getenv("GDM_PERS_SLOTS"))
+        slots = std::max(1, atoi(env));
+      const int   min_len = 2 * P; // the shortest job that can hand its first 2P partial planes down
+      const char *env_al  = std::getenv("GDM_PERS_ALIGNED");
+      const bool  aligned = !(env_al && env_al[0] == '0');
+      const char *env_L   = std::getenv("GDM_PERS_L");
+      std::vector<int> ptr, j6;
+      pers_partition_host(plan.tiles_x, plan.tiles_y, k0, std::max(k0, k1), slots, min_len, aligned, env_L ? atoi(env_L) : 0, ptr, j6);
+      PartitionP part;
+      part.grid   = (int)ptr.size() - 1;
+      part.n_jobs = (int)(j6.size() / 6);
+      std::vector<JobP> jobs(part.n_jobs);
+      for (int j = 0; j < part.n_jobs; ++j)
+        {
+          jobs[j].x0      = plan.xorg + j6[6 * j + 0] * C::TX;
+          jobs[j].y0      = plan.cy0 + j6[6 * j + 1] * C::TY;
+          jobs[j].k0      = j6[6 * j + 2];
+          jobs[j].k1      = j6[6 * j + 3];
+          jobs[j].seam_lo = j6[6 * j + 4];
+          jobs[j].seam_hi = j6[6 * j + 5];
+          jobs[j].pad0 = jobs[j].pad1 = 0;
+          if (jobs[j].seam_lo >= 0)
+            {
+              part.n_seams++;
+              GDM_REQUIRE(jobs[j].k1 - jobs[j].k0 >= 2 * P, GDM_ERR_INTERNAL, "persistent partition: job shorter than a seam");
+            }
+        }
+      for (int w = 0; w < part.grid; ++w)
+        {
+          int64_t n = 0;
+          for (int j = ptr[w]; j < ptr[w + 1]; ++j)
+            n += jobs[j].k1 - jobs[j].k0;
+          part.max_planes = std::max(part.max_planes, n);
+        }
+      if (part.grid > 0)
+        {
+          GDM_CUDA_CHECK(cudaMalloc(&part.d_jobs, std::max<size_t>(1, jobs.size()) * sizeof(JobP)));
+          GDM_CUDA_CHECK(cudaMalloc(&part.d_ptr, ptr.size() * sizeof(int)));
+          GDM_CUDA_CHECK(cudaMemcpy(part.d_jobs, jobs.data(), jobs.size() * sizeof(JobP), cudaMemcpyHostToDevice));
+          GDM_CUDA_CHECK(cudaMemcpy(part.d_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+          GDM_CUDA_CHECK(cudaMalloc(&part.d_sync, (size_t)(2 + part.n_jobs) * sizeof(unsigned)));
+          GDM_CUDA_CHECK(cudaMemset(part.d_sync, 0, (size_t)(2 + part.n_jobs) * sizeof(unsigned)));
+          if (part.n_seams > 0) // slots are indexed by job: simple, 48 KB per job at p = 3
+            GDM_CUDA_CHECK(cudaMalloc(&part.d_scratch, (size_t)part.n_jobs * 2 * P * C::TY * C::TX * sizeof(double)));
+          if (std::getenv("GDM_PERS_TRACE"))
+            {
+              GDM_CUDA_CHECK(cudaMalloc(&part.d_trace, (size_t)2 * part.grid * sizeof(long long)));
+              part.h_jobs = jobs;
+              part.h_ptr  = ptr;
+            }
+          GDM_CUDA_CHECK(cudaDeviceSynchronize());
+        }
+      if (std::getenv("GDM_FUSED_VERBOSE"))
+        fprintf(stderr, "[gdm] persistent partition: outputs [%d, %d), inputs [%d, %d), %d x %d tiles -> %d shares, %d jobs, %d seams, longest share %lld planes\n",
+                oz0, oz1, k0, k1, plan.tiles_x, plan.tiles_y, part.grid, part.n_jobs, part.n_seams, (long long)part.max_planes);
+      return plan.parts.emplace(key, part).first->second;
+    }
+
+    template <class C>
+    const CUtensorMap &get_map(Operator &op, PersPlan &plan, const double *src)
+    {
+      auto it = plan.maps.find(src);
+      if (it != plan.maps.end())
+        return it->second;
+      if (plan.maps.size() > 64)
+        plan.maps.clear();
+      const Layout &L = op.sys->L;
+      CUtensorMap   m;
+      cuuint64_t    dims[3]    = {(cuuint64_t)L.ln[0], (cuuint64_t)L.ln[1], (cuuint64_t)L.ln[2]};
+      cuuint64_t    strides[2] = {(cuuint64_t)L.pitch * 8, (cuuint64_t)L.plane * 8};
+      cuuint32_t    box[3]     = {(cuuint32_t)C::PIN, (cuuint32_t)C::NR, 1};
+      cuuint32_t    estr[3]    = {1, 1, 1};
+      const CUresult rc = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(src), dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      GDM_REQUIRE(rc == CUDA_SUCCESS, GDM_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)rc));
+      return plan.maps.emplace(src, m).first->second;
+    }
+
+    template <class C, int MODE>
+    int launch_p(Operator &op, PersPlan &plan, double *dst, const double *src, bool accumulate, int oz0, int oz1, cudaStream_t stream,
+                 const double *dot_src, double *dot_partials)
+    {
+      constexpr int P = C::P, W = C::W;
+      Context      &ctx = *op.sys->ctx;
+      const Layout &L   = op.sys->L;
+      if (oz1 <= oz0)
+        return 0;
+      PartitionP &part = get_partition<C>(ctx, plan, oz0, oz1);
+      if (part.grid <= 0)
+        return 0;
+      ArgsP<P> a;
+      a.dst      = dst;
+      a.pitch    = L.pitch;
+      a.plane    = L.plane;
+      a.cx0      = plan.cx0;
+      a.cx1      = plan.cx1;
+      a.cy0      = plan.cy0;
+      a.cy1      = plan.cy1;
+      a.cz0      = oz0;
+      a.cz1      = oz1;
+      a.nx       = L.N[0];
+      a.ny       = L.N[1];
+      a.nz_local = L.ln[2];
+      a.kz_lo    = plan.kz_lo;
+      a.kz_hi    = plan.kz_hi;
+      a.grid     = part.grid;
+      a.tabAx    = op.dA[0];
+      a.tabAy    = op.dA[1];
+      a.tabBx    = (MODE == 1) ? plan.d_Be[0] : op.dB[0];
+      a.tabBy    = (MODE == 1) ? plan.d_Be[1] : op.dB[1];
+      a.sigma    = plan.sigma;
+      a.zt       = plan.d_zt;
+      a.jobs     = part.d_jobs;
+      a.job_ptr  = part.d_ptr;
+      a.ticket   = part.d_sync;
+      a.error    = reinterpret_cast<int *>(part.d_sync + 1);
+      a.flags    = part.d_sync + 2;
+      a.scratch  = part.d_scratch;
+      a.trace    = part.d_trace;
+      a.dot_src  = dot_src;
+      a.dot_partials = dot_partials;
+      const std::vector<double> *hB = (MODE == 1) ? plan.hBe : op.hB;
+      const int                  ir = P + 1; // any interior (Toeplitz) row
+      for (int d = 0; d <= P; ++d)
+        {
+          a.Ax[d] = op.hA[0][(size_t)ir * W + P + d];
+          a.Ay[d] = op.hA[1][(size_t)ir * W + P + d];
+          a.Bx[d] = op.has_B ? hB[0][(size_t)ir * W + P + d] : 0.0;
+          a.By[d] = op.has_B ? hB[1][(size_t)ir * W + P + d] : 0.0;
+        }
+      for (int j = 0; j < W; ++j)
+        a.Az[j] = a.Bz[j] = 0.0;
+      if (plan.kz_hi > plan.kz_lo)
+        {
+          // interior rows of direction 2 are Toeplitz: the scatter row of an interior input plane is any interior row reversed
+          int r = -1;
+          for (int q = 0; q < L.ln[2]; ++q)
+            if (q + L.loc0 > P && q + L.loc0 < L.N[2] - P)
+              {
+                r = q;
+                break;
+              }
+          GDM_REQUIRE(r >= 0, GDM_ERR_INTERNAL, "persistent fused kernel: no interior z row on this rank");
+          for (int j = 0; j < W; ++j)
+            {
+              a.Az[j] = op.desc.scale * op.hA[2][(size_t)r * W + (2 * P - j)];
+              a.Bz[j] = op.has_B ? op.desc.scale * hB[2][(size_t)r * W + (2 * P - j)] : 0.0;
+            }
+        }
+      void (*kern)(const CUtensorMap, const ArgsP<P>) = nullptr;
+      const bool dot = dot_partials != nullptr;
+      GDM_REQUIRE(!(dot && accumulate), GDM_ERR_INTERNAL, "fused dot product with accumulation");
+      if (dot)
+        kern = kron3d_pers_kernel<C, MODE, false, true>;
+      else if (accumulate)
+        kern = kron3d_pers_kernel<C, MODE, true, false>;
+      else
+        kern = kron3d_pers_kernel<C, MODE, false, false>;
+      const size_t smem = smem_bytes_p<C, MODE != 0>();
+      GDM_REQUIRE(smem <= 227 * 1024, GDM_ERR_INTERNAL, "persistent fused kernel exceeds the shared memory of an SM");
+      bool &attr = plan.attr_set[{ctx.device, (const void *)kern}];
+      if (!attr)
+        {
+          GDM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          attr = true;
+        }
+      part.epoch += 1;
+      a.epoch       = part.epoch;
+      a.ticket_base = part.ticket_base;
+      part.ticket_base += (unsigned)part.grid;
+      const CUtensorMap &map = get_map<C>(op, plan, src);
+      kern<<<part.grid, C::THREADS, smem, stream>>>(map, a);
+      ctx.launches++;
+      GDM_CUDA_CHECK(cudaGetLastError());
+      if (part.d_trace != nullptr) // diagnostic: per-share cycles and SM of this launch -> file named by GDM_PERS_TRACE
+        {
+          GDM_CUDA_CHECK(cudaStreamSynchronize(stream));
+          std::vector<long long> t((size_t)2 * part.grid);
+          GDM_CUDA_CHECK(cudaMemcpy(t.data(), part.d_trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+          if (FILE *f = fopen(std::getenv("GDM_PERS_TRACE"), "w"))
+            {
+              fprintf(f, "# share cycles smid planes jobs first_tile_x first_tile_y\n");
+              for (int w = 0; w < part.grid; ++w)
+                {
+                  int n = 0;
+                  for (int j = part.h_ptr[w]; j < part.h_ptr[w + 1]; ++j)
+                    n += part.h_jobs[j].k1 - part.h_jobs[j].k0;
+                  const JobP &J = part.h_jobs[part.h_ptr[w]];
+                  fprintf(f, "%d %lld %lld %d %d %d %d\n", w, t[2 * w], t[2 * w + 1], n, part.h_ptr[w + 1] - part.h_ptr[w],
+                          (J.x0 - plan.xorg) / C::TX, (J.y0 - plan.cy0) / C::TY);
+                }
+              fclose(f);
+            }
+        }
+      return part.grid;
+    }
+  } // namespace
+
+  bool pers_supported(const Operator &op)
+  {
+    const Layout &L = op.sys->L;
+    if (L.dim != 3 || L.nc != 1)
+      return false;
+    if (!(L.p == 1 || L.p == 3 || L.p == 5))
+      return false;
+    for (int d = 0; d < 3; ++d)
+      if (op.periodic[d] || L.N[d] < 2 * L.p + 2)
+        return false;
+    if (L.own1 <= L.own0)
+      return false;
+    return true;
+  }
+
+  // returns nullptr if the operator cannot use the tap split it relies on (the caller falls back to the round-1 kernels)
+  void *pers_plan_create(Operator &op)
+  {
+    const Layout &L = op.sys->L;
+    const int     P = L.p, W = 2 * P + 1;
+    std::unique_ptr<PersPlan> plan(new PersPlan);
+    plan->cfg = default_config(P);
+    plan->cx0 = op.dirichlet[0][0] ? 1 : 0;
+    plan->cx1 = L.nn[0] - (op.dirichlet[0][1] ? 1 : 0);
+    plan->cy0 = op.dirichlet[1][0] ? 1 : 0;
+    plan->cy1 = L.nn[1] - (op.dirichlet[1][1] ? 1 : 0);
+    int z0 = L.own0, z1 = L.own1; // global
+    if (op.dirichlet[2][0])
+      z0 = std::max(z0, 1);
+    if (op.dirichlet[2][1])
+      z1 = std::min(z1, L.nn[2] - 1);
+    plan->cz0 = z0 - L.loc0;
+    plan->cz1 = std::max(z1 - L.loc0, plan->cz0);
+    // stored planes that can contribute: Dirichlet planes have zero columns
+    plan->in_lo = (op.dirichlet[2][0] && L.loc0 == 0) ? 1 : 0;
+    plan->in_hi = L.ln[2] - ((op.dirichlet[2][1] && L.loc1 == L.nn[2]) ? 1 : 0);
+    int tx = 32, ty = 32;
+    with_config(plan->cfg, [&](auto c) {
+      tx = decltype(c)::TX;
+      ty = decltype(c)::TY;
+    });
+    // TMA box starts must be 16-byte aligned: keep (x0 - P) even by starting one column early if needed
+    plan->xorg    = plan->cx0 - ((plan->cx0 - P) & 1);
+    plan->tiles_x = (plan->cx1 - plan->xorg + tx - 1) / tx;
+    plan->tiles_y = (plan->cy1 - plan->cy0 + ty - 1) / ty;
+    plan->mode    = !op.has_B ? 0 : (op.b_symmetry > 0 ? 1 : 2);
+    // Toeplitz z planes [kz_lo, kz_hi): input planes whose 2P+1 target rows are all interior rows of A_z, B_z
+    plan->kz_lo = plan->kz_hi = 0;
+    if (L.N[2] >= 4 * P + 2)
+      {
+        plan->kz_lo = std::max(0, 2 * P + 1 - L.loc0);
+        plan->kz_hi = std::max(plan->kz_lo, std::min(L.ln[2], L.N[2] - 2 * P - L.loc0));
+      }
+    const int zrows = 2 * W;
+    if (plan->kz_lo + (L.ln[2] - plan->kz_hi) > zrows)
+      return nullptr;
+    for (int d = 0; d < 3; ++d)
+      plan->hBe[d] = op.hB[d];
+    plan->sigma = 0.0;
+    if (plan->mode == 1)
+      {
+        // K_d = alpha_d M_d + R_d with alpha_d = (outer tap of K_d) / (outer tap of M_d): R_d has zero outer taps on
+        // Toeplitz rows; the identity holds row by row, so the one-sided and masked rows need no special treatment
+        double alpha[3] = {0, 0, 0};
+        for (int d = 0; d < 3; ++d)
+          {
+            int row = P + 1;
+            if (d == 2)
+              {
+                row = -1;
+                for (int r = 0; r < L.ln[2]; ++r)
+                  if (r + L.loc0 > P && r + L.loc0 < L.N[2] - P)
+                    {
+                      row = r;
+                      break;
+                    }
+              }
+            if (row < 0)
+              return nullptr;
+            const double m = op.hA[d][(size_t)row * W + 2 * P], k = op.hB[d][(size_t)row * W + 2 * P];
+            if (m == 0.0 || op.hA[d][(size_t)row * W] != m || op.hB[d][(size_t)row * W] != k)
+              return nullptr;
+            alpha[d] = k / m;
+          }
+        for (int d = 0; d < 3; ++d)
+          {
+            const int rows = (int)(op.hB[d].size() / W);
+            for (int r = 0; r < rows; ++r)
+              {
+                for (int t = 0; t < W; ++t)
+                  plan->hBe[d][(size_t)r * W + t] = op.hB[d][(size_t)r * W + t] - alpha[d] * op.hA[d][(size_t)r * W + t];
+                const int gr = r + (d == 2 ? L.loc0 : 0); // global row
+                if (gr > P && gr < L.N[d] - P)
+                  plan->hBe[d][(size_t)r * W] = plan->hBe[d][(size_t)r * W + 2 * P] = 0.0;
+              }
+          }
+        plan->sigma = alpha[0] + alpha[1] + alpha[2];
+        for (int d = 0; d < 2; ++d)
+          {
+            GDM_CUDA_CHECK(cudaMalloc(&plan->d_Be[d], plan->hBe[d].size() * sizeof(double)));
+            GDM_CUDA_CHECK(cudaMemcpy(plan->d_Be[d], plan->hBe[d].data(), plan->hBe[d].size() * sizeof(double), cudaMemcpyHostToDevice));
+          }
+      }
+    const int           wz = W + 1;
+    std::vector<double> zt((size_t)zrows * 2 * wz, 0.0);
+    for (int c = 0; c < zrows; ++c)
+      {
+        const int k = (c < plan->kz_lo) ? c : plan->kz_hi + (c - plan->kz_lo);
+        if (k < 0 || k >= L.ln[2])
+          continue;
+        for (int j = 0; j < W; ++j)
+          {
+            const int r = k - P + j;
+            if (r < 0 || r >= L.ln[2])
+              continue;
+            zt[(size_t)(c * 2 + 0) * wz + j] = op.desc.scale * op.hA[2][(size_t)r * W + (2 * P - j)];
+            if (op.has_B)
+              zt[(size_t)(c * 2 + 1) * wz + j] = op.desc.scale * plan->hBe[2][(size_t)r * W + (2 * P - j)];
+          }
+      }
+    GDM_CUDA_CHECK(cudaMalloc(&plan->d_zt, zt.size() * sizeof(double)));
+    GDM_CUDA_CHECK(cudaMemcpy(plan->d_zt, zt.data(), zt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return plan.release();
+  }
+
+  void pers_plan_destroy(void *p)
+  {
+    delete static_cast<PersPlan *>(p);
+  }
+
+  void pers_window(const void *p, int &cz0, int &cz1)
+  {
+    const PersPlan &plan = *static_cast<const PersPlan *>(p);
+    cz0                  = plan.cz0;
+    cz1                  = plan.cz1;
+  }
+
+  int pers_max_grid(const Operator &op, const void *p)
+  {
+    const PersPlan &plan = *static_cast<const PersPlan *>(p);
+    int             mb   = 2;
+    with_config(plan.cfg, [&](auto c) { mb = decltype(c)::MINB; });
+    int slots = op.sys->ctx->sm_count * mb;
+    if (const char *env = std::getenv("GDM_PERS_SLOTS"))
+      slots = std::max(slots, atoi(env));
+    return slots;
+  }
+
+  // output planes [oz0, oz1) (local indices, clipped to the plan's window); returns the number of CTAs launched
+  int pers_launch(Operator &op, void *p, double *dst, const double *src, bool accumulate, int oz0, int oz1, cudaStream_t stream,
+                  const double *dot_src, double *dot_partials)
+  {
+    PersPlan &plan = *static_cast<PersPlan *>(p);
+    oz0            = std::max(oz0, plan.cz0);
+    oz1            = std::min(oz1, plan.cz1);
+    int grid       = 0;
+    with_config(plan.cfg, [&](auto c) {
+      using C = decltype(c);
+      if (plan.mode == 0)
+        grid = launch_p<C, 0>(op, plan, dst, src, accumulate, oz0, oz1, stream, dot_src, dot_partials);
+      else if (plan.mode == 1)
+        grid = launch_p<C, 1>(op, plan, dst, src, accumulate, oz0, oz1, stream, dot_src, dot_partials);
+      else
+        grid = launch_p<C, 2>(op, plan, dst, src, accumulate, oz0, oz1, stream, dot_src, dot_partials);
+    });
+    return grid;
+  }
+
+  // 0 if no seam wait of any launch of this plan timed out (diagnostic; synchronises the device)
+  int pers_error_flag(void *p)
+  {
+    PersPlan &plan = *static_cast<PersPlan *>(p);
+    int       any  = 0;
+    GDM_CUDA_CHECK(cudaDeviceSynchronize());
+    for (auto &kv : plan.parts)
+      if (kv.second.d_sync)
+        {
+          unsigned e = 0;
+          GDM_CUDA_CHECK(cudaMemcpy(&e, kv.second.d_sync + 1, sizeof(unsigned), cudaMemcpyDeviceToHost));
+          any |= (int)e;
+        }
+    return any;
+  }
+} // namespace gdm

@@ -135,6 +135,16 @@ int      gdm_fused_partition(int aligned, int tiles_x, int tiles_y, int z0, int 
                              int32_t *seg_ptr, int32_t cap_ptr, int32_t *segs4, int32_t cap_segs, int32_t *n_ctas,
                              int32_t *n_segs);
 
+/* Work partition of the persistent fused kernel (kron3d_pers.cu; host logic, no device needed): the input planes
+ * [k0, k1) of a tiles_x x tiles_y tile grid are split into at most `slots` shares (one CTA each); share w runs jobs
+ * [job_ptr[w], job_ptr[w+1]) of jobs6 = {tile x, tile y, k_begin, k_end, seam_lo, seam_hi} per job.  A job with
+ * seam_lo >= 0 hands its first 2p partial output planes to the job below it through scratch slot seam_lo; seam_hi is
+ * the slot a job reads when it flushes.  No job is shorter than min_len planes unless it is a whole column.
+ * Replaces the per-rank slab loop of the reference's cell iteration (system.h:703-761) inside one GPU. */
+int      gdm_pers_partition(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, int aligned,
+                            int32_t *job_ptr, int32_t cap_ptr, int32_t *jobs6, int32_t cap_jobs, int32_t *n_shares,
+                            int32_t *n_jobs);
+
 /* ----------------------------------------------------------- constraints */
 int gdm_constraints_create(gdm_system_t sys, gdm_constraints_t *c);
 int gdm_constraints_destroy(gdm_constraints_t c);

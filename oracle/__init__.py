@@ -25,6 +25,7 @@ from .assemble import (assemble_cell_loop, kron_operator, kron_unconstrained, ma
 from .solvers import (ReductionControl, SolverControlNoConvergence, solver_cg,
                       PreconditionIdentity, PreconditionJacobi, DiagonalMatrix,
                       ExplicitRungeKutta4, DiscreteTime)
+from .kron_apply import KronApply, kron_apply, constraint_matrices_1d
 from .vector_tools import interpolate, integrate_difference, compute_global_error
 
 __all__ = [n for n in dir() if not n.startswith("_")]
