@@ -255,6 +255,47 @@ def run_ours(args):
         ms_cg = e0.elapsed_time(e1)
         cg = {"iterations": ctl.last_step(), "ms_per_iteration": ms_cg / max(ctl.last_step(), 1),
               "gdof_iterations_per_s": total_dofs * ctl.last_step() / (ms_cg * 1e-3) / 1e9}
+        # ---- the converged solve of SURVEY 8d: -Laplace u = 1, u = 0 on the boundary, x0 = 0,
+        # ReductionControl(10000, 1e-10, 1e-8), identity and Jacobi (reference: tests/poisson_02_gdm.cc:213-215).
+        # b_i = int phi_i = (M 1)_i (partition of unity), zero on constrained rows.  On the BASELINE grid (1 GPU) the
+        # iteration counts are checked against the oracle's converged solves (tests/golden/cg_poisson3d.json).
+        free = g.AffineConstraints()
+        free.close()
+        M = g.SparseMatrix()
+        g.MatrixCreator.create_mass_matrix(g.MappingQ1(), sys_, g.QGauss(p + 1), M, free)
+        ones = g.Vector(sys_)
+        ones.set(1.0)
+        M.vmult(b, ones)
+        con.set_zero(b)
+        gold = {}
+        gpath = os.path.join(ROOT, "tests", "golden", "cg_poisson3d.json")
+        if world == 1 and os.path.exists(gpath):
+            gold = {r["precondition"]: r for r in json.load(open(gpath)) if r["N"] == n and r["p"] == p}
+        cg["solve"] = {}
+        for pre in ("identity", "jacobi"):
+            if pre == "identity":
+                P = g.PreconditionIdentity()
+            else:
+                P = g.PreconditionJacobi()
+                P.initialize(A)
+            sctl = g.ReductionControl(10000, 1e-10, 1e-8)
+            u.set(0.0)
+            barrier()
+            e0.record()
+            g.SolverCG(sctl).solve(A, u, b, P)
+            e1.record()
+            barrier()
+            sec = e0.elapsed_time(e1) * 1e-3
+            t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            if world > 1:
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            rec = {"iterations": sctl.last_step(), "seconds": float(t.item()), "initial_residual": sctl.initial_value(),
+                   "final_residual": sctl.last_value(), "control": "ReductionControl(10000, 1e-10, 1e-8)"}
+            if pre in gold:
+                rec["oracle_iterations"] = gold[pre]["iterations"]
+                rec["oracle_seconds_cpu"] = gold[pre]["oracle_seconds"]
+                assert abs(rec["iterations"] - gold[pre]["iterations"]) <= 1, (pre, rec["iterations"], gold[pre]["iterations"])
+            cg["solve"][pre] = rec
 
     if rank != 0:
         return

@@ -425,7 +425,9 @@ class SparseMatrix:
         capi.check(self.lib.gdm_operator_vmult_dot(self.h, dst.h, src.h, C.byref(out)))
         return out.value
 
-    Tvmult = vmult  # mass/stiffness are symmetric; advection operators expose the transpose as a separate kind
+    def Tvmult(self, dst, src):
+        """dst = A^T src (`SparseMatrix::Tvmult`): vmult for mass/stiffness, the transposed operator for advection."""
+        capi.check(self.lib.gdm_operator_tvmult(self.h, dst.h, src.h))
 
     def vmult_host(self, dst, src):
         """vmult on HOST numpy buffers (H2D, apply, D2H)."""

@@ -94,7 +94,7 @@ SIGNATURES = {
     "gdm_system_halo_plan": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "gdm_fused_partition": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
-    "gdm_pers_partition": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+    "gdm_pers_partition": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gdm_constraints_create": (C.c_int, [_H, _PH]),
     "gdm_constraints_destroy": (C.c_int, [_H]),
@@ -125,6 +125,7 @@ SIGNATURES = {
     "gdm_operator_attach_csr": (C.c_int, [_H, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gdm_operator_vmult": (C.c_int, [_H, _H, _H]),
     "gdm_operator_vmult_add": (C.c_int, [_H, _H, _H]),
+    "gdm_operator_tvmult": (C.c_int, [_H, _H, _H]),
     "gdm_operator_vmult_dot": (C.c_int, [_H, _H, _H, C.POINTER(C.c_double)]),
     "gdm_operator_vmult_host": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "gdm_operator_diagonal": (C.c_int, [_H, _H]),

@@ -286,11 +286,17 @@ namespace gdm
         };
         GDM_REQUIRE(!(op.periodic[d] && N <= 2 * p), GDM_ERR_NOT_IMPLEMENTED,
                     "periodic direction needs more than 2*fe_degree cells");
-        constrain(M);
-        constrain(B);
         // slice the local rows of the partitioned direction
         const int r0 = (d == L.pdim) ? L.loc0 : 0;
         const int nr = L.ln[d];
+        if (op.periodic[d])
+          {
+            op.hAu[d].assign(M.begin() + (size_t)r0 * W, M.begin() + (size_t)(r0 + nr) * W);
+            if (!B.empty())
+              op.hBu[d].assign(B.begin() + (size_t)r0 * W, B.begin() + (size_t)(r0 + nr) * W);
+          }
+        constrain(M);
+        constrain(B);
         op.hA[d].assign(M.begin() + (size_t)r0 * W, M.begin() + (size_t)(r0 + nr) * W);
         op.hdiagA[d].assign(diagA.begin() + r0, diagA.begin() + r0 + nr);
         if (!B.empty())
@@ -319,7 +325,9 @@ namespace gdm
     const bool overlap = (op.kernel_used == GDM_KERNEL_FUSED); // the fused path imports the ghosts itself, overlapped
     if (!overlap)
       vector_update_ghosts(src);
-    const bool via_tmp = accumulate && op.csr;
+    // y += A x through a temporary: CSR overlay rows replace rows, and the fused periodic path folds rows of its output
+    const bool fused_periodic = op.kernel_used == GDM_KERNEL_FUSED && (op.periodic[0] || op.periodic[1] || op.periodic[2]);
+    const bool via_tmp = accumulate && (op.csr || fused_periodic);
     double    *out     = dst.d;
     if (via_tmp)
       {
@@ -689,14 +697,14 @@ int gdm_fused_partition(int aligned, int tiles_x, int tiles_y, int z0, int z1, i
   GDM_CATCH
 }
 
-int gdm_pers_partition(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, int aligned, int32_t *job_ptr,
+int gdm_pers_partition(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, int aligned, const int32_t *weights, int32_t *job_ptr,
                        int32_t cap_ptr, int32_t *jobs6, int32_t cap_jobs, int32_t *n_shares, int32_t *n_jobs)
 {
   GDM_TRY
   GDM_ARG(n_shares);
   GDM_ARG(n_jobs);
   std::vector<int> ptr, jobs;
-  pers_partition_host(tiles_x, tiles_y, k0, k1, slots, min_len, aligned != 0, 0, ptr, jobs);
+  pers_partition_host(tiles_x, tiles_y, k0, k1, slots, min_len, aligned != 0, weights, ptr, jobs);
   *n_shares = (int32_t)ptr.size() - 1;
   *n_jobs   = (int32_t)(jobs.size() / 6);
   GDM_REQUIRE(job_ptr != nullptr && jobs6 != nullptr && cap_ptr >= (int32_t)ptr.size() && cap_jobs >= *n_jobs, GDM_ERR_INVALID,
@@ -1033,8 +1041,6 @@ int gdm_operator_create(gdm_system_t sys, gdm_constraints_t c, const gdm_operato
       op.periodic[d]     = c ? c->impl.periodic[d] : false;
       op.dirichlet[d][0] = c ? c->impl.dirichlet[d][0] : false;
       op.dirichlet[d][1] = c ? c->impl.dirichlet[d][1] : false;
-      GDM_REQUIRE(!(op.periodic[d] && d == sys->impl.L.pdim && sys->impl.L.n_ranks > 1), GDM_ERR_NOT_IMPLEMENTED,
-                  "periodicity along the partitioned direction with more than one rank");
     }
   op.has_B      = desc->kind != GDM_OP_MASS;
   op.b_symmetry = (desc->kind == GDM_OP_STIFFNESS) ? +1 : -1;
@@ -1051,14 +1057,61 @@ int gdm_operator_create(gdm_system_t sys, gdm_constraints_t c, const gdm_operato
     }
   GDM_REQUIRE(!(desc->kernel == GDM_KERNEL_FUSED && op.kernel_used != GDM_KERNEL_FUSED), GDM_ERR_NOT_IMPLEMENTED,
               "the fused kernel does not cover this configuration");
+  GDM_REQUIRE(!(op.periodic[sys->impl.L.pdim] && sys->impl.L.n_ranks > 1 && op.kernel_used != GDM_KERNEL_FUSED),
+              GDM_ERR_NOT_IMPLEMENTED,
+              "periodicity along the partitioned direction with more than one rank needs the fused kernel (dim 3, scalar)");
   *out = o.release();
   GDM_CATCH
 }
 
 int gdm_operator_destroy(gdm_operator_t op)
 {
+  if (op && op->impl.transposed)
+    {
+      delete static_cast<gdm_operator_s *>(op->impl.transposed);
+      op->impl.transposed = nullptr;
+    }
   delete op;
   return GDM_OK;
+}
+
+// SparseMatrix::Tvmult: mass and stiffness are symmetric (Tvmult == vmult); the advection operators are not: the
+// transposed operator (kind ADVECTION <-> ADVECTION_T, same velocity, scale and constraints) is created on first use.
+int gdm_operator_tvmult(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src)
+{
+  GDM_TRY
+  GDM_ARG(op);
+  GDM_ARG(dst);
+  GDM_ARG(src);
+  Operator &o = op->impl;
+  if (o.desc.kind == GDM_OP_MASS || o.desc.kind == GDM_OP_STIFFNESS)
+    {
+      operator_apply(o, dst->impl, src->impl, false);
+      return GDM_OK;
+    }
+  GDM_REQUIRE(!o.csr, GDM_ERR_NOT_IMPLEMENTED, "Tvmult of an operator with CSR overlay rows");
+  if (!o.transposed)
+    {
+      gdm_constraints_s cs;
+      cs.impl.sys    = o.sys;
+      cs.impl.closed = true;
+      for (int d = 0; d < 3; ++d)
+        {
+          cs.impl.periodic[d]     = o.periodic[d];
+          cs.impl.dirichlet[d][0] = o.dirichlet[d][0];
+          cs.impl.dirichlet[d][1] = o.dirichlet[d][1];
+        }
+      gdm_operator_desc desc = o.desc;
+      desc.kind              = (o.desc.kind == GDM_OP_ADVECTION) ? GDM_OP_ADVECTION_T : GDM_OP_ADVECTION;
+      gdm_system_s *sys_h    = reinterpret_cast<gdm_system_s *>(o.sys); // gdm_system_s has the System as its only member
+      gdm_operator_t t       = nullptr;
+      const int      rc      = gdm_operator_create(sys_h, &cs, &desc, &t);
+      if (rc != GDM_OK)
+        return rc;
+      o.transposed = t;
+    }
+  operator_apply(static_cast<gdm_operator_s *>(o.transposed)->impl, dst->impl, src->impl, false);
+  GDM_CATCH
 }
 
 int gdm_operator_attach_csr(gdm_operator_t op, uint64_t n_rows, const uint64_t *row_ids, const uint64_t *rowptr,
@@ -1163,7 +1216,8 @@ int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *s
   vd.d    = o.host_dst;
   vs.owns = vd.owns = false;
   const Layout &L = sys.L;
-  if (o.kernel_used == GDM_KERNEL_FUSED && L.n_ranks == 1 && !o.csr && L.ln[2] >= 16 * L.p)
+  if (o.kernel_used == GDM_KERNEL_FUSED && L.n_ranks == 1 && !o.csr && L.ln[2] >= 16 * L.p &&
+      !(o.periodic[0] || o.periodic[1] || o.periodic[2]))
     {
       // Pipelined over z chunks: H2D of chunk c+1, apply of the planes whose inputs have arrived and D2H
       // of finished planes overlap on three streams (PCIe is full duplex; the apply hides behind it).

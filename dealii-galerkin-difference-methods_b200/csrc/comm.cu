@@ -187,6 +187,31 @@ namespace gdm
     return h;
   }
 
+  // rank that owns node plane `plane` (global index) of the partitioned direction
+  int comm_plane_owner(const Layout &L, int plane)
+  {
+    for (int r = 0; r < L.n_ranks; ++r)
+      {
+        int o0, o1;
+        owned_range(L, r, o0, o1);
+        if (plane >= o0 && plane < o1)
+          return r;
+      }
+    return -1;
+  }
+
+  // point-to-point transfers of `count` doubles (periodic wrap of the partitioned direction)
+  void comm_send(Context &ctx, const double *buf, int64_t count, int peer, cudaStream_t stream)
+  {
+    GDM_REQUIRE(ctx.comm && ctx.comm->comm, GDM_ERR_COMM, "communicator not initialised");
+    check(nccl().Send(buf, (size_t)count, ncclFloat64, peer, ctx.comm->comm, stream), "ncclSend");
+  }
+  void comm_recv(Context &ctx, double *buf, int64_t count, int peer, cudaStream_t stream)
+  {
+    GDM_REQUIRE(ctx.comm && ctx.comm->comm, GDM_ERR_COMM, "communicator not initialised");
+    check(nccl().Recv(buf, (size_t)count, ncclFloat64, peer, ctx.comm->comm, stream), "ncclRecv");
+  }
+
   // Import L.ghost planes from each neighbouring slab into the ghost zones of v.
   void comm_halo_exchange(Context &ctx, const Layout &L, double *v, cudaStream_t stream)
   {

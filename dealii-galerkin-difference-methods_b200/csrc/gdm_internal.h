@@ -174,6 +174,9 @@ namespace gdm
     // host band tables (local rows in pdim): [d] -> ln[d]*(2p+1)
     std::vector<double> hA[3], hB[3];
     std::vector<double> hdiagA[3], hdiagB[3]; // unconstrained 1D diagonals (constrained-row value)
+    // periodic directions: the unfolded tables (plain one-sided rows on N+1 nodes); the fused kernel applies
+    // C^T A C as "duplicate node 0 into node N, apply A, add row N to row 0" 
+    std::vector<double> hAu[3], hBu[3];
     double *dA[3] = {nullptr, nullptr, nullptr};
     double *dB[3] = {nullptr, nullptr, nullptr};
     double *ddiagA[3] = {nullptr, nullptr, nullptr};
@@ -181,6 +184,7 @@ namespace gdm
     int     kernel_used = GDM_KERNEL_GENERIC;
     std::unique_ptr<CsrOverlay> csr;
     void   *fused = nullptr;          // FusedPlan* (kron3d.cu)
+    void   *transposed = nullptr;     // gdm_operator_s* of the transposed advection operator (Tvmult), created on first use
     double *tmp = nullptr;            // vmult_add with CSR overlay
     double *host_src = nullptr, *host_dst = nullptr; // staging of vmult_host (padded layout)
     double *stage_src = nullptr, *stage_dst = nullptr; // contiguous staging (host order) for 1D PCIe copies
@@ -245,7 +249,12 @@ namespace gdm
   int   pers_launch(Operator &op, void *plan, double *dst, const double *src, bool accumulate, int oz0, int oz1, cudaStream_t stream,
                     const double *dot_src, double *dot_partials);
   int   pers_error_flag(void *plan);
-  void  pers_partition_host(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, bool aligned, int forced_L,
+  // periodic directions of the persistent path (C^T A C = fold . A . duplicate): pre patches src in place (node N := node 0,
+  // old values saved), post folds dst (row 0 += row N) and restores src.  No-ops without periodic directions.
+  bool  pers_has_periodic(const void *plan);
+  void  pers_periodic_pre(Operator &op, void *plan, double *src, cudaStream_t stream);
+  void  pers_periodic_post(Operator &op, void *plan, double *dst, double *src, cudaStream_t stream);
+  void  pers_partition_host(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, bool aligned, const int *weights,
                             std::vector<int> &job_ptr, std::vector<int> &jobs6);
 
   // blas1.cu
@@ -304,6 +313,9 @@ namespace gdm
   };
   HaloPlan halo_plan(const Layout &L);
   void comm_halo_exchange(Context &ctx, const Layout &L, double *v, cudaStream_t stream = nullptr); // nullptr: ctx.stream
+  int  comm_plane_owner(const Layout &L, int plane);
+  void comm_send(Context &ctx, const double *buf, int64_t count, int peer, cudaStream_t stream);
+  void comm_recv(Context &ctx, double *buf, int64_t count, int peer, cudaStream_t stream);
   void comm_destroy(Context &ctx);
 
   // vector helpers

@@ -659,8 +659,19 @@ namespace gdm
       {
         if (!periodic[d])
           continue;
-        GDM_REQUIRE(!(d == L.pdim && L.n_ranks > 1), GDM_ERR_NOT_IMPLEMENTED,
-                    "periodicity along the partitioned direction with more than one rank");
+        if (d == L.pdim && L.n_ranks > 1)
+          {
+            // the duplicate plane lives on another rank: one plane from the owner of plane 0 to the owner of plane N
+            const int first = comm_plane_owner(L, 0), last = comm_plane_owner(L, L.N[d]);
+            if (first != last)
+              {
+                if (L.rank == first)
+                  comm_send(ctx, v + (int64_t)(0 - L.loc0) * L.stride[d], L.stride[d], last, ctx.stream);
+                if (L.rank == last)
+                  comm_recv(ctx, v + (int64_t)(L.N[d] - L.loc0) * L.stride[d], L.stride[d], first, ctx.stream);
+                continue;
+              }
+          }
         SetFaceK a;
         a.v        = v;
         a.dim      = L.dim;

@@ -1509,14 +1509,23 @@ namespace gdm
       return false;
     if (!(L.p == 1 || L.p == 3 || L.p == 5))
       return false;
-    for (int d = 0; d < 3; ++d)
-      if (op.periodic[d] || L.N[d] < 2 * L.p + 2)
-        return false;
-    if (L.own1 <= L.own0)
-      return false;
     const char *env = std::getenv("GDM_DISABLE_FUSED");
     if (env && env[0] == '1')
       return false;
+    bool any_periodic = false;
+    for (int d = 0; d < 3; ++d)
+      {
+        if (L.N[d] < 2 * L.p + 2)
+          return false;
+        any_periodic |= op.periodic[d];
+      }
+    if (L.own1 <= L.own0)
+      return false;
+    if (any_periodic) // only the persistent kernel handles periodic directions (fold . A . duplicate)
+      {
+        const char *fam = std::getenv("GDM_FUSED_FAMILY");
+        return (!fam || fam[0] == '8') && !std::getenv("GDM_FUSED_CFG") && pers_supported(op);
+      }
     return true;
   }
 
@@ -1544,6 +1553,8 @@ namespace gdm
       const char *fam = std::getenv("GDM_FUSED_FAMILY");
       if ((!fam || fam[0] == '8') && !std::getenv("GDM_FUSED_CFG") && pers_supported(op))
         plan->pers = pers_plan_create(op);
+      GDM_REQUIRE(plan->pers || !(op.periodic[0] || op.periodic[1] || op.periodic[2]), GDM_ERR_NOT_IMPLEMENTED,
+                  "fused kernel: periodic directions need the persistent kernel");
     }
     int tx = 32, ty = 32, min_blocks = 2;
     plan->cfg = default_config(P);
@@ -1808,6 +1819,13 @@ namespace gdm
       }
     const int P = L.p;
     const bool want_dot = dot_slot >= 0;
+    // periodic directions (persistent kernel): C^T A C x = fold(A(dup x)); src is patched in place and restored
+    const bool periodic = plan.pers && pers_has_periodic(plan.pers);
+    if (periodic)
+      {
+        GDM_REQUIRE(!accumulate, GDM_ERR_INTERNAL, "fused periodic apply cannot accumulate (use a temporary)");
+        pers_periodic_pre(op, plan.pers, const_cast<double *>(src), ctx.stream);
+      }
     double    *face_partials = nullptr; // where the face kernel puts its partial sums (set below)
     if (want_dot)
       {
@@ -1880,6 +1898,10 @@ namespace gdm
             with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
           }
       }
+    else if (periodic)
+      {
+        with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
+      }
     else
       {
         // Dirichlet faces (skipped by the tiles) and deal.II's constrained diagonal: disjoint outputs, so the small
@@ -1895,6 +1917,8 @@ namespace gdm
         finish_dot();
         return;
       }
+    if (periodic)
+      pers_periodic_post(op, plan.pers, dst, const_cast<double *>(src), ctx.stream);
     // Dirichlet faces (skipped by the tiles) and deal.II's constrained diagonal
     face_blocks = launch_constrained_rows(ctx, L, op, dst, src, accumulate, -1, -1, face_partials);
     finish_dot();

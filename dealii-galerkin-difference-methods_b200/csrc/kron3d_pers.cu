@@ -81,10 +81,15 @@ namespace gdm
     }
 
     // ------------------------------------------------------------------ configuration
-    template <int P_, int RY_, int NW_, int RX_, int STAGES_, int MINB_>
+    // SPLIT_ = 1: no CTA barrier in the plane loop; the x pass -> y/z pass hand-over runs through full/empty mbarriers
+    // over three a/r buffers, so a warp only ever waits for what the others did one plane earlier (the warps that own an
+    // extra x task or the TMA issue no longer hold everybody back at every plane)
+    template <int P_, int RY_, int NW_, int RX_, int STAGES_, int MINB_, int SPLIT_ = 0>
     struct CfgP
     {
       static constexpr int  P = P_, TX = 32, RY = RY_, NW = NW_, RX = RX_, STAGES = STAGES_, MINB = MINB_;
+      static constexpr bool SPLIT = SPLIT_ != 0;
+      static constexpr int  NAB   = SPLIT ? 3 : 2; // a/r buffers
       static constexpr int  W       = 2 * P + 1;
       static constexpr int  TY      = RY * NW;
       static constexpr int  NR      = TY + 2 * P;                   // rows of the staged tile
@@ -101,7 +106,6 @@ namespace gdm
       static constexpr int  NLT      = REM * NXB; // left-over thread tasks
       static constexpr int  NLW      = (NLT + 31) / 32;
       static constexpr int  NWT      = NWT_FULL + NLW;
-      static constexpr int  ROUNDS   = (NWT + NW - 1) / NW;
       static constexpr int  NBT        = 2 * (P + 1);
       static constexpr int  WP         = 8 * ((W + 7) / 8);
       static constexpr int  TB_DOUBLES = 2 * 2 * NBT * WP;
@@ -152,8 +156,8 @@ namespace gdm
     template <class C, bool HASB>
     constexpr size_t smem_bytes_p()
     {
-      return (size_t)(C::STAGES * C::STAGE_DOUBLES + 2 * (HASB ? 2 : 1) * C::TX * C::PY + C::ZT_DOUBLES + C::TB_DOUBLES) * sizeof(double) +
-             (size_t)C::STAGES * sizeof(uint64_t) + 64 + 128;
+      return (size_t)(C::STAGES * C::STAGE_DOUBLES + C::NAB * (HASB ? 2 : 1) * C::TX * C::PY + C::ZT_DOUBLES + C::TB_DOUBLES) * sizeof(double) +
+             (size_t)(C::STAGES + 2 * C::NAB) * sizeof(uint64_t) + 64 + 128;
     }
 
     // MODE 0: mass; MODE 1: B symmetric with the tap split (B tables hold R = B - alpha A); MODE 2: B antisymmetric.
@@ -169,10 +173,12 @@ namespace gdm
       static constexpr int  S  = C::STAGES;
       static constexpr int  AB_BUF   = NF * TX * PY; // [field][x][PY] (y contiguous)
       static constexpr int  OFF_AB   = S * C::STAGE_DOUBLES;
-      static constexpr int  OFF_ZT   = OFF_AB + 2 * AB_BUF;
+      static constexpr int  NAB      = C::NAB;
+      static constexpr bool SPLIT    = C::SPLIT;
+      static constexpr int  OFF_ZT   = OFF_AB + NAB * AB_BUF;
       static constexpr int  OFF_TB   = OFF_ZT + C::ZT_DOUBLES;
       static constexpr int  OFF_BAR  = OFF_TB + C::TB_DOUBLES;
-      static constexpr int  OFF_MISC = OFF_BAR + S;
+      static constexpr int  OFF_MISC = OFF_BAR + S + 2 * NAB; // barriers: [S] TMA stages, [NAB] a/r full, [NAB] a/r empty
       static constexpr int  WP = C::WP, NBT = C::NBT, WZ = C::WZ;
       static constexpr unsigned STAGE_BYTES = NR * PIN * sizeof(double);
       static constexpr int  FULL_ROUNDS = C::NWT / C::NW, EXTRA = C::NWT % C::NW;
@@ -184,6 +190,10 @@ namespace gdm
       double            *smem;
       uint32_t           sb, bar0;
       int                tid, lane, warp, yz_off;
+      // the thread that issues the TMA loads sits in a middle warp: the first and last warp own the one-sided y rows of
+      // edge tiles, the x tasks of the one-sided columns are mapped away from all three (x_pass)
+      static constexpr int ISSUE_WARP = C::NW / 2, ISSUE_TID = 32 * ISSUE_WARP;
+      static constexpr int XSHIFT     = (C::NW >= 8) ? 3 : 0; // task t of a full round runs on warp (t + XSHIFT) % NW
       double             acc[RY][2 * P];
       double             dsum; // fused dot product (DOT): sum of src * (A src) over the points this thread stores
       // pipeline state: seq = number of planes whose x pass is done; everything else is derived from it
@@ -246,7 +256,32 @@ namespace gdm
       // stage / parity of the TMA ring and a/r buffers of plane sequence number q
       __device__ __forceinline__ int      stage_of(const int q) const { return q % S; }
       __device__ __forceinline__ unsigned parity_of(const int q) const { return (unsigned)(q / S) & 1u; }
-      __device__ __forceinline__ int      ab_of(const int q) const { return OFF_AB + (q & 1) * AB_BUF; }
+      __device__ __forceinline__ int      ab_of(const int q) const { return OFF_AB + (q % NAB) * AB_BUF; }
+      // split hand-over (SPLIT): full[b] = every warp finished its x tasks into buffer b (and its reads of the TMA stage),
+      // empty[b] = every warp finished reading buffer b in its y/z pass
+      __device__ __forceinline__ uint32_t bar_full(const int q) const { return bar0 + 8 * (S + q % NAB); }
+      __device__ __forceinline__ uint32_t bar_empty(const int q) const { return bar0 + 8 * (S + NAB + q % NAB); }
+      __device__ __forceinline__ void     warp_arrive(const uint32_t bar) const
+      {
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+      }
+      // before the y/z pass of plane q: its a/r buffer is complete; thread 0 then refills the TMA stage plane q was read from
+      __device__ __forceinline__ void yz_acquire(const int q)
+      {
+        if constexpr (SPLIT)
+          {
+            mbar_wait(bar_full(q), (unsigned)(q / NAB) & 1u);
+            if (tid == ISSUE_TID)
+              issue(stage_of(q));
+          }
+      }
+      __device__ __forceinline__ void yz_release(const int q)
+      {
+        if constexpr (SPLIT)
+          warp_arrive(bar_empty(q));
+      }
 
       // ---- x pass of one plane: staged tile at in_off -> a/r buffer at a_off (doubles); x0 = first output column.
       // FIX: the tile touches one-sided rows of A_x/B_x (recomputed from the row tables by the threads that own them).
@@ -319,16 +354,26 @@ namespace gdm
                         const int     rc = (gxx <= P) ? gxx : gxx - (g.nx - P) + P + 1;
                         const double *ta = smem + OFF_TB + (0 * NBT + rc) * WP;
                         const double *tb = smem + OFF_TB + (1 * NBT + rc) * WP;
-                        double        ra = 0.0, rbv = 0.0;
+                        // two partial sums per row: the one-sided rows sit on the critical path of their warp
+                        double ra = 0.0, rbv = 0.0, ra2 = 0.0, rbv2 = 0.0;
 #pragma unroll
                         for (int t = 0; t < W; ++t)
                           {
-                            ra = fma(ta[t], v[j + t], ra);
-                            if (HASB)
-                              rbv = fma(tb[t], v[j + t], rbv);
+                            if (t & 1)
+                              {
+                                ra2 = fma(ta[t], v[j + t], ra2);
+                                if (HASB)
+                                  rbv2 = fma(tb[t], v[j + t], rbv2);
+                              }
+                            else
+                              {
+                                ra = fma(ta[t], v[j + t], ra);
+                                if (HASB)
+                                  rbv = fma(tb[t], v[j + t], rbv);
+                              }
                           }
-                        a[j]  = ra;
-                        bb[j] = rbv;
+                        a[j]  = ra + ra2;
+                        bb[j] = rbv + rbv2;
                       }
                   }
               }
@@ -350,17 +395,26 @@ namespace gdm
       __device__ __forceinline__ void x_pass(const int q, const int x0)
       {
         const int st = stage_of(q);
+        if constexpr (SPLIT)
+          if (q >= NAB)
+            mbar_wait(bar_empty(q), (unsigned)(q / NAB - 1) & 1u); // the y/z pass of plane q - NAB has released the buffer
         mbar_wait(bar0 + 8 * st, parity_of(q));
         const int in_off = st * C::STAGE_DOUBLES, a_off = ab_of(q);
 #pragma unroll
+        const int wrot = (warp >= XSHIFT) ? warp - XSHIFT : warp - XSHIFT + C::NW;
+#pragma unroll
         for (int rd = 0; rd < FULL_ROUNDS; ++rd)
-          x_task<FIX>(warp + rd * C::NW, in_off, a_off, x0);
+          x_task<FIX>(wrot + rd * C::NW, in_off, a_off, x0);
         if constexpr (EXTRA > 0)
           {
-            const int e = (warp - 1 + q) % (C::NW - 1);
-            if (warp != 0 && e < EXTRA)
+            // the tasks left over rotate over the warps other than the issuer's with the plane counter
+            const int wi = (warp > ISSUE_WARP) ? warp - 1 : warp;
+            const int e  = (wi + q) % (C::NW - 1);
+            if (warp != ISSUE_WARP && e < EXTRA)
               x_task<FIX>(FULL_ROUNDS * C::NW + e, in_off, a_off, x0);
           }
+        if constexpr (SPLIT)
+          warp_arrive(bar_full(q));
       }
 
       // ---- y pass + z pass of input plane k from the a/r buffer at ab_off: res = emitted plane k - P.
@@ -426,19 +480,34 @@ namespace gdm
                       const int     rc = (gy <= P) ? gy : gy - (g.ny - P) + P + 1;
                       const double *ta = smem + OFF_TB + (2 * NBT + rc) * WP;
                       const double *tb = smem + OFF_TB + (3 * NBT + rc) * WP;
-                      t1               = 0.0;
-                      t2               = 0.0;
+                      t1 = 0.0;
+                      t2 = 0.0;
+                      double t1b = 0.0, t2b = 0.0, t2c = 0.0, t2d = 0.0; // independent partial sums (short chains)
 #pragma unroll
                       for (int t = 0; t < W; ++t)
                         {
                           const double ca = ta[t];
-                          t1              = fma(ca, aw[i + t], t1);
+                          if (t & 1)
+                            t1b = fma(ca, aw[i + t], t1b);
+                          else
+                            t1 = fma(ca, aw[i + t], t1);
                           if (HASB)
                             {
-                              t2 = fma(ca, bw[i + t], t2);
-                              t2 = fma(tb[t], aw[i + t], t2);
+                              if (t & 1)
+                                {
+                                  t2b = fma(ca, bw[i + t], t2b);
+                                  t2d = fma(tb[t], aw[i + t], t2d);
+                                }
+                              else
+                                {
+                                  t2  = fma(ca, bw[i + t], t2);
+                                  t2c = fma(tb[t], aw[i + t], t2c);
+                                }
                             }
                         }
+                      t1 += t1b;
+                      if (HASB)
+                        t2 = (t2 + t2b) + (t2c + t2d);
                     }
                 }
             // z pass, scatter form: y_r += A_z[r][k] ua + R_z[r][k] t1 for the 2P+1 rows r around input plane k; the
@@ -514,7 +583,9 @@ namespace gdm
             if (!last || c.more)
               x_pass<true>(seq, last ? c.x0_next : c.J.x0);
             double res[RY];
+            yz_acquire(seq - 1);
             yz_pass<true>(k >= g.kz_lo && k < g.kz_hi, k, ab_of(seq - 1), c.gy_first, res);
+            yz_release(seq - 1);
             if (k < c.k_scr)
               {
 #pragma unroll
@@ -524,11 +595,14 @@ namespace gdm
               }
             else if (k - P >= g.cz0)
               store_rows<false>(c.out, res, c.nst);
-            __syncthreads();
-            if (tid == 0)
+            const bool signal = (k + 1 == c.k_scr && c.J.seam_lo >= 0); // the partial planes of the seam are complete
+            if (!SPLIT || signal)
+              __syncthreads();
+            if (tid == ISSUE_TID)
               {
-                issue(stage_of(seq));
-                if (k + 1 == c.k_scr && c.J.seam_lo >= 0)
+                if constexpr (!SPLIT)
+                  issue(stage_of(seq));
+                if (signal)
                   {
                     __threadfence();
                     st_release(g.flags + c.J.seam_lo, g.epoch);
@@ -548,11 +622,16 @@ namespace gdm
           {
             x_pass<!INNER>(seq, c.J.x0);
             double res[RY];
+            yz_acquire(seq - 1);
             yz_rows<!INNER, true>(g.Az, g.Bz, ab_of(seq - 1), c.gy_first, res);
+            yz_release(seq - 1);
             store_rows<INNER>(c.out, res, c.nst);
-            __syncthreads();
-            if (tid == 0)
-              issue(stage_of(seq));
+            if constexpr (!SPLIT)
+              {
+                __syncthreads();
+                if (tid == ISSUE_TID)
+                  issue(stage_of(seq));
+              }
             ++seq;
             c.out += g.plane;
           }
@@ -572,6 +651,8 @@ namespace gdm
           {
             for (int s = 0; s < S; ++s)
               mbar_init(bar0 + 8 * s, 1);
+            for (int s = 0; s < 2 * NAB; ++s)
+              mbar_init(bar0 + 8 * (S + s), C::NW);
             mbar_fence_init();
             const unsigned t = atomicAdd(g.ticket, 1u) - g.ticket_base;
             smisc[0]         = g.grid - 1 - (int)t; // descending: a share only waits for shares with a larger index
@@ -599,7 +680,7 @@ namespace gdm
             return;
           }
         JobP Jn = load_job(jb); // next job of the compute loop (every thread); the issuer keeps its own cursor
-        if (tid == 0)
+        if (tid == ISSUE_TID)
           {
             int *cur = smisc + 4;
             cur[0]   = 0;
@@ -623,9 +704,12 @@ namespace gdm
         // prologue: x pass of the first plane of the first job
         seq = 0;
         x_pass<true>(0, Jn.x0);
-        __syncthreads();
-        if (tid == 0)
-          issue(0);
+        if constexpr (!SPLIT)
+          {
+            __syncthreads();
+            if (tid == ISSUE_TID)
+              issue(0);
+          }
         seq = 1;
 
         for (int j = 0; j < njobs; ++j)
@@ -777,16 +861,24 @@ namespace gdm
       int      mode = 0;
       double   sigma = 0.0;
       int      kz_lo = 0, kz_hi = 0;
-      std::vector<double> hBe[3];
+      // effective tables: A (unfolded in periodic directions), B or R = B - alpha A (tap split)
+      std::vector<double> hAe[3], hBe[3];
+      double  *d_Ae[2] = {nullptr, nullptr};
       double  *d_Be[2] = {nullptr, nullptr};
+      bool     periodic[3] = {false, false, false};
+      double  *d_save = nullptr; // periodic: saved values of the patched nodes
+      int64_t  n_save = 0;
       double  *d_zt    = nullptr;
       std::map<std::pair<int, int>, PartitionP> parts;
       std::map<const void *, CUtensorMap>        maps;
       std::map<std::pair<int, const void *>, bool> attr_set; // (device, kernel)
       ~PersPlan()
       {
+        cudaFree(d_Ae[0]);
+        cudaFree(d_Ae[1]);
         cudaFree(d_Be[0]);
         cudaFree(d_Be[1]);
+        cudaFree(d_save);
         cudaFree(d_zt);
         for (auto &kv : parts)
           free_part(kv.second);
@@ -819,7 +911,11 @@ namespace gdm
   X(822, CfgP<3, 4, 7, 4, 4, 2>)      \
   X(823, CfgP<3, 6, 5, 4, 3, 2>)      \
   X(824, CfgP<3, 4, 6, 8, 3, 2>)      \
-  X(825, CfgP<3, 4, 6, 4, 4, 2>)
+  X(825, CfgP<3, 4, 6, 4, 4, 2>)      \
+  X(830, CfgP<3, 4, 8, 4, 4, 2, 1>)   \
+  X(831, CfgP<3, 4, 6, 4, 4, 2, 1>)   \
+  X(832, CfgP<3, 4, 6, 4, 3, 2, 1>)   \
+  X(833, CfgP<3, 4, 6, 8, 4, 2, 1>)
 #else
 #define GDM_PERS_CONFIGS_EXP(X)
 #endif
@@ -862,12 +958,15 @@ namespace gdm
   } // namespace
 
   // Work partition of the persistent kernel (host logic, also exported for the CPU tests).
-  //   tiles_x x tiles_y tile columns, input planes [k0, k1), at most `slots` shares, shares cut no closer than min_len
-  //   planes to a column end or to each other.  aligned: m = slots / tiles equal chunks per column cut at the same planes
-  //   (neighbouring tiles stream the same planes at the same time, their halos meet in L2), the planes above them are
-  //   swept tile-major over the spare shares.
-  // Output: job_ptr (size grid+1) and jobs as 6 ints {tile x, tile y, k0, k1, seam_lo, seam_hi}; seam ids are job indices.
-  void pers_partition_host(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, bool aligned, int forced_L,
+  //   tiles_x x tiles_y tile columns, input planes [k0, k1), at most `slots` shares (one CTA each).  weights[t] is the
+  //   cost of one plane of tile t (per mille of an interior tile; nullptr: all equal): tiles that touch one-sided rows
+  //   are slower, so their columns are cut into shorter jobs.  No job is shorter than min_len planes unless it is a whole
+  //   column.  aligned: every column is cut into equal-cost chunks from the bottom (neighbouring tiles of the same class
+  //   stream the same planes at the same time: their halos meet in L2); the planes left above the last full chunk are
+  //   swept tile-major over the spare shares.  Otherwise: one tile-major sweep.
+  // Output: job_ptr (size grid+1) and jobs as 6 ints {tile x, tile y, k_begin, k_end, seam_lo, seam_hi}; seam ids are job
+  // indices.  A job's upper neighbour always lies in a share with a larger index (the kernel's ticket order relies on it).
+  void pers_partition_host(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, bool aligned, const int *weights,
                            std::vector<int> &job_ptr, std::vector<int> &jobs6)
   {
     GDM_REQUIRE(tiles_x > 0 && tiles_y > 0 && k1 >= k0 && slots > 0 && min_len > 0, GDM_ERR_INVALID, "invalid partition request");
@@ -882,72 +981,106 @@ namespace gdm
     jobs6.clear();
     if (nz == 0)
       return;
-    // tile-major sweep of planes [za, zb) of every tile over at most n shares: ideal cuts every total/G planes, each moved
-    // to the nearest position that leaves no piece shorter than min_len
-    auto sweep = [&](Shares &shares, int za, int zb, int n) {
-      const int len = zb - za;
-      if (len <= 0 || n <= 0)
+    auto wt = [&](int t) -> int64_t { return weights ? std::max(1, weights[t]) : 1000; };
+    int64_t total = 0;
+    for (int t = 0; t < tiles; ++t)
+      total += wt(t) * nz;
+    // tile-major sweep of planes [za[t], k1) of every tile over at most n shares of about equal cost; a cut is moved to
+    // the nearest position that leaves no piece shorter than min_len
+    auto sweep = [&](Shares &shares, const std::vector<int> &za, int n) {
+      int64_t rem = 0, planes = 0;
+      int     cols = 0, max_piece = 0;
+      for (int t = 0; t < tiles; ++t)
+        if (k1 > za[t])
+          {
+            rem += wt(t) * (k1 - za[t]);
+            planes += k1 - za[t];
+            max_piece = std::max(max_piece, k1 - za[t]);
+            ++cols;
+          }
+      if (rem == 0 || n <= 0)
         return;
-      const int64_t total = (int64_t)tiles * len;
-      int64_t       G     = std::min<int64_t>(n, std::max<int64_t>(1, total / (2 * (int64_t)min_len)));
-      if (len < 2 * min_len) // columns are not cut
-        G = std::min<int64_t>(G, tiles);
-      std::vector<int64_t> cuts;
-      for (int64_t j = 0; j <= G; ++j)
+      // number of shares: at least 2 min_len planes each; columns shorter than 2 min_len are not cut
+      int64_t G = std::max<int64_t>(1, std::min<int64_t>(n, planes / (2 * (int64_t)min_len)));
+      if (max_piece < 2 * min_len)
+        G = std::min<int64_t>(G, cols);
+      const double target = (double)rem / (double)G;
+      std::vector<Piece> cur;
+      int64_t            closed = 0;
+      double             done = 0.0; // cost swept so far
+      for (int t = 0; t < tiles; ++t)
         {
-          int64_t c = (total * j + G / 2) / G;
-          if (len < 2 * min_len)
-            c = ((c + len / 2) / len) * len;
-          else
+          int z = za[t];
+          while (z < k1)
             {
-              const int64_t off = c % len, base = c - off;
-              if (off != 0 && off < min_len)
-                c = base + ((2 * off < min_len) ? 0 : min_len);
-              else if (off != 0 && len - off < min_len)
-                c = base + ((2 * (len - off) < min_len) ? len : len - min_len);
+              const double w     = (double)wt(t);
+              const double room  = target * (double)(closed + 1) - done; // cost left in the current share
+              int          take  = (int)(room / w + 0.5);
+              const int    avail = k1 - z;
+              const bool   lastshare = closed + 1 >= G;
+              if (lastshare || take >= avail)
+                take = avail;
+              else
+                {
+                  // valid cut positions inside this column piece: >= min_len from either end of [z0, k1) where z0 is the
+                  // start of the piece being carved (z itself starts a new piece of this share)
+                  if (take < min_len)
+                    take = (2 * take < min_len && !cur.empty()) ? 0 : min_len;
+                  if (avail - take < min_len)
+                    take = (2 * (avail - take) < min_len || avail < 2 * min_len) ? avail : avail - min_len;
+                  if (take > avail)
+                    take = avail;
+                  if (avail < 2 * min_len && take != 0)
+                    take = avail;
+                }
+              if (take > 0)
+                {
+                  if (!cur.empty() && cur.back().tile == t && cur.back().b == z)
+                    cur.back().b = z + take;
+                  else
+                    cur.push_back({t, z, z + take});
+                  z += take;
+                  done += w * take;
+                }
+              if (!lastshare && (take == 0 || done >= target * (double)(closed + 1) - 0.5 * w))
+                {
+                  if (!cur.empty())
+                    {
+                      shares.push_back(cur);
+                      cur.clear();
+                    }
+                  ++closed;
+                }
             }
-          if (cuts.empty() || c > cuts.back())
-            cuts.push_back(c);
         }
-      for (size_t j = 0; j + 1 < cuts.size(); ++j)
-        {
-          std::vector<Piece> sh;
-          int64_t            c = cuts[j];
-          while (c < cuts[j + 1])
-            {
-              const int     t   = (int)(c / len);
-              const int64_t end = std::min<int64_t>(cuts[j + 1], (int64_t)(t + 1) * len);
-              sh.push_back({t, za + (int)(c - (int64_t)t * len), za + (int)(end - (int64_t)t * len)});
-              c = end;
-            }
-          shares.push_back(sh);
-        }
+      if (!cur.empty())
+        shares.push_back(cur);
     };
-    // m aligned chunks of L planes per column, the planes above them swept over the spare shares
-    auto build = [&](int L) {
-      Shares shares;
-      if (L <= 0)
+    // aligned chunks of cost T per column from the bottom, the rest swept over the spare shares
+    auto build = [&](double T) {
+      Shares           shares;
+      std::vector<int> za(tiles, k0);
+      if (T > 0.0)
         {
-          sweep(shares, k0, k1, slots);
-          return shares;
-        }
-      const int m  = std::min(slots / tiles, std::max(1, nz / (2 * min_len)));
-      int       zl = k0;
-      for (int c = 0; c < m; ++c)
-        {
-          const int a = k0 + c * L, b = std::min(k1, a + L);
-          if (a >= b)
-            break;
-          int bb = b;
-          if (k1 - b > 0 && k1 - b < min_len)
-            bb = k1;
+          std::vector<int> Lt(tiles), mt(tiles);
+          int              mmax = 0;
           for (int t = 0; t < tiles; ++t)
-            shares.push_back({{t, a, bb}});
-          zl = bb;
-          if (bb == k1)
-            break;
+            {
+              Lt[t] = std::max(min_len, (int)(T / (double)wt(t) + 0.5));
+              mt[t] = nz / Lt[t];
+              if (mt[t] > 0 && nz - mt[t] * Lt[t] > 0 && nz - mt[t] * Lt[t] < min_len)
+                --mt[t]; // keep the remainder a valid piece (it is swept)
+              mmax = std::max(mmax, mt[t]);
+            }
+          for (int c = 0; c < mmax; ++c)
+            for (int t = 0; t < tiles; ++t)
+              if (c < mt[t])
+                {
+                  shares.push_back({{t, k0 + c * Lt[t], k0 + (c + 1) * Lt[t]}});
+                  za[t] = k0 + (c + 1) * Lt[t];
+                }
         }
-      sweep(shares, zl, k1, std::max(1, slots - (int)shares.size()));
+      sweep(shares, za, std::max(1, slots - (int)shares.size()));
       return shares;
     };
     auto longest = [&](const Shares &shares) {
@@ -956,45 +1089,36 @@ namespace gdm
         {
           int64_t n = 0;
           for (auto &p : sh)
-            n += p.b - p.a;
+            n += wt(p.tile) * (p.b - p.a);
           mx = std::max(mx, n);
         }
       return mx;
     };
     Shares shares;
-    // (no aligned part if the spare shares would each have to visit many tile columns)
-    if (aligned && slots >= tiles && nz >= 4 * min_len && (slots % tiles == 0 || tiles / (slots % tiles) <= 3))
+    const bool cuttable = nz >= 4 * min_len && slots >= tiles;
+    if (aligned && cuttable)
       {
-        const int m     = std::min(slots / tiles, std::max(1, nz / (2 * min_len)));
-        const int spare = (m == slots / tiles) ? slots - m * tiles : 0;
-        const int Lmax  = (nz + m - 1) / m;
-        if (forced_L > 0)
-          shares = build(std::min(std::max(forced_L, min_len), Lmax));
-        else if (spare == 0)
-          shares = build(Lmax);
-        else
+        // search the chunk cost around the ideal share for the shortest longest share
+        const double T0   = (double)total / (double)slots;
+        int64_t      best = -1;
+        for (int i = -6; i <= 12; ++i)
           {
-            // equal shares: m L + R = nz with L = tiles R / spare; search around it for the shortest longest share
-            const int Lbal = (int)((double)nz / ((double)m + (double)spare / tiles) + 0.5);
-            int64_t   best = -1;
-            for (int L = std::min(Lmax, Lbal + 6); L >= std::max(min_len, Lbal - 6); --L)
+            const double T = T0 * (1.0 + 0.01 * i);
+            if (T / 1000.0 < (double)min_len)
+              continue;
+            Shares        cand = build(T);
+            const int64_t mx   = longest(cand);
+            if ((int)cand.size() <= slots && (best < 0 || mx < best))
               {
-                if ((int64_t)m * L < nz && nz - m * L < min_len)
-                  continue;
-                Shares        cand = build(L);
-                const int64_t mx   = longest(cand);
-                if ((int)cand.size() <= slots && (best < 0 || mx < best))
-                  {
-                    best   = mx;
-                    shares = std::move(cand);
-                  }
+                best   = mx;
+                shares = std::move(cand);
               }
-            if (best < 0)
-              shares = build(0);
           }
+        if (best < 0)
+          shares = build(0.0);
       }
     else
-      shares = build(0);
+      shares = build(0.0);
     // jobs in share order; seams: the job that starts at plane b of tile t is the upper neighbour of the job ending at b
     std::map<std::pair<int, int>, int> starts; // (tile, first plane) -> job index
     int                                nj = 0;
@@ -1024,7 +1148,7 @@ namespace gdm
   namespace
   {
     template <class C>
-    PartitionP &get_partition(Context &ctx, PersPlan &plan, int oz0, int oz1)
+    PartitionP &get_partition(Operator &op, PersPlan &plan, int oz0, int oz1)
     {
       const auto key = std::make_pair(oz0, oz1);
       auto       it  = plan.parts.find(key);
@@ -1038,6 +1162,7 @@ namespace gdm
           plan.parts.clear();
         }
       constexpr int P = C::P;
+      Context      &ctx = *op.sys->ctx;
       const int     k0 = std::max(oz0 - P, plan.in_lo), k1 = std::min(oz1 + P, plan.in_hi);
       int           slots = ctx.sm_count * C::MINB;
       if (const char *env = std::getenv("GDM_PERS_SLOTS"))
@@ -1047,7 +1172,24 @@ namespace gdm
       const bool  aligned = !(env_al && env_al[0] == '0');
       const char *env_L   = std::getenv("GDM_PERS_L");
       std::vector<int> ptr, j6;
-      pers_partition_host(plan.tiles_x, plan.tiles_y, k0, std::max(k0, k1), slots, min_len, aligned, env_L ? atoi(env_L) : 0, ptr, j6);
+      // cost of a plane per tile (per mille of an interior tile): tiles that touch one-sided rows in x / y or store
+      // partial rows run the general plane body and wait for the warps that recompute the boundary rows
+      // (measured on B200, profiles/r2/pers_trace_*.txt).  GDM_PERS_WEIGHTS="x,y,xy" overrides (per mille).
+      int wx = 1390, wy = 1330, wxy = 1480;
+      if (const char *env = std::getenv("GDM_PERS_WEIGHTS"))
+        sscanf(env, "%d,%d,%d", &wx, &wy, &wxy);
+      const Layout    &L = op.sys->L;
+      std::vector<int> weights((size_t)plan.tiles_x * plan.tiles_y, 1000);
+      for (int ty = 0; ty < plan.tiles_y; ++ty)
+        for (int tx = 0; tx < plan.tiles_x; ++tx)
+          {
+            const int  x0 = plan.xorg + tx * C::TX, y0 = plan.cy0 + ty * C::TY;
+            const bool xe = !(x0 > P && x0 + C::TX - 1 < L.N[0] - P && x0 >= plan.cx0 && x0 + C::TX <= plan.cx1);
+            const bool ye = !(y0 > P && y0 + C::TY - 1 < L.N[1] - P && y0 >= plan.cy0 && y0 + C::TY <= plan.cy1);
+            weights[(size_t)ty * plan.tiles_x + tx] = (xe && ye) ? wxy : (xe ? wx : (ye ? wy : 1000));
+          }
+      (void)env_L;
+      pers_partition_host(plan.tiles_x, plan.tiles_y, k0, std::max(k0, k1), slots, min_len, aligned, weights.data(), ptr, j6);
       PartitionP part;
       part.grid   = (int)ptr.size() - 1;
       part.n_jobs = (int)(j6.size() / 6);
@@ -1128,7 +1270,7 @@ namespace gdm
       const Layout &L   = op.sys->L;
       if (oz1 <= oz0)
         return 0;
-      PartitionP &part = get_partition<C>(ctx, plan, oz0, oz1);
+      PartitionP &part = get_partition<C>(op, plan, oz0, oz1);
       if (part.grid <= 0)
         return 0;
       ArgsP<P> a;
@@ -1147,10 +1289,10 @@ namespace gdm
       a.kz_lo    = plan.kz_lo;
       a.kz_hi    = plan.kz_hi;
       a.grid     = part.grid;
-      a.tabAx    = op.dA[0];
-      a.tabAy    = op.dA[1];
-      a.tabBx    = (MODE == 1) ? plan.d_Be[0] : op.dB[0];
-      a.tabBy    = (MODE == 1) ? plan.d_Be[1] : op.dB[1];
+      a.tabAx    = plan.d_Ae[0];
+      a.tabAy    = plan.d_Ae[1];
+      a.tabBx    = plan.d_Be[0];
+      a.tabBy    = plan.d_Be[1];
       a.sigma    = plan.sigma;
       a.zt       = plan.d_zt;
       a.jobs     = part.d_jobs;
@@ -1162,12 +1304,12 @@ namespace gdm
       a.trace    = part.d_trace;
       a.dot_src  = dot_src;
       a.dot_partials = dot_partials;
-      const std::vector<double> *hB = (MODE == 1) ? plan.hBe : op.hB;
+      const std::vector<double> *hA = plan.hAe, *hB = plan.hBe;
       const int                  ir = P + 1; // any interior (Toeplitz) row
       for (int d = 0; d <= P; ++d)
         {
-          a.Ax[d] = op.hA[0][(size_t)ir * W + P + d];
-          a.Ay[d] = op.hA[1][(size_t)ir * W + P + d];
+          a.Ax[d] = hA[0][(size_t)ir * W + P + d];
+          a.Ay[d] = hA[1][(size_t)ir * W + P + d];
           a.Bx[d] = op.has_B ? hB[0][(size_t)ir * W + P + d] : 0.0;
           a.By[d] = op.has_B ? hB[1][(size_t)ir * W + P + d] : 0.0;
         }
@@ -1186,7 +1328,7 @@ namespace gdm
           GDM_REQUIRE(r >= 0, GDM_ERR_INTERNAL, "persistent fused kernel: no interior z row on this rank");
           for (int j = 0; j < W; ++j)
             {
-              a.Az[j] = op.desc.scale * op.hA[2][(size_t)r * W + (2 * P - j)];
+              a.Az[j] = op.desc.scale * hA[2][(size_t)r * W + (2 * P - j)];
               a.Bz[j] = op.has_B ? op.desc.scale * hB[2][(size_t)r * W + (2 * P - j)] : 0.0;
             }
         }
@@ -1239,6 +1381,232 @@ namespace gdm
     }
   } // namespace
 
+  namespace
+  {
+    // ---- periodic directions: C^T A C x = fold( A ( dup x ) ) on the N+1 stored nodes per direction.
+    // With several ranks the partitioned direction wraps between the first and the last slab: the last rank receives
+    // plane 0 of rank 0 (zimg) before it patches its plane N, rank 0 receives row N of the last rank (zimg again) before
+    // it folds its plane 0 (one extra plane between the last and the first rank).
+    struct PeriodicK
+    {
+      double       *v;     // vector that is patched / folded / restored
+      double       *save;  // saved values of the patched nodes
+      const double *zimg;  // one plane received from the peer rank (nullptr: the wrap in z is local)
+      int           ln[3]; // stored nodes per direction
+      int           face[3]; // coordinate (local index) of the face this kernel enumerates per direction, -1: none
+      int           hi[3], lo[3]; // local index of the duplicate node N / of node 0 per periodic direction (-1: not periodic;
+                                  // for direction 2 the index may lie outside this rank's planes)
+      int64_t       stride[3];
+      int64_t       face_off[4]; // prefix sums of the face sizes (in direction order)
+      int           z_lo, z_hi;  // planes of direction 2 this rank works on (local indices: its owned planes)
+    };
+
+    // thread -> node of the union of the enumerated faces; a node on several faces is handled through the lowest
+    // direction.  Returns false if the thread has no node.
+    __device__ __forceinline__ bool periodic_node(const PeriodicK &a, int64_t tid, int (&idx)[3])
+    {
+      if (tid >= a.face_off[3])
+        return false;
+      int d = 0;
+      while (tid >= a.face_off[d + 1])
+        ++d;
+      tid -= a.face_off[d];
+      const int e0 = (d == 0) ? 1 : 0, e1 = (d == 2) ? 1 : 2;
+      idx[d]       = a.face[d];
+      idx[e0]      = (int)(tid % a.ln[e0]);
+      idx[e1]      = (int)(tid / a.ln[e0]);
+      if (idx[e1] >= a.ln[e1])
+        return false;
+      for (int e = 0; e < d; ++e)
+        if (a.face[e] >= 0 && idx[e] == a.face[e])
+          return false;
+      return idx[2] >= a.z_lo && idx[2] < a.z_hi;
+    }
+
+    // x~ = C x: every node with a periodic coordinate N takes the value of its image in the fundamental domain; the old
+    // value is saved (the vector is restored after the apply)
+    __global__ void periodic_patch_kernel(const PeriodicK a)
+    {
+      const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      int           idx[3];
+      if (!periodic_node(a, tid, idx))
+        return;
+      int64_t off = 0, img = 0;
+      bool    remote = false;
+      for (int d = 0; d < 3; ++d)
+        {
+          off += idx[d] * a.stride[d];
+          const bool dup = a.hi[d] >= 0 && idx[d] == a.hi[d];
+          if (d == 2 && dup && a.zimg != nullptr)
+            remote = true; // the image plane (global plane 0) was received into zimg
+          else
+            img += (dup ? a.lo[d] : idx[d]) * a.stride[d];
+        }
+      a.save[tid] = a.v[off];
+      a.v[off]    = remote ? a.zimg[img] : a.v[img];
+    }
+    __global__ void periodic_restore_kernel(const PeriodicK a)
+    {
+      const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      int           idx[3];
+      if (!periodic_node(a, tid, idx))
+        return;
+      int64_t off = 0;
+      for (int d = 0; d < 3; ++d)
+        off += idx[d] * a.stride[d];
+      a.v[off] = a.save[tid];
+    }
+    // y = C^T y~: a node with periodic coordinates equal to 0 adds the rows of its images (coordinate N)
+    __global__ void periodic_fold_kernel(const PeriodicK a)
+    {
+      const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      int           idx[3];
+      if (!periodic_node(a, tid, idx))
+        return;
+      for (int d = 0; d < 3; ++d)
+        if (a.hi[d] >= 0 && idx[d] == a.hi[d])
+          return; // itself a duplicate node: its row is overwritten by the constrained-row kernel
+      int64_t off = 0;
+      for (int d = 0; d < 3; ++d)
+        off += idx[d] * a.stride[d];
+      double sum = a.v[off];
+      for (int m = 1; m < 8; ++m)
+        {
+          int64_t o  = 0;
+          bool    ok = true, remote = false;
+          for (int d = 0; d < 3; ++d)
+            {
+              const bool shift = (m >> d) & 1;
+              if (shift && !(a.lo[d] >= 0 && idx[d] == a.lo[d] && a.hi[d] != -1))
+                ok = false;
+              if (shift && d == 2 && a.zimg != nullptr)
+                remote = true; // row N of the last rank was received into zimg
+              else
+                o += (shift ? a.hi[d] : idx[d]) * a.stride[d];
+            }
+          if (ok)
+            sum += remote ? a.zimg[o] : a.v[o];
+        }
+      a.v[off] = sum;
+    }
+
+    // which: 0 patch / restore (faces at the duplicate nodes), 1 fold (faces at node 0)
+    PeriodicK periodic_args(const Operator &op, PersPlan &plan, double *v, int which)
+    {
+      const Layout &L = op.sys->L;
+      PeriodicK     a;
+      a.v    = v;
+      a.zimg = nullptr;
+      a.z_lo = L.own0 - L.loc0;
+      a.z_hi = L.own1 - L.loc0;
+      a.face_off[0] = 0;
+      for (int d = 0; d < 3; ++d)
+        {
+          a.ln[d]     = L.ln[d];
+          a.stride[d] = L.stride[d];
+          const int shift = (d == 2) ? L.loc0 : 0;
+          a.hi[d]     = plan.periodic[d] ? L.N[d] - shift : -1;
+          a.lo[d]     = plan.periodic[d] ? 0 - shift : -1;
+          if (plan.periodic[d] && a.hi[d] == -1)
+            a.hi[d] = -2; // (periodic, but the duplicate plane is far below this rank's planes: keep it distinct from -1)
+          const int f = plan.periodic[d] ? (which == 0 ? a.hi[d] : a.lo[d]) : -1;
+          bool stored = f >= 0 && f < L.ln[d];
+          if (d == 2)
+            stored = stored && f >= a.z_lo && f < a.z_hi;
+          a.face[d]   = stored ? f : -1;
+          const int e0 = (d == 0) ? 1 : 0, e1 = (d == 2) ? 1 : 2;
+          a.face_off[d + 1] = a.face_off[d] + (a.face[d] >= 0 ? (int64_t)L.ln[e0] * L.ln[e1] : 0);
+        }
+      const int64_t need = std::max<int64_t>(a.face_off[3], 1) + L.plane; // saved values + one received plane
+      if (plan.n_save < need)
+        {
+          GDM_CUDA_CHECK(cudaDeviceSynchronize());
+          cudaFree(plan.d_save);
+          plan.d_save = nullptr;
+          GDM_CUDA_CHECK(cudaMalloc(&plan.d_save, (size_t)need * sizeof(double)));
+          plan.n_save = need;
+        }
+      a.save = plan.d_save + L.plane;
+      return a;
+    }
+  } // namespace
+
+  bool pers_has_periodic(const void *p)
+  {
+    const PersPlan &plan = *static_cast<const PersPlan *>(p);
+    return plan.periodic[0] || plan.periodic[1] || plan.periodic[2];
+  }
+
+  void pers_periodic_pre(Operator &op, void *p, double *src, cudaStream_t stream)
+  {
+    PersPlan &plan = *static_cast<PersPlan *>(p);
+    if (!pers_has_periodic(p))
+      return;
+    const Layout &L = op.sys->L;
+    Context      &ctx = *op.sys->ctx;
+    PeriodicK     a = periodic_args(op, plan, src, 0);
+    if (plan.periodic[2] && L.n_ranks > 1)
+      {
+        // plane 0 of the first rank -> the rank that owns plane N
+        const int first = comm_plane_owner(L, 0), last = comm_plane_owner(L, L.N[2]);
+        if (first != last)
+          {
+            if (L.rank == first)
+              comm_send(ctx, src + (int64_t)(0 - L.loc0) * L.plane, L.plane, last, stream);
+            if (L.rank == last)
+              {
+                comm_recv(ctx, plan.d_save, L.plane, first, stream);
+                a.zimg = plan.d_save;
+              }
+          }
+      }
+    if (a.face_off[3] == 0)
+      return;
+    const int th = 128;
+    periodic_patch_kernel<<<(unsigned)((a.face_off[3] + th - 1) / th), th, 0, stream>>>(a);
+    ctx.launches++;
+    GDM_CUDA_CHECK(cudaGetLastError());
+  }
+
+  void pers_periodic_post(Operator &op, void *p, double *dst, double *src, cudaStream_t stream)
+  {
+    PersPlan &plan = *static_cast<PersPlan *>(p);
+    if (!pers_has_periodic(p))
+      return;
+    const Layout &L = op.sys->L;
+    Context      &ctx = *op.sys->ctx;
+    const int     th = 128;
+    // restore the input first (the received plane buffer is reused below)
+    PeriodicK r = periodic_args(op, plan, src, 0);
+    if (r.face_off[3] > 0)
+      {
+        periodic_restore_kernel<<<(unsigned)((r.face_off[3] + th - 1) / th), th, 0, stream>>>(r);
+        ctx.launches++;
+      }
+    PeriodicK a = periodic_args(op, plan, dst, 1);
+    if (plan.periodic[2] && L.n_ranks > 1)
+      {
+        // row N of the last rank -> the first rank (added to its plane 0)
+        const int first = comm_plane_owner(L, 0), last = comm_plane_owner(L, L.N[2]);
+        if (first != last)
+          {
+            if (L.rank == last)
+              comm_send(ctx, dst + (int64_t)(L.N[2] - L.loc0) * L.plane, L.plane, first, stream);
+            if (L.rank == first)
+              {
+                comm_recv(ctx, plan.d_save, L.plane, last, stream);
+                a.zimg = plan.d_save;
+              }
+          }
+      }
+    if (a.face_off[3] > 0)
+      {
+        periodic_fold_kernel<<<(unsigned)((a.face_off[3] + th - 1) / th), th, 0, stream>>>(a);
+        ctx.launches++;
+      }
+    GDM_CUDA_CHECK(cudaGetLastError());
+  }
+
   bool pers_supported(const Operator &op)
   {
     const Layout &L = op.sys->L;
@@ -1247,9 +1615,17 @@ namespace gdm
     if (!(L.p == 1 || L.p == 3 || L.p == 5))
       return false;
     for (int d = 0; d < 3; ++d)
-      if (op.periodic[d] || L.N[d] < 2 * L.p + 2)
-        return false;
+      {
+        if (L.N[d] < 2 * L.p + 2)
+          return false;
+        // a periodic direction is applied as fold . A . duplicate with the plain one-sided tables
+        if (op.periodic[d] && (op.dirichlet[d][0] || op.dirichlet[d][1] || op.hAu[d].empty()))
+          return false;
+      }
     if (L.own1 <= L.own0)
+      return false;
+    const char *env = std::getenv("GDM_PERS_PERIODIC");
+    if (env && env[0] == '0' && (op.periodic[0] || op.periodic[1] || op.periodic[2]))
       return false;
     return true;
   }
@@ -1296,7 +1672,13 @@ namespace gdm
     if (plan->kz_lo + (L.ln[2] - plan->kz_hi) > zrows)
       return nullptr;
     for (int d = 0; d < 3; ++d)
-      plan->hBe[d] = op.hB[d];
+      {
+        plan->periodic[d] = op.periodic[d];
+        plan->hAe[d]      = op.periodic[d] ? op.hAu[d] : op.hA[d];
+        plan->hBe[d]      = op.periodic[d] ? op.hBu[d] : op.hB[d];
+      }
+    const std::vector<double> *hA = plan->hAe;
+    const std::vector<double>  hB0[3] = {plan->hBe[0], plan->hBe[1], plan->hBe[2]};
     plan->sigma = 0.0;
     if (plan->mode == 1)
       {
@@ -1318,25 +1700,30 @@ namespace gdm
               }
             if (row < 0)
               return nullptr;
-            const double m = op.hA[d][(size_t)row * W + 2 * P], k = op.hB[d][(size_t)row * W + 2 * P];
-            if (m == 0.0 || op.hA[d][(size_t)row * W] != m || op.hB[d][(size_t)row * W] != k)
+            const double m = hA[d][(size_t)row * W + 2 * P], k = hB0[d][(size_t)row * W + 2 * P];
+            if (m == 0.0 || hA[d][(size_t)row * W] != m || hB0[d][(size_t)row * W] != k)
               return nullptr;
             alpha[d] = k / m;
           }
         for (int d = 0; d < 3; ++d)
           {
-            const int rows = (int)(op.hB[d].size() / W);
+            const int rows = (int)(hB0[d].size() / W);
             for (int r = 0; r < rows; ++r)
               {
                 for (int t = 0; t < W; ++t)
-                  plan->hBe[d][(size_t)r * W + t] = op.hB[d][(size_t)r * W + t] - alpha[d] * op.hA[d][(size_t)r * W + t];
+                  plan->hBe[d][(size_t)r * W + t] = hB0[d][(size_t)r * W + t] - alpha[d] * hA[d][(size_t)r * W + t];
                 const int gr = r + (d == 2 ? L.loc0 : 0); // global row
                 if (gr > P && gr < L.N[d] - P)
                   plan->hBe[d][(size_t)r * W] = plan->hBe[d][(size_t)r * W + 2 * P] = 0.0;
               }
           }
         plan->sigma = alpha[0] + alpha[1] + alpha[2];
-        for (int d = 0; d < 2; ++d)
+      }
+    for (int d = 0; d < 2; ++d)
+      {
+        GDM_CUDA_CHECK(cudaMalloc(&plan->d_Ae[d], plan->hAe[d].size() * sizeof(double)));
+        GDM_CUDA_CHECK(cudaMemcpy(plan->d_Ae[d], plan->hAe[d].data(), plan->hAe[d].size() * sizeof(double), cudaMemcpyHostToDevice));
+        if (op.has_B)
           {
             GDM_CUDA_CHECK(cudaMalloc(&plan->d_Be[d], plan->hBe[d].size() * sizeof(double)));
             GDM_CUDA_CHECK(cudaMemcpy(plan->d_Be[d], plan->hBe[d].data(), plan->hBe[d].size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -1354,7 +1741,7 @@ namespace gdm
             const int r = k - P + j;
             if (r < 0 || r >= L.ln[2])
               continue;
-            zt[(size_t)(c * 2 + 0) * wz + j] = op.desc.scale * op.hA[2][(size_t)r * W + (2 * P - j)];
+            zt[(size_t)(c * 2 + 0) * wz + j] = op.desc.scale * hA[2][(size_t)r * W + (2 * P - j)];
             if (op.has_B)
               zt[(size_t)(c * 2 + 1) * wz + j] = op.desc.scale * plan->hBe[2][(size_t)r * W + (2 * P - j)];
           }

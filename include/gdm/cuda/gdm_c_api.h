@@ -142,7 +142,7 @@ int      gdm_fused_partition(int aligned, int tiles_x, int tiles_y, int z0, int 
  * the slot a job reads when it flushes.  No job is shorter than min_len planes unless it is a whole column.
  * Replaces the per-rank slab loop of the reference's cell iteration (system.h:703-761) inside one GPU. */
 int      gdm_pers_partition(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, int aligned,
-                            int32_t *job_ptr, int32_t cap_ptr, int32_t *jobs6, int32_t cap_jobs, int32_t *n_shares,
+                            const int32_t *weights /* cost of a plane per tile, per mille; NULL = equal */, int32_t *job_ptr, int32_t cap_ptr, int32_t *jobs6, int32_t cap_jobs, int32_t *n_shares,
                             int32_t *n_jobs);
 
 /* ----------------------------------------------------------- constraints */
@@ -210,6 +210,9 @@ int gdm_operator_attach_csr(gdm_operator_t op, uint64_t n_rows, const uint64_t *
                             const uint64_t *rowptr, const uint64_t *col, const double *val);
 int gdm_operator_vmult(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src);     /* imports ghosts of src */
 int gdm_operator_vmult_add(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src);
+/* SparseMatrix::Tvmult: dst = A^T src.  Equal to vmult for mass and stiffness; for the advection kinds the transposed
+ * operator is created on first use (same velocity, scale, constraints). */
+int gdm_operator_tvmult(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src);
 /* Host-buffer form of vmult (the call a deal.II user makes with host vectors):
  * copies src to the device, applies, copies dst back; synchronises. */
 /* dst = A src and *src_dot_dst = <src, dst> over all ranks (the q = A p, p.q pair of SolverCG): on the fused path the

@@ -353,7 +353,10 @@ namespace dealii
     {
       internal::check(gdm_operator_vmult_add(h, dst.handle(), src.handle()));
     }
-    void Tvmult(Vector<double> &dst, const Vector<double> &src) const { vmult(dst, src); }
+    void Tvmult(Vector<double> &dst, const Vector<double> &src) const
+    {
+      internal::check(gdm_operator_tvmult(h, dst.handle(), src.handle()));
+    }
     unsigned long long m() const { return gdm_operator_m(h); }
     unsigned long long n() const { return gdm_operator_m(h); }
     gdm_operator_t     handle() const { return h; }

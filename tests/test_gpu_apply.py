@@ -147,3 +147,21 @@ def test_lumped_mass(lib):
             lumped[i] += rows[i]
     ref = np.where(lumped != 0, 1.0 / np.where(lumped != 0, lumped, 1.0), 0.0)
     assert rel_err(inv.numpy(), ref) <= TOL
+
+
+@pytest.mark.parametrize("dim,p,reps,bc", [(3, 3, [12, 11, 13], "dirichlet"), (2, 5, [14, 13], "periodic"), (3, 3, [35, 33, 20], "periodic")])
+@pytest.mark.parametrize("kind", ["mass", "stiffness", "advection", "advection_t"])
+def test_tvmult(lib, dim, p, reps, bc, kind):
+    """SparseMatrix::Tvmult: the transpose, not vmult, for the (unsymmetric) advection operators."""
+    import gdm_b200 as g
+    gs, gc, os_, oc = make_pair(dim, p, 1, reps, bc)
+    b = [1.0, 0.15, -0.05][:dim]
+    A = make_operator(gs, gc, kind, b=b)
+    Ao = oracle_operator(os_, oc, kind, b=b)
+    xh = np.random.default_rng(5).uniform(-1, 1, gs.n_dofs())
+    x, y = g.Vector(gs, xh), g.Vector(gs)
+    A.Tvmult(y, x)
+    ref = Ao.T @ xh
+    assert rel_err(y.numpy(), ref) <= 1e-12
+    A.vmult(y, x)
+    assert rel_err(y.numpy(), Ao @ xh) <= 1e-12

@@ -20,6 +20,11 @@ FUSED_CASES = [
     (5, [35, 29, 14], "dirichlet"),
     (5, [13, 12, 27], "none"),
     (3, [8, 8, 8], "dirichlet"),
+    # periodic directions (fold . A . duplicate): all three, and Dirichlet in x with periodic y, z
+    (3, [35, 33, 20], "periodic"),
+    (5, [34, 29, 31], "periodic"),
+    (1, [33, 12, 9], "periodic"),
+    (3, [40, 36, 17], "mixed"),
 ]
 
 
@@ -57,6 +62,8 @@ def test_auto_picks_fused_and_falls_back(lib):
     gs, gc, _, _ = make_pair(3, 3, 1, [12, 12, 12], "dirichlet")
     assert make_operator(gs, gc, "stiffness").kernel_used() == g.capi.KERNEL_FUSED
     gs, gc, _, _ = make_pair(3, 3, 1, [12, 12, 12], "periodic")
+    assert make_operator(gs, gc, "stiffness").kernel_used() == g.capi.KERNEL_FUSED
+    gs, gc, _, _ = make_pair(3, 3, 2, [12, 12, 12], "dirichlet")  # two components: generic passes
     assert make_operator(gs, gc, "stiffness").kernel_used() == g.capi.KERNEL_GENERIC
     with pytest.raises(g.ExcNotImplemented):
         make_operator(gs, gc, "stiffness", kernel=g.capi.KERNEL_FUSED)

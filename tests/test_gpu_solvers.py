@@ -174,3 +174,150 @@ def test_advection_rk4_matches_oracle(lib):
         time.advance_time()
     assert iters == oiters
     assert rel_err(sol.numpy(), uo) <= 1e-10
+
+
+def _poisson3d_rhs(g, gs, gc):
+    """b_i = int phi_i over the unit cube (= M 1 because the GDM basis is a partition of unity), zero on constrained rows."""
+    free = g.AffineConstraints()
+    free.close()
+    M = g.SparseMatrix()
+    g.MatrixCreator.create_mass_matrix(g.MappingQ1(), gs, g.QGauss(gs.fe_degree + 1), M, free)
+    ones, b = g.Vector(gs), g.Vector(gs)
+    ones.set(1.0)
+    M.vmult(b, ones)
+    gc.set_zero(b)
+    return b
+
+
+@pytest.mark.parametrize("N", [16, 32, 64, 128, 256])
+@pytest.mark.parametrize("pre", ["identity", "jacobi"])
+def test_cg_poisson3d_golden_counts(lib, N, pre):
+    """SURVEY 8d CG: -Laplace u = 1, ReductionControl(10000, 1e-10, 1e-8); iteration counts, residuals and the
+    solution's maximum against the oracle's converged solves (tests/golden/cg_poisson3d.json, made by
+    tests/golden/make_cg_golden.py; 256^3 = BASELINE config 2).  Reference call site: tests/poisson_02_gdm.cc:213-215."""
+    import json
+    import os
+    import gdm_b200 as g
+    gold = [r for r in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cg_poisson3d.json")))
+            if r["N"] == N and r["p"] == 3 and r["precondition"] == pre][0]
+    gs, gc, _, _ = make_pair(3, 3, 1, [N, N, N], "dirichlet", hi=[1.0, 1.0, 1.0])
+    A = make_operator(gs, gc, "stiffness")
+    b = _poisson3d_rhs(g, gs, gc)
+    u = g.Vector(gs)
+    ctl = g.ReductionControl(10000, 1e-10, 1e-8)
+    if pre == "identity":
+        P = g.PreconditionIdentity()
+    else:
+        P = g.PreconditionJacobi()
+        P.initialize(A)
+    g.SolverCG(ctl).solve(A, u, b, P)
+    assert abs(ctl.initial_value() - gold["initial_residual"]) <= 1e-12 * gold["initial_residual"]
+    # the stopping test compares a residual norm of ~1e-10 with the tolerance: rounding may move the count by one
+    assert abs(ctl.last_step() - gold["iterations"]) <= 1, (ctl.last_step(), gold["iterations"])
+    if ctl.last_step() == gold["iterations"]:
+        assert abs(ctl.last_value() - gold["final_residual"]) <= 5e-2 * gold["final_residual"]
+    assert abs(u.linfty_norm() - gold["u_max"]) <= 1e-8 * gold["u_max"]
+
+
+def test_advection_rk4_3d_periodic_fused(lib):
+    """BASELINE config 3 at a small size: 3D periodic p=5 advection, RK4, Jacobi-CG mass solves (app setting
+    (1000, 1e-20, 1e-14) is unreachable in a few steps at this size: prototype setting (100, 1e-10, 1e-8)); fused
+    kernel for both operators; per-stage CG counts identical to the oracle (prototypes/advection_01_gdm.cc:144-224,268-281)."""
+    import gdm_b200 as g
+    n, p = 12, 5
+    b = [1.0, 0.15, -0.05]
+    gs, gc, os_, oc = make_pair(3, p, 1, [n, n, n], "periodic", hi=[1.0, 1.0, 1.0])
+    M = make_operator(gs, gc, "mass")
+    R = make_operator(gs, gc, "advection", b=b, scale=-1.0)
+    assert M.kernel_used() == g.capi.KERNEL_FUSED and R.kernel_used() == g.capi.KERNEL_FUSED
+    Mo = oracle_operator(os_, oc, "mass")
+    Ro = oracle_operator(os_, oc, "advection", b=b, scale=-1.0)
+    u0 = lambda pts, c: np.sin(2 * np.pi * pts[:, 0]) * np.cos(2 * np.pi * pts[:, 1]) * np.cos(2 * np.pi * pts[:, 2])
+    uh = O.interpolate(os_, u0)
+    sol = g.Vector(gs, uh)
+    pre = g.PreconditionJacobi()
+    pre.initialize(M)
+    tmp0, tmp1 = g.Vector(gs), g.Vector(gs)
+    iters, oiters = [], []
+
+    def f(t, y, out):
+        tmp0.equ(y)
+        gc.distribute(tmp0)
+        R.vmult(tmp1, tmp0)
+        out.set(0.0)
+        ctl = g.ReductionControl(100, 1e-10, 1e-8)
+        g.SolverCG(ctl).solve(M, out, tmp1, pre)
+        iters.append(ctl.last_step())
+
+    def fo(t, y):
+        v0 = oc.distribute(y.copy())
+        ctl = O.ReductionControl(100, 1e-10, 1e-8)
+        out = O.solver_cg(Mo, np.zeros_like(y), Ro @ v0, O.PreconditionJacobi(Mo), ctl)
+        oiters.append(ctl.last_step())
+        return out
+
+    rk, rko = g.TimeStepping.ExplicitRungeKutta(g.TimeStepping.RK_CLASSIC_FOURTH_ORDER), O.ExplicitRungeKutta4()
+    dt = 0.5 / n
+    uo, t = uh.copy(), 0.0
+    for step in range(3):
+        rk.evolve_one_time_step(f, t, dt, sol)
+        gc.distribute(sol)
+        t, uo = rko.evolve_one_time_step(fo, t, dt, uo)
+        oc.distribute(uo)
+    assert iters == oiters
+    assert rel_err(sol.numpy(), uo) <= 1e-10
+
+
+@pytest.mark.parametrize("dim,reps", [(2, [14, 13]), (3, [12, 12, 13])])
+def test_wave_rk4_block_system(lib, dim, reps):
+    """BASELINE config 4 (applications/wave wave-rk, uncut): u_tt = Laplace u as the first-order block system
+    [u; v]' = [v; M^-1(-K u)] (applications/wave/include/gdm/wave/problem.h:294-320), RK4 over TWO blocks
+    (problem.h:330-345), Jacobi-CG mass solves; solution and per-stage CG counts against the oracle."""
+    import gdm_b200 as g
+    p = 3
+    gs, gc, os_, oc = make_pair(dim, p, 1, reps, "dirichlet", hi=[1.0] * dim)
+    M = make_operator(gs, gc, "mass")
+    K = make_operator(gs, gc, "stiffness")
+    Mo, Ko = oracle_operator(os_, oc, "mass"), oracle_operator(os_, oc, "stiffness")
+    u0 = lambda pts, c: np.prod(np.sin(np.pi * pts), axis=1)
+    uh = O.interpolate(os_, u0)
+    oc.set_zero(uh)
+    n = len(uh)
+    u, v = g.Vector(gs, uh), g.Vector(gs)
+    pre = g.PreconditionJacobi()
+    pre.initialize(M)
+    rhs = g.Vector(gs)
+    iters, oiters = [], []
+
+    def f(t, y, out):
+        out[0].equ(y[1])                    # u' = v
+        K.vmult(rhs, y[0])
+        rhs.scale(-1.0)
+        gc.set_zero(rhs)
+        out[1].set(0.0)
+        ctl = g.ReductionControl(100, 1e-10, 1e-8)
+        g.SolverCG(ctl).solve(M, out[1], rhs, pre)   # v' = M^-1 (-K u)
+        iters.append(ctl.last_step())
+
+    def fo(t, y):
+        uu, vv = y[:n], y[n:]
+        r = -(Ko @ uu)
+        oc.set_zero(r)
+        ctl = O.ReductionControl(100, 1e-10, 1e-8)
+        dv = O.solver_cg(Mo, np.zeros(n), r, O.PreconditionJacobi(Mo), ctl)
+        oiters.append(ctl.last_step())
+        return np.concatenate([vv, dv])
+
+    rk, rko = g.TimeStepping.ExplicitRungeKutta(g.TimeStepping.RK_CLASSIC_FOURTH_ORDER), O.ExplicitRungeKutta4()
+    dt = 0.3 / max(reps)
+    yo, t = np.concatenate([uh, np.zeros(n)]), 0.0
+    for step in range(4):
+        rk.evolve_one_time_step(f, t, dt, [u, v])
+        t, yo = rko.evolve_one_time_step(fo, t, dt, yo)
+    assert iters == oiters
+    assert rel_err(u.numpy(), yo[:n]) <= 1e-10
+    assert np.abs(v.numpy() - yo[n:]).max() <= 1e-9 * max(np.abs(yo[n:]).max(), 1e-300)
+    # energy 1/2 (v.Mv + u.Ku) is conserved by the exact flow; RK4 keeps it to O(dt^4) per step
+    E0 = 0.5 * float(uh @ (Ko @ uh))
+    E1 = 0.5 * float(yo[n:] @ (Mo @ yo[n:]) + yo[:n] @ (Ko @ yo[:n]))
+    assert abs(E1 - E0) <= 1e-3 * E0

@@ -12,12 +12,13 @@ import pytest
 MAXJ = 8  # not a limit of the kernel (jobs are read from global memory); keeps shares compact
 
 
-def partition(lib, tx, ty, k0, k1, slots, min_len, aligned):
+def partition(lib, tx, ty, k0, k1, slots, min_len, aligned, weights=None):
     cap_p, cap_j = 8192, 16384
+    w = None if weights is None else (C.c_int32 * len(weights))(*[int(v) for v in weights])
     ptr = (C.c_int32 * cap_p)()
     jobs = (C.c_int32 * (6 * cap_j))()
     ns, nj = C.c_int32(), C.c_int32()
-    rc = lib.gdm_pers_partition(tx, ty, k0, k1, slots, min_len, aligned, ptr, cap_p, jobs, cap_j, C.byref(ns), C.byref(nj))
+    rc = lib.gdm_pers_partition(tx, ty, k0, k1, slots, min_len, aligned, w, ptr, cap_p, jobs, cap_j, C.byref(ns), C.byref(nj))
     assert rc == 0, lib.gdm_last_error()
     return np.array(ptr[: ns.value + 1]), np.array(jobs[: 6 * nj.value]).reshape(-1, 6)
 
@@ -41,13 +42,25 @@ CASES = [
 ]
 
 
+def edge_weights(tx, ty, wx=1390, wy=1330, wxy=1480):
+    w = np.full((ty, tx), 1000)
+    w[:, [0, -1]] = wx
+    w[[0, -1], :] = wy
+    for j in (0, -1):
+        for i in (0, -1):
+            w[j, i] = wxy
+    return w.reshape(-1)
+
+
 @pytest.mark.parametrize("tx,ty,k0,k1,slots,p,aligned", CASES)
-def test_partition(lib, tx, ty, k0, k1, slots, p, aligned):
+@pytest.mark.parametrize("weighted", [False, True])
+def test_partition(lib, tx, ty, k0, k1, slots, p, aligned, weighted):
     min_len = 2 * p
-    ptr, jobs = partition(lib, tx, ty, k0, k1, slots, min_len, aligned)
+    wts = edge_weights(tx, ty) if weighted else np.full(tx * ty, 1000)
+    ptr, jobs = partition(lib, tx, ty, k0, k1, slots, min_len, aligned, wts if weighted else None)
     n_shares = len(ptr) - 1
     assert 1 <= n_shares <= slots
-    assert ptr[0] == 0 and ptr[-1] == len(jobs) and np.all(np.diff(ptr) >= 1) and np.all(np.diff(ptr) <= MAXJ)
+    assert ptr[0] == 0 and ptr[-1] == len(jobs) and np.all(np.diff(ptr) >= 1) and np.all(np.diff(ptr) <= MAXJ + 8)
     cover = np.zeros((tx * ty, k1 - k0), dtype=int)
     share_of = np.repeat(np.arange(n_shares), np.diff(ptr))
     start = {}
@@ -67,7 +80,8 @@ def test_partition(lib, tx, ty, k0, k1, slots, p, aligned):
             assert share_of[hi] > share_of[j]           # only waits for a share that took its ticket earlier
         else:
             assert hi == -1
-    planes = np.array([sum(jobs[j][3] - jobs[j][2] for j in range(ptr[w], ptr[w + 1])) for w in range(n_shares)])
-    ideal = tx * ty * (k1 - k0) / min(slots, max(1, tx * ty * (k1 - k0) // (2 * min_len)))
+    cost = np.array([sum((jobs[j][3] - jobs[j][2]) * wts[jobs[j][1] * tx + jobs[j][0]] for j in range(ptr[w], ptr[w + 1]))
+                     for w in range(n_shares)]) / 1000.0
+    ideal = wts.sum() / 1000.0 * (k1 - k0) / min(slots, max(1, tx * ty * (k1 - k0) // (2 * min_len)))
     if k1 - k0 >= 4 * min_len and slots >= tx * ty:
-        assert planes.max() <= 1.05 * ideal + min_len, (planes.max(), ideal)
+        assert cost.max() <= 1.06 * ideal + min_len, (cost.max(), ideal)
