@@ -335,6 +335,157 @@ def run_ours(args):
     emit(line)
 
 
+def run_app(args):
+    """BASELINE configs 3 and 4: explicit RK4 time stepping with a Jacobi-CG mass solve in every stage.
+
+    advection_rk4 (config 3, strong scaling): periodic [0,1]^3, `--cells` (512) cells per direction in total, p = `--p`
+    (5), b = (1, 0.15, -0.05), u0 = sin(2 pi x) cos(2 pi y) cos(2 pi z), dt = 0.5 h
+    (prototypes/advection_01_gdm.cc:33-52,79,144-224,268-281), slabs over the ranks.
+    wave_rk4 (config 4, weak scaling): u_tt = Laplace u on `--cells`^3 cells per GPU, zero Dirichlet, first-order system
+    [u; v]' = [v; M^-1(-K u)] (applications/wave/include/gdm/wave/problem.h:294-345), dt = 0.3 h.
+    Mass solves: ReductionControl(1000, 1e-20, 1e-14) (applications/wave/include/gdm/wave/parameters.h:41-44).
+    One "step" = one RK4 step (4 operator applies + 4 CG solves + stage updates).
+    """
+    import numpy as np
+    import torch
+    import gdm_b200 as g
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    ctx = g.init_distributed(local) if world > 1 else g.default_context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    adv = args.workload == "advection_rk4"
+    n, p = args.cells, args.p
+    reps = [n, n, n] if adv else [n, n, n * world]
+    hi = [1.0, 1.0, 1.0] if adv else [1.0, 1.0, float(world)]
+    sys_ = g.System(3, p, 1, comm="world" if world > 1 else None, context=ctx)
+    sys_.subdivided_hyper_rectangle(reps, [0.0, 0.0, 0.0], hi)
+    con = g.AffineConstraints()
+    if adv:
+        for d in range(3):
+            sys_.make_periodicity_constraints(d, con)
+    else:
+        sys_.make_zero_boundary_constraints(con)
+    con.close()
+    mp, q = g.MappingQ1(), g.QGauss(p + 1)
+    M = g.SparseMatrix()
+    g.MatrixCreator.create_mass_matrix(mp, sys_, q, M, con)
+    R = g.SparseMatrix()
+    bvec = [1.0, 0.15, -0.05]
+    if adv:
+        g.MatrixCreator.create_advection_matrix(mp, sys_, q, R, con, bvec, -1.0)
+    else:
+        g.MatrixCreator.create_laplace_matrix(mp, sys_, q, R, con)
+    own = sys_.locally_owned_dofs()
+    nx, ny = reps[0] + 1, reps[1] + 1
+    z0, z1 = own.start // (nx * ny), own.stop // (nx * ny)
+    h = 1.0 / n
+    X = np.arange(nx) * h
+    Y = np.arange(ny) * h
+    Z = np.arange(z0, z1) * h
+
+    def exact(t):
+        if adv:
+            return (np.cos(2 * np.pi * (Z - t * bvec[2]))[:, None, None] * np.cos(2 * np.pi * (Y - t * bvec[1]))[None, :, None] *
+                    np.sin(2 * np.pi * (X - t * bvec[0]))[None, None, :]).reshape(-1)
+        w = np.pi * np.sqrt(2.0 + 1.0 / world ** 2)  # standing wave of the box [0,1]^2 x [0,world]
+        return (np.sin(np.pi * Z / world)[:, None, None] * np.sin(np.pi * Y)[None, :, None] * np.sin(np.pi * X)[None, None, :]).reshape(-1) * np.cos(w * t)
+
+    u = g.Vector(sys_, exact(0.0))
+    v = g.Vector(sys_)
+    pre = g.PreconditionJacobi()
+    pre.initialize(M)
+    tmp0, tmp1 = g.Vector(sys_), g.Vector(sys_)
+    iters = []
+    max_it, tol, red = 1000, 1e-20, args.cg_reduce
+
+    def f_adv(t, y, out):
+        tmp0.equ(y)
+        con.distribute(tmp0)
+        R.vmult(tmp1, tmp0)
+        out.set(0.0)
+        ctl = g.ReductionControl(max_it, tol, red)
+        g.SolverCG(ctl).solve(M, out, tmp1, pre)
+        iters.append(ctl.last_step())
+
+    def f_wave(t, y, out):
+        out[0].equ(y[1])
+        R.vmult(tmp1, y[0])
+        tmp1.scale(-1.0)
+        con.set_zero(tmp1)
+        out[1].set(0.0)
+        ctl = g.ReductionControl(max_it, tol, red)
+        g.SolverCG(ctl).solve(M, out[1], tmp1, pre)
+        iters.append(ctl.last_step())
+
+    rk = g.TimeStepping.ExplicitRungeKutta(g.TimeStepping.RK_CLASSIC_FOURTH_ORDER)
+    dt = (0.5 if adv else 0.3) * h
+    state = u if adv else [u, v]
+    f = f_adv if adv else f_wave
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    t = 0.0
+    for _ in range(max(args.warmup, 1) if args.warmup < 3 else 3):
+        t = rk.evolve_one_time_step(f, t, dt, state)
+        if adv:
+            con.distribute(u)
+    iters.clear()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        t = rk.evolve_one_time_step(f, t, dt, state)
+        if adv:
+            con.distribute(u)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    n_owned = sys_.n_locally_owned_dofs()
+    err = float(np.abs(u.numpy() - exact(t)).max())
+    tt = torch.tensor([ms, err], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_owned)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(tot, op=torch.distributed.ReduceOp.SUM)
+    ms, err, total_dofs = float(tt[0].item()), float(tt[1].item()), float(tot.item())
+    if rank != 0:
+        return
+    peak, which = peaks()
+    n_it = float(np.mean(iters)) if iters else 0.0
+    # algorithmic bytes per RK step and DoF: 4 stages x (apply 16 + Jacobi-CG iterations x 96) + stage combinations
+    # (lincomb: read y and up to 4 k, write 1) ~ 4 x 24 + 48; the wave system adds the copy u' = v and the scale/zero passes
+    bytes_per_dof = 4 * (16 + n_it * 96) + 4 * 24 + 48 + (0 if adv else 4 * (16 + 16))
+    achieved = bytes_per_dof * (total_dofs / world) / (ms / args.steps * 1e-3) / 1e9
+    value = total_dofs * args.steps / (ms * 1e-3) / 1e9
+    line = {"metric": f"gdm_{args.workload}_3d_p{p}_fp64", "value": value, "unit": "GDoF-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": 3, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if adv else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": (f"advection u_t + b.grad u = 0, periodic [0,1]^3, {n}^3 cells p={p} ({int(total_dofs)} DoFs), RK4, dt=0.5h, "
+                                    f"Jacobi-CG mass solve ReductionControl({max_it},{tol:g},{red:g}) per stage" if adv else
+                                    f"wave u_tt = Laplace u as [u;v] block system, {n}x{n}x{n * world} cells p={p} ({int(total_dofs)} DoFs per block), "
+                                    f"zero Dirichlet, RK4, dt=0.3h, Jacobi-CG mass solve ReductionControl({max_it},{tol:g},{red:g}) per stage"),
+                       "parallelism": f"slab{world}", "kernel": "fused" if (M.kernel_used() == 2 and R.kernel_used() == 2) else "generic"},
+            "cg_iterations_per_stage": n_it, "cg_iterations_min_max": [int(min(iters)), int(max(iters))] if iters else None,
+            "nodal_linf_error_vs_exact": err, "t_end": t,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_dof_per_step": bytes_per_dof, "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)"},
+            "gpu_launches": int(launches), "clocks": clocks}
+    emit(line)
+
+
 _REAL_STDOUT = None
 
 
@@ -361,9 +512,21 @@ def main():
     ap.add_argument("--cpu-cells", type=int, default=96, help="grid of the bounded CPU sample")
     ap.add_argument("--cg-steps", type=int, default=50)
     ap.add_argument("--quick", action="store_true", help="timed applies only (for ncu captures)")
+    ap.add_argument("--workload", default="apply", choices=["apply", "advection_rk4", "wave_rk4"],
+                    help="apply (default, BASELINE config 2), advection_rk4 (config 3), wave_rk4 (config 4)")
+    ap.add_argument("--cg-reduce", type=float, default=1e-14, help="reduction of the mass solves of the RK workloads")
     args = ap.parse_args()
+    if args.workload != "apply":
+        if "--cells" not in sys.argv:
+            args.cells = 512 if args.workload == "advection_rk4" else 256
+        if "--p" not in sys.argv:
+            args.p = 5 if args.workload == "advection_rk4" else 3
+        if "--steps" not in sys.argv:
+            args.steps = 10
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "apply":
+        run_app(args)
     else:
         run_ours(args)
 

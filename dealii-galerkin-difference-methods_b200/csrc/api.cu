@@ -108,8 +108,9 @@ namespace gdm
   {
     cudaFree(d_row_off);
     cudaFree(d_rowptr);
-    cudaFree(d_col_off);
+    cudaFree(d_col_rel);
     cudaFree(d_val);
+    cudaFree(d_diag);
   }
 
   Operator::~Operator()
@@ -704,7 +705,7 @@ int gdm_pers_partition(int tiles_x, int tiles_y, int k0, int k1, int slots, int 
   GDM_ARG(n_shares);
   GDM_ARG(n_jobs);
   std::vector<int> ptr, jobs;
-  pers_partition_host(tiles_x, tiles_y, k0, k1, slots, min_len, aligned != 0, weights, ptr, jobs);
+  pers_partition_host(tiles_x, tiles_y, k0, k1, slots, min_len, aligned, weights, ptr, jobs);
   *n_shares = (int32_t)ptr.size() - 1;
   *n_jobs   = (int32_t)(jobs.size() / 6);
   GDM_REQUIRE(job_ptr != nullptr && jobs6 != nullptr && cap_ptr >= (int32_t)ptr.size() && cap_jobs >= *n_jobs, GDM_ERR_INVALID,
@@ -1126,8 +1127,18 @@ int gdm_operator_attach_csr(gdm_operator_t op, uint64_t n_rows, const uint64_t *
     {
       GDM_ARG(row_ids);
       GDM_ARG(rowptr);
+      GDM_REQUIRE(rowptr[0] == 0, GDM_ERR_INVALID, "CSR rowptr must start at 0");
+      for (uint64_t i = 0; i < n_rows; ++i)
+        GDM_REQUIRE(rowptr[i + 1] >= rowptr[i], GDM_ERR_INVALID, "CSR rowptr must be non-decreasing");
       csr->nnz = (int64_t)rowptr[n_rows];
-      std::vector<int64_t> row_off(n_rows), rp(n_rows + 1), col_off(csr->nnz);
+      if (csr->nnz > 0)
+        {
+          GDM_ARG(col);
+          GDM_ARG(val);
+        }
+      std::vector<int64_t> row_off(n_rows), rp(n_rows + 1);
+      std::vector<int32_t> col_rel(csr->nnz);
+      std::vector<double>  diag(n_rows, 0.0);
       uint64_t own_b, own_e;
       gdm_system_locally_owned_range(reinterpret_cast<gdm_system_t>(op->impl.sys), &own_b, &own_e);
       for (uint64_t i = 0; i < n_rows; ++i)
@@ -1135,18 +1146,26 @@ int gdm_operator_attach_csr(gdm_operator_t op, uint64_t n_rows, const uint64_t *
           GDM_REQUIRE(row_ids[i] >= own_b && row_ids[i] < own_e, GDM_ERR_INVALID, "CSR row is not locally owned");
           row_off[i] = storage_offset(L, row_ids[i]);
           rp[i]      = (int64_t)rowptr[i];
+          for (uint64_t j = rowptr[i]; j < rowptr[i + 1]; ++j)
+            {
+              // columns must be stored on this rank (owned or ghost planes); the offset relative to the row fits 32 bits
+              const int64_t rel = storage_offset(L, col[j]) - row_off[i];
+              GDM_REQUIRE(rel >= INT32_MIN && rel <= INT32_MAX, GDM_ERR_INVALID, "CSR column too far from its row");
+              col_rel[j] = (int32_t)rel;
+              if (col[j] == row_ids[i])
+                diag[i] += val[j];
+            }
         }
       rp[n_rows] = csr->nnz;
-      for (int64_t i = 0; i < csr->nnz; ++i)
-        col_off[i] = storage_offset(L, col[i]);
       auto up = [&](auto *&dptr, const void *h, size_t bytes) {
         GDM_CUDA_CHECK(cudaMalloc(&dptr, std::max<size_t>(bytes, 8)));
         GDM_CUDA_CHECK(cudaMemcpy(dptr, h, bytes, cudaMemcpyHostToDevice));
       };
       up(csr->d_row_off, row_off.data(), row_off.size() * 8);
       up(csr->d_rowptr, rp.data(), rp.size() * 8);
-      up(csr->d_col_off, col_off.data(), col_off.size() * 8);
+      up(csr->d_col_rel, col_rel.data(), col_rel.size() * 4);
       up(csr->d_val, val, (size_t)csr->nnz * 8);
+      up(csr->d_diag, diag.data(), diag.size() * 8);
     }
   op->impl.csr = std::move(csr);
   GDM_CATCH
@@ -1285,7 +1304,6 @@ int gdm_operator_diagonal(gdm_operator_t op, gdm_vector_t diag)
   GDM_ARG(op);
   GDM_ARG(diag);
   GDM_REQUIRE(diag->impl.sys == op->impl.sys, GDM_ERR_INVALID, "vector/operator system mismatch");
-  GDM_REQUIRE(!op->impl.csr, GDM_ERR_NOT_IMPLEMENTED, "diagonal of an operator with CSR overlay rows");
   System  &sys = *op->impl.sys;
   Context &ctx = *sys.ctx;
   launch_diagonal(ctx, sys.L, op->impl, diag->impl.d);
@@ -1295,6 +1313,8 @@ int gdm_operator_diagonal(gdm_operator_t op, gdm_vector_t diag)
       blas_set(ctx, ctx.scratch[0], sys.L.size, 1.0);
       launch_constrained_rows(ctx, sys.L, op->impl, diag->impl.d, ctx.scratch[0], true);
     }
+  if (op->impl.csr) // irregular rows replace the tensor-product rows: so do their diagonal entries
+    launch_csr_diagonal(ctx, *op->impl.csr, diag->impl.d);
   GDM_CATCH
 }
 

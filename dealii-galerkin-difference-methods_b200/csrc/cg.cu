@@ -66,7 +66,6 @@ namespace gdm
     if (precondition == GDM_PRECONDITION_JACOBI)
       {
         w.dinv = ctx.acquire((size_t)L.size);
-        GDM_REQUIRE(!A.csr, GDM_ERR_NOT_IMPLEMENTED, "Jacobi with CSR overlay rows: pass the diagonal with GDM_PRECONDITION_DIAGONAL");
         launch_diagonal(ctx, L, A, w.dinv);
         if (A.desc.constrained_diagonal == GDM_DIAG_ASSEMBLED)
           {
@@ -74,6 +73,8 @@ namespace gdm
             blas_set(ctx, ctx.scratch[0], L.size, 1.0);
             launch_constrained_rows(ctx, L, A, w.dinv, ctx.scratch[0], true);
           }
+        if (A.csr)
+          launch_csr_diagonal(ctx, *A.csr, w.dinv);
         blas_invert(ctx, w.dinv + off, n);
         dinv = w.dinv + off;
       }
@@ -147,7 +148,7 @@ namespace gdm
                                 cg_rz_slot(it), it, ctl.max_steps, ctl.tolerance);
           }
         cg_status_read(ctx, status.p, done, last_step, last_value, initial);
-        batch = std::min(batch * 2, 64u);
+        batch = std::min(batch * 2, 16u); // at most 15 applies are enqueued behind a converged state (they are no-ops)
       }
     ctl.last_step     = last_step;
     ctl.last_value    = last_value;

@@ -158,8 +158,9 @@ namespace gdm
     int64_t  n_rows = 0, nnz = 0;
     int64_t *d_row_off = nullptr; // storage offset of each irregular row
     int64_t *d_rowptr = nullptr;
-    int64_t *d_col_off = nullptr; // storage offsets of the columns
+    int32_t *d_col_rel = nullptr; // storage offset of a column relative to its row (12 B per nonzero with the value)
     double  *d_val = nullptr;
+    double  *d_diag = nullptr;    // diagonal entry of each irregular row (Jacobi)
     ~CsrOverlay();
   };
 
@@ -215,6 +216,8 @@ namespace gdm
   int  constrained_rows_max_blocks(const Layout &L);
   void launch_csr_overlay(Context &ctx, const CsrOverlay &csr, double *dst, const double *src,
                           bool accumulate);
+  // diag[row] = diagonal entry of the irregular rows (after launch_diagonal of the tensor-product part)
+  void launch_csr_diagonal(Context &ctx, const CsrOverlay &csr, double *diag);
   void launch_periodic_copy(Context &ctx, const Layout &L, const bool periodic[3], double *v);
   void launch_set_constrained(Context &ctx, const Layout &L, const bool dirichlet[3][2],
                               const bool periodic[3], double *v, double value);
@@ -246,16 +249,18 @@ namespace gdm
   int   pers_max_grid(const Operator &op, const void *plan);
   // output planes [oz0, oz1) (local indices); dot_partials != nullptr: CTA w leaves its share of <dot_src, A src> in
   // dot_partials[w]; returns the number of CTAs launched
+  // slots_limit > 0: use at most that many CTAs (launches that share the GPU: slab faces beside the interior planes)
   int   pers_launch(Operator &op, void *plan, double *dst, const double *src, bool accumulate, int oz0, int oz1, cudaStream_t stream,
-                    const double *dot_src, double *dot_partials);
+                    const double *dot_src, double *dot_partials, int slots_limit = 0);
   int   pers_error_flag(void *plan);
   // periodic directions of the persistent path (C^T A C = fold . A . duplicate): pre patches src in place (node N := node 0,
   // old values saved), post folds dst (row 0 += row N) and restores src.  No-ops without periodic directions.
   bool  pers_has_periodic(const void *plan);
   void  pers_periodic_pre(Operator &op, void *plan, double *src, cudaStream_t stream);
   void  pers_periodic_post(Operator &op, void *plan, double *dst, double *src, cudaStream_t stream);
-  void  pers_partition_host(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, bool aligned, const int *weights,
-                            std::vector<int> &job_ptr, std::vector<int> &jobs6);
+  // mode 0: tile-major sweep, 1: aligned chunks + sweep (one share per CTA, weighted), 2: guided levels (self-scheduling)
+  void  pers_partition_host(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, int mode, const int *weights,
+                            std::vector<int> &job_ptr, std::vector<int> &jobs6, double guide_k = 1.0, int guide_min = 8);
 
   // blas1.cu
   enum SumSlot

@@ -366,25 +366,40 @@ namespace gdm
         }
     }
 
-    __global__ void csr_overlay_kernel(int64_t n_rows, const int64_t *row_off, const int64_t *rowptr,
-                                       const int64_t *col_off, const double *val, double *dst,
-                                       const double *src, int accumulate)
+    // irregular rows (cut cells, ghost penalty, Nitsche): one warp per row, 12 B per nonzero (value + 32-bit storage
+    // offset of the column relative to the row) + 16 B per row
+    __global__ void csr_overlay_kernel(int64_t n_rows, const int64_t *__restrict__ row_off, const int64_t *__restrict__ rowptr,
+                                       const int32_t *__restrict__ col_rel, const double *__restrict__ val, double *dst,
+                                       const double *__restrict__ src, int accumulate)
     {
       const int     lane = threadIdx.x & 31;
       const int64_t row  = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
       if (row >= n_rows)
         return;
-      double        acc = 0.0;
+      const int64_t off = row_off[row];
+      const double *s   = src + off;
+      double        acc = 0.0, acc2 = 0.0;
       const int64_t b = rowptr[row], e = rowptr[row + 1];
-      for (int64_t i = b + lane; i < e; i += 32)
-        acc = fma(val[i], src[col_off[i]], acc);
+      int64_t       i = b + lane;
+      for (; i + 32 < e; i += 64)
+        {
+          acc  = fma(val[i], s[col_rel[i]], acc);
+          acc2 = fma(val[i + 32], s[col_rel[i + 32]], acc2);
+        }
+      if (i < e)
+        acc = fma(val[i], s[col_rel[i]], acc);
+      acc += acc2;
       for (int o = 16; o > 0; o >>= 1)
         acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0)
-        {
-          const int64_t off = row_off[row];
-          dst[off]          = accumulate ? dst[off] + acc : acc;
-        }
+        dst[off] = accumulate ? dst[off] + acc : acc;
+    }
+
+    __global__ void csr_diagonal_kernel(int64_t n_rows, const int64_t *row_off, const double *d, double *diag)
+    {
+      const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (row < n_rows)
+        diag[row_off[row]] = d[row];
     }
 
     struct SetFaceK
@@ -646,8 +661,18 @@ namespace gdm
     const int     th     = 128;
     const int64_t blocks = (csr.n_rows * 32 + th - 1) / th;
     csr_overlay_kernel<<<(unsigned)blocks, th, 0, ctx.stream>>>(csr.n_rows, csr.d_row_off, csr.d_rowptr,
-                                                                csr.d_col_off, csr.d_val, dst, src,
+                                                                csr.d_col_rel, csr.d_val, dst, src,
                                                                 accumulate ? 1 : 0);
+    ctx.launches++;
+    GDM_CUDA_CHECK(cudaGetLastError());
+  }
+
+  void launch_csr_diagonal(Context &ctx, const CsrOverlay &csr, double *diag)
+  {
+    if (csr.n_rows == 0)
+      return;
+    const int th = 128;
+    csr_diagonal_kernel<<<(unsigned)((csr.n_rows + th - 1) / th), th, 0, ctx.stream>>>(csr.n_rows, csr.d_row_off, csr.d_diag, diag);
     ctx.launches++;
     GDM_CUDA_CHECK(cudaGetLastError());
   }

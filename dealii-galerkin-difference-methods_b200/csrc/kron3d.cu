@@ -993,6 +993,7 @@ namespace gdm
     struct FusedPlan
     {
       void    *pers = nullptr; // persistent ramp-free kernel (kron3d_pers.cu); used for every launch when set
+      int      slots_limit = 0; // persistent kernel: CTAs of the next launch (0: all slots)
       int      cfg = 0;     // index into GDM_FUSED_CONFIGS
       int      tiles_x = 0, tiles_y = 0, n_chunks = 0, lz = 0;
       int      cx0, cx1, cy0, cy1, cz0, cz1, xorg;
@@ -1715,7 +1716,7 @@ namespace gdm
         dp = plan.d_dot + plan.dot_cursor;
       }
     const int grid = pers_launch(op, plan.pers, dst, src, accumulate, z0, z1, plan.use_comm_stream ? ctx.comm_stream : ctx.stream,
-                                 dp ? plan.dot_src : nullptr, dp);
+                                 dp ? plan.dot_src : nullptr, dp, plan.slots_limit);
     if (dp)
       plan.dot_cursor += grid;
   }
@@ -1873,8 +1874,21 @@ namespace gdm
         comm_halo_exchange(ctx, L, const_cast<double *>(src), ctx.comm_stream);
         if (thick)
           {
-            // slab faces: behind the ghost import on the comm stream, concurrent with the interior planes
+            // slab faces: behind the ghost import on the comm stream, concurrent with the interior planes.  Persistent
+            // kernel: the interior launch leaves a share of the CTA slots free (as many as the face planes' share of the
+            // work, and they start late by the latency of the exchange), so the face launches find room the moment the
+            // ghost planes arrive instead of queueing behind the interior CTAs.
+            int face_slots = 0, all_slots = 0;
+            if (plan.pers)
+              {
+                all_slots = pers_max_grid(op, plan.pers);
+                // face work: 2 windows x 3P input planes of (hi - lo) + 2P; +15 % for the late start
+                face_slots = std::max(4, (int)(1.15 * all_slots * (3.0 * P) / (double)((hi - lo) + 4 * P) + 0.5));
+                if (const char *env = std::getenv("GDM_PERS_FACE_SLOTS"))
+                  face_slots = std::max(1, atoi(env));
+              }
             plan.use_comm_stream = true;
+            plan.slots_limit     = face_slots;
             plan.wlz             = P;
             plan.wz0             = lo;
             plan.wz1             = lo + P;
@@ -1887,7 +1901,9 @@ namespace gdm
             plan.wz0 = lo + P;
             plan.wz1 = hi - P;
             plan.wlz = 0;
+            plan.slots_limit = plan.pers ? std::max(1, all_slots - 2 * face_slots) : 0;
             with_config(plan.cfg, [&](auto c) { dispatch<decltype(c)>(op, plan, dst, src, accumulate); });
+            plan.slots_limit = 0;
             plan.wz0 = plan.wz1 = -1;
             GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, ctx.ev_b, 0));
           }

@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <type_traits>
 
 #include "gdm_internal.h"
@@ -103,8 +104,9 @@ namespace gdm
       static constexpr int  NG_FULL  = NR / 32;
       static constexpr int  REM      = NR % 32;
       static constexpr int  NWT_FULL = NXB * NG_FULL;
-      static constexpr int  NLT      = REM * NXB; // left-over thread tasks
-      static constexpr int  NLW      = (NLT + 31) / 32;
+      static constexpr int  XPT      = (REM > 0) ? 32 / REM : 1;       // whole x blocks per left-over warp task
+      static constexpr int  NLW      = (REM > 0) ? (NXB + XPT - 1) / XPT : 0;
+      static constexpr int  XROT     = NW;                             // period of the task -> warp rotation (SPLIT)
       static constexpr int  NWT      = NWT_FULL + NLW;
       static constexpr int  NBT        = 2 * (P + 1);
       static constexpr int  WP         = 8 * ((W + 7) / 8);
@@ -135,7 +137,7 @@ namespace gdm
       int           nx, ny;                       // cells per direction (boundary rows: <= P or >= N-P)
       int           nz_local;
       int           kz_lo, kz_hi;                 // input planes [kz_lo, kz_hi) only touch Toeplitz z rows
-      int           grid;                         // number of shares
+      int           n_shares;                     // number of shares (>= grid: CTAs take shares until none is left)
       unsigned      ticket_base, epoch;
       const double *tabAx, *tabBx, *tabAy, *tabBy; // row tables [node][2P+1]
       double        Ax[P + 1], Bx[P + 1], Ay[P + 1], By[P + 1]; // interior taps by distance
@@ -149,6 +151,7 @@ namespace gdm
       double       *scratch; // [job][2P][TY][TX]
       int          *error;   // set if a seam wait timed out
       long long    *trace;   // diagnostic (GDM_PERS_TRACE): per share {clock cycles, SM id}
+      const unsigned short *xassign; // SPLIT: x tasks of warp w at plane q of tile t: xassign[(t * XROT + q % XROT) * NW + w] (bit mask)
       const double *dot_src; // fused dot product <src, A src>: every CTA writes its sum to dot_partials[share]
       double       *dot_partials;
     };
@@ -211,7 +214,17 @@ namespace gdm
         double *sp;        // scratch slot position of this thread
         int     k_scr;     // planes k < k_scr emit into the scratch slot
         int     x0_next;   // x origin of the job that follows
+        int     tile_next; // its tile index
       };
+
+      // x tasks of this warp for plane sequence number q of tile `tile` (SPLIT; bit mask made by the host)
+      __device__ __forceinline__ unsigned xm(const int tile, const int q) const
+      {
+        if constexpr (SPLIT)
+          return (unsigned)__ldg(g.xassign + ((size_t)tile * C::XROT + q % C::XROT) * C::NW + warp);
+        else
+          return 0u;
+      }
 
       __device__ __forceinline__ PersWorker(const ArgsP<P> &g_, const CUtensorMap *tmap_, double *smem_)
         : g(g_)
@@ -224,7 +237,7 @@ namespace gdm
         const int4 *q = reinterpret_cast<const int4 *>(g.jobs + j);
         const int4  a = __ldg(q), b = __ldg(q + 1);
         JobP        J;
-        J.x0 = a.x, J.y0 = a.y, J.k0 = a.z, J.k1 = a.w, J.seam_lo = b.x, J.seam_hi = b.y, J.pad0 = 0, J.pad1 = 0;
+        J.x0 = a.x, J.y0 = a.y, J.k0 = a.z, J.k1 = a.w, J.seam_lo = b.x, J.seam_hi = b.y, J.pad0 = b.z, J.pad1 = 0; // pad0: tile index
         return J;
       }
 
@@ -297,11 +310,11 @@ namespace gdm
           }
         else
           {
-            const int idx = (wt - C::NWT_FULL) * 32 + lane;
-            if (idx >= C::NLT)
+            const int sub = lane / C::REM; // (REM > 0 here)
+            xb            = (wt - C::NWT_FULL) * C::XPT + sub;
+            if (sub >= C::XPT || xb >= C::NXB)
               return;
-            xb = idx / C::REM;
-            r  = C::NG_FULL * 32 + idx % C::REM;
+            r = C::NG_FULL * 32 + lane % C::REM;
           }
         double v[RX + 2 * P];
         {
@@ -392,7 +405,7 @@ namespace gdm
       // counter (warp 0 issues the TMA loads instead)
       // x pass of plane sequence number q (waits for its TMA stage)
       template <bool FIX>
-      __device__ __forceinline__ void x_pass(const int q, const int x0)
+      __device__ __forceinline__ void x_pass(const int q, const int x0, [[maybe_unused]] const unsigned xmask = 0u)
       {
         const int st = stage_of(q);
         if constexpr (SPLIT)
@@ -400,7 +413,21 @@ namespace gdm
             mbar_wait(bar_empty(q), (unsigned)(q / NAB - 1) & 1u); // the y/z pass of plane q - NAB has released the buffer
         mbar_wait(bar0 + 8 * st, parity_of(q));
         const int in_off = st * C::STAGE_DOUBLES, a_off = ab_of(q);
-#pragma unroll
+        if constexpr (SPLIT)
+          {
+            // the task -> warp map of this tile and plane comes from a table made by the host (x_assignment): the warps that
+            // recompute one-sided rows in their y/z pass, or issue the TMA loads, get fewer x tasks, so that the warps of an
+            // edge tile carry about the same load (without the plane-wide barrier only the average load of a warp counts)
+            unsigned mask = xmask;
+            while (mask != 0u)
+              {
+                const int t = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                x_task<FIX>(t, in_off, a_off, x0);
+              }
+            warp_arrive(bar_full(q));
+            return;
+          }
         const int wrot = (warp >= XSHIFT) ? warp - XSHIFT : warp - XSHIFT + C::NW;
 #pragma unroll
         for (int rd = 0; rd < FULL_ROUNDS; ++rd)
@@ -581,7 +608,7 @@ namespace gdm
           {
             const bool last = (k + 1 == c.J.k1);
             if (!last || c.more)
-              x_pass<true>(seq, last ? c.x0_next : c.J.x0);
+              x_pass<true>(seq, last ? c.x0_next : c.J.x0, xm(last ? c.tile_next : c.J.pad0, seq));
             double res[RY];
             yz_acquire(seq - 1);
             yz_pass<true>(k >= g.kz_lo && k < g.kz_hi, k, ab_of(seq - 1), c.gy_first, res);
@@ -620,7 +647,7 @@ namespace gdm
       {
         for (int k = ka; k < kb; ++k)
           {
-            x_pass<!INNER>(seq, c.J.x0);
+            x_pass<!INNER>(seq, c.J.x0, xm(c.J.pad0, seq));
             double res[RY];
             yz_acquire(seq - 1);
             yz_rows<!INNER, true>(g.Az, g.Bz, ab_of(seq - 1), c.gy_first, res);
@@ -654,8 +681,6 @@ namespace gdm
             for (int s = 0; s < 2 * NAB; ++s)
               mbar_init(bar0 + 8 * (S + s), C::NW);
             mbar_fence_init();
-            const unsigned t = atomicAdd(g.ticket, 1u) - g.ticket_base;
-            smisc[0]         = g.grid - 1 - (int)t; // descending: a share only waits for shares with a larger index
           }
         // one-sided rows of A/B in x and y (row class c: node c for c <= P, node N-P+(c-P-1) above)
         for (int e = tid; e < 2 * 2 * NBT * W; e += C::THREADS)
@@ -668,17 +693,35 @@ namespace gdm
           }
         for (int e = tid; e < C::ZT_DOUBLES; e += C::THREADS)
           smem[OFF_ZT + e] = __ldg(g.zt + e);
+        // y/z pass ownership: lane -> x, warp -> RY consecutive rows
+        yz_off = lane * PY + warp * RY; // start of this thread's window in an a/r buffer
+#pragma unroll
+        for (int i = 0; i < RY; ++i)
+#pragma unroll
+          for (int j = 0; j < 2 * P; ++j)
+            acc[i][j] = 0.0;
+        dsum = 0.0;
+        seq  = 0;
+        // ---- shares are handed out by a ticket in DESCENDING order: a share only ever waits (at a seam) for a share with a
+        // larger index, i.e. one that was started before it -- no deadlock even when there are more shares than resident
+        // CTAs.  With the guided partition the shares that are handed out last are the short ones (no tail).
+        // The plane sequence number seq runs on across shares (TMA stages and a/r buffers keep their mbarrier phases).
+        for (;;)
+          {
+        __syncthreads(); // every warp is done with the previous share (and with the tables on the first pass)
+        if (tid == 0)
+          {
+            const unsigned t = atomicAdd(g.ticket, 1u) - g.ticket_base;
+            smisc[0]         = (t < (unsigned)g.n_shares) ? g.n_shares - 1 - (int)t : -1;
+          }
         __syncthreads();
         const int share = smisc[0];
-        jb              = __ldg(g.job_ptr + share);
-        njobs           = __ldg(g.job_ptr + share + 1) - jb;
+        if (share < 0)
+          break;
+        jb    = __ldg(g.job_ptr + share);
+        njobs = __ldg(g.job_ptr + share + 1) - jb;
         if (njobs <= 0)
-          {
-            if constexpr (DOT)
-              if (tid == 0)
-                g.dot_partials[share] = 0.0;
-            return;
-          }
+          continue;
         JobP Jn = load_job(jb); // next job of the compute loop (every thread); the issuer keeps its own cursor
         if (tid == ISSUE_TID)
           {
@@ -689,28 +732,18 @@ namespace gdm
             cur[3]   = Jn.y0 - P;
             cur[4]   = Jn.k1;
             for (int s = 0; s < S; ++s)
-              issue(s);
+              issue(stage_of(seq + s));
           }
 
-        // y/z pass ownership: lane -> x, warp -> RY consecutive rows
-        yz_off = lane * PY + warp * RY; // start of this thread's window in an a/r buffer
-#pragma unroll
-        for (int i = 0; i < RY; ++i)
-#pragma unroll
-          for (int j = 0; j < 2 * P; ++j)
-            acc[i][j] = 0.0;
-        dsum = 0.0;
-
         // prologue: x pass of the first plane of the first job
-        seq = 0;
-        x_pass<true>(0, Jn.x0);
+        x_pass<true>(seq, Jn.x0, xm(Jn.pad0, seq));
         if constexpr (!SPLIT)
           {
             __syncthreads();
             if (tid == ISSUE_TID)
-              issue(0);
+              issue(stage_of(seq));
           }
-        seq = 1;
+        ++seq;
 
         for (int j = 0; j < njobs; ++j)
           {
@@ -726,6 +759,7 @@ namespace gdm
             c.sp         = g.scratch + ((int64_t)max(c.J.seam_lo, 0) * (2 * P)) * (TY * TX) + (warp * RY) * TX + lane;
             c.k_scr      = (c.J.seam_lo >= 0) ? c.J.k0 + 2 * P : c.J.k0;
             c.x0_next    = Jn.x0;
+            c.tile_next  = Jn.pad0;
             const bool inner = c.J.x0 > P && c.J.x0 + TX - 1 < g.nx - P && c.J.y0 > P && c.J.y0 + TY - 1 < g.ny - P &&
                                c.J.x0 >= g.cx0 && c.J.x0 + TX <= g.cx1 && c.J.y0 >= g.cy0 && c.J.y0 + TY <= g.cy1;
             const int fa = max(max(c.J.k0, c.k_scr), max(g.cz0 + P, g.kz_lo));
@@ -784,12 +818,13 @@ namespace gdm
                 c.out += g.plane;
               }
           }
+          } // shares
         if (g.trace != nullptr && tid == 0)
           {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            g.trace[2 * share]     = clock64() - t_start;
-            g.trace[2 * share + 1] = (long long)smid;
+            g.trace[2 * blockIdx.x]     = clock64() - t_start;
+            g.trace[2 * blockIdx.x + 1] = (long long)smid;
           }
         if constexpr (DOT)
           {
@@ -805,7 +840,7 @@ namespace gdm
                 double t = 0.0;
                 for (int w = 0; w < C::NW; ++w)
                   t += smem[w];
-                g.dot_partials[share] = t;
+                g.dot_partials[blockIdx.x] = t;
               }
           }
       }
@@ -840,7 +875,7 @@ namespace gdm
 
     struct PartitionP // work partition of one output-plane window
     {
-      int       grid = 0, n_jobs = 0, n_seams = 0;
+      int       grid = 0, n_shares = 0, n_jobs = 0, n_seams = 0;
       JobP     *d_jobs = nullptr;
       int      *d_ptr  = nullptr;
       unsigned *d_sync = nullptr; // [0] ticket, [1] error, [2 ...] flags per job
@@ -865,11 +900,12 @@ namespace gdm
       std::vector<double> hAe[3], hBe[3];
       double  *d_Ae[2] = {nullptr, nullptr};
       double  *d_Be[2] = {nullptr, nullptr};
+      unsigned short *d_xassign = nullptr; // SPLIT configurations: x task masks [tile][rotation][warp]
       bool     periodic[3] = {false, false, false};
       double  *d_save = nullptr; // periodic: saved values of the patched nodes
       int64_t  n_save = 0;
       double  *d_zt    = nullptr;
-      std::map<std::pair<int, int>, PartitionP> parts;
+      std::map<std::tuple<int, int, int>, PartitionP> parts; // (first output plane, end, slots)
       std::map<const void *, CUtensorMap>        maps;
       std::map<std::pair<int, const void *>, bool> attr_set; // (device, kernel)
       ~PersPlan()
@@ -879,6 +915,7 @@ namespace gdm
         cudaFree(d_Be[0]);
         cudaFree(d_Be[1]);
         cudaFree(d_save);
+        cudaFree(d_xassign);
         cudaFree(d_zt);
         for (auto &kv : parts)
           free_part(kv.second);
@@ -895,27 +932,14 @@ namespace gdm
 
     //                    id   P  RY NW RX ST MINB
 #define GDM_PERS_CONFIGS_CORE(X)      \
-  X(800, CfgP<3, 4, 8, 4, 3, 2>)      \
   X(801, CfgP<1, 4, 8, 4, 3, 2>)      \
-  X(802, CfgP<5, 4, 8, 4, 3, 2>)
+  X(833, CfgP<3, 4, 6, 8, 4, 2, 1>)   \
+  X(836, CfgP<5, 4, 8, 4, 4, 1, 1>)
 #ifdef GDM_FUSED_EXPERIMENTAL
 #define GDM_PERS_CONFIGS_EXP(X)       \
-  X(810, CfgP<3, 4, 8, 8, 3, 2>)      \
-  X(811, CfgP<3, 4, 8, 4, 4, 2>)      \
-  X(812, CfgP<3, 8, 4, 8, 3, 2>)      \
-  X(813, CfgP<3, 8, 4, 8, 4, 3>)      \
-  X(814, CfgP<3, 8, 8, 8, 3, 1>)      \
-  X(815, CfgP<3, 2, 16, 4, 3, 1>)      \
-  X(820, CfgP<3, 4, 7, 4, 3, 2>)      \
-  X(821, CfgP<3, 4, 6, 4, 3, 2>)      \
-  X(822, CfgP<3, 4, 7, 4, 4, 2>)      \
-  X(823, CfgP<3, 6, 5, 4, 3, 2>)      \
-  X(824, CfgP<3, 4, 6, 8, 3, 2>)      \
+  X(800, CfgP<3, 4, 8, 4, 3, 2>)      \
   X(825, CfgP<3, 4, 6, 4, 4, 2>)      \
-  X(830, CfgP<3, 4, 8, 4, 4, 2, 1>)   \
-  X(831, CfgP<3, 4, 6, 4, 4, 2, 1>)   \
-  X(832, CfgP<3, 4, 6, 4, 3, 2, 1>)   \
-  X(833, CfgP<3, 4, 6, 8, 4, 2, 1>)
+  X(831, CfgP<3, 4, 6, 4, 4, 2, 1>)
 #else
 #define GDM_PERS_CONFIGS_EXP(X)
 #endif
@@ -939,7 +963,9 @@ namespace gdm
 
     int default_config(int p)
     {
-      int id = (p == 1) ? 801 : (p == 3 ? 800 : 802);
+      // defaults by measurement on B200 (profiles/r2): p=1 barrier per plane, 8 warps; p=3 split hand-over, 6 warps x 168
+      // registers, RX=8; p=5 split hand-over, one CTA of 8 warps x 255 registers per SM
+      int id = (p == 1) ? 801 : (p == 3 ? 833 : 836);
       if (const char *env = std::getenv("GDM_PERS_CFG"))
         {
           const int e  = atoi(env);
@@ -966,9 +992,14 @@ namespace gdm
   //   swept tile-major over the spare shares.  Otherwise: one tile-major sweep.
   // Output: job_ptr (size grid+1) and jobs as 6 ints {tile x, tile y, k_begin, k_end, seam_lo, seam_hi}; seam ids are job
   // indices.  A job's upper neighbour always lies in a share with a larger index (the kernel's ticket order relies on it).
-  void pers_partition_host(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, bool aligned, const int *weights,
-                           std::vector<int> &job_ptr, std::vector<int> &jobs6)
+  // mode 2 (guided): every column is cut at the same planes into levels whose length shrinks from the top of the column to
+  //   its bottom, length = planes left x tiles / (guide_k x slots), at least guide_min planes; one share per (tile, level),
+  //   bottom level first.  The kernel hands shares out from the last to the first, so the CTAs start on the long top levels
+  //   and finish on short ones: self-scheduling with a short tail, whatever the tiles cost.
+  void pers_partition_host(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, int mode, const int *weights,
+                           std::vector<int> &job_ptr, std::vector<int> &jobs6, double guide_k, int guide_min)
   {
+    const bool aligned = mode == 1;
     GDM_REQUIRE(tiles_x > 0 && tiles_y > 0 && k1 >= k0 && slots > 0 && min_len > 0, GDM_ERR_INVALID, "invalid partition request");
     struct Piece
     {
@@ -1096,7 +1127,39 @@ namespace gdm
     };
     Shares shares;
     const bool cuttable = nz >= 4 * min_len && slots >= tiles;
-    if (aligned && cuttable)
+    if (mode == 2)
+      {
+        std::vector<int> len; // level lengths from the top of the column down
+        int              left = nz;
+        const int        gmin = std::max(min_len, guide_min);
+        while (left > 0)
+          {
+            int l = (int)((double)left * tiles / (std::max(0.1, guide_k) * slots) + 0.5);
+            l     = std::max(l, gmin);
+            if (l >= left)
+              l = left;
+            else if (left - l < gmin)
+              {
+                // a remainder too short for a level of its own goes to the top level (handed out first)
+                const int rem = left - l;
+                if (len.empty())
+                  l += rem;
+                else
+                  len[0] += rem;
+                left -= len.empty() ? 0 : rem;
+              }
+            len.push_back(l);
+            left -= l;
+          }
+        int z = k0;
+        for (int i = (int)len.size() - 1; i >= 0; --i) // bottom level first
+          {
+            for (int t = 0; t < tiles; ++t)
+              shares.push_back({{t, z, z + len[i]}});
+            z += len[i];
+          }
+      }
+    else if (aligned && cuttable)
       {
         // search the chunk cost around the ideal share for the shortest longest share
         const double T0   = (double)total / (double)slots;
@@ -1148,9 +1211,9 @@ namespace gdm
   namespace
   {
     template <class C>
-    PartitionP &get_partition(Operator &op, PersPlan &plan, int oz0, int oz1)
+    PartitionP &get_partition(Operator &op, PersPlan &plan, int oz0, int oz1, int slots_limit)
     {
-      const auto key = std::make_pair(oz0, oz1);
+      const auto key = std::make_tuple(oz0, oz1, slots_limit);
       auto       it  = plan.parts.find(key);
       if (it != plan.parts.end())
         return it->second;
@@ -1167,6 +1230,8 @@ namespace gdm
       int           slots = ctx.sm_count * C::MINB;
       if (const char *env = std::getenv("GDM_PERS_SLOTS"))
         slots = std::max(1, atoi(env));
+      if (slots_limit > 0)
+        slots = std::min(slots, slots_limit);
       const int   min_len = 2 * P; // the shortest job that can hand its first 2P partial planes down
       const char *env_al  = std::getenv("GDM_PERS_ALIGNED");
       const bool  aligned = !(env_al && env_al[0] == '0');
@@ -1175,7 +1240,7 @@ namespace gdm
       // cost of a plane per tile (per mille of an interior tile): tiles that touch one-sided rows in x / y or store
       // partial rows run the general plane body and wait for the warps that recompute the boundary rows
       // (measured on B200, profiles/r2/pers_trace_*.txt).  GDM_PERS_WEIGHTS="x,y,xy" overrides (per mille).
-      int wx = 1390, wy = 1330, wxy = 1480;
+      int wx = 1250, wy = 1250, wxy = 1400;
       if (const char *env = std::getenv("GDM_PERS_WEIGHTS"))
         sscanf(env, "%d,%d,%d", &wx, &wy, &wxy);
       const Layout    &L = op.sys->L;
@@ -1189,9 +1254,18 @@ namespace gdm
             weights[(size_t)ty * plan.tiles_x + tx] = (xe && ye) ? wxy : (xe ? wx : (ye ? wy : 1000));
           }
       (void)env_L;
-      pers_partition_host(plan.tiles_x, plan.tiles_y, k0, std::max(k0, k1), slots, min_len, aligned, weights.data(), ptr, j6);
+      // partition mode: guided self-scheduling by default; GDM_PERS_MODE=static: one weighted share per CTA
+      int         mode   = 2;
+      double      gk     = 1.0;
+      int         gmin   = 8;
+      if (const char *env = std::getenv("GDM_PERS_MODE"))
+        mode = (env[0] == 's') ? (aligned ? 1 : 0) : 2;
+      if (const char *env = std::getenv("GDM_PERS_GUIDE"))
+        sscanf(env, "%lf,%d", &gk, &gmin);
+      pers_partition_host(plan.tiles_x, plan.tiles_y, k0, std::max(k0, k1), slots, min_len, mode, weights.data(), ptr, j6, gk, gmin);
       PartitionP part;
-      part.grid   = (int)ptr.size() - 1;
+      part.n_shares = (int)ptr.size() - 1;
+      part.grid     = std::min(part.n_shares, slots);
       part.n_jobs = (int)(j6.size() / 6);
       std::vector<JobP> jobs(part.n_jobs);
       for (int j = 0; j < part.n_jobs; ++j)
@@ -1202,14 +1276,15 @@ namespace gdm
           jobs[j].k1      = j6[6 * j + 3];
           jobs[j].seam_lo = j6[6 * j + 4];
           jobs[j].seam_hi = j6[6 * j + 5];
-          jobs[j].pad0 = jobs[j].pad1 = 0;
+          jobs[j].pad0 = j6[6 * j + 1] * plan.tiles_x + j6[6 * j + 0]; // tile index (x task assignment table)
+          jobs[j].pad1 = 0;
           if (jobs[j].seam_lo >= 0)
             {
               part.n_seams++;
               GDM_REQUIRE(jobs[j].k1 - jobs[j].k0 >= 2 * P, GDM_ERR_INTERNAL, "persistent partition: job shorter than a seam");
             }
         }
-      for (int w = 0; w < part.grid; ++w)
+      for (int w = 0; w < part.n_shares; ++w)
         {
           int64_t n = 0;
           for (int j = ptr[w]; j < ptr[w + 1]; ++j)
@@ -1236,7 +1311,7 @@ namespace gdm
         }
       if (std::getenv("GDM_FUSED_VERBOSE"))
         fprintf(stderr, "[gdm] persistent partition: outputs [%d, %d), inputs [%d, %d), %d x %d tiles -> %d shares, %d jobs, %d seams, longest share %lld planes\n",
-                oz0, oz1, k0, k1, plan.tiles_x, plan.tiles_y, part.grid, part.n_jobs, part.n_seams, (long long)part.max_planes);
+                oz0, oz1, k0, k1, plan.tiles_x, plan.tiles_y, part.n_shares, part.n_jobs, part.n_seams, (long long)part.max_planes);
       return plan.parts.emplace(key, part).first->second;
     }
 
@@ -1261,16 +1336,96 @@ namespace gdm
       return plan.maps.emplace(src, m).first->second;
     }
 
+    // x task -> warp assignment of every tile (SPLIT configurations): longest-processing-time greedy over a cost model in
+    // units of one full x task.  Loads before the x tasks: the y/z pass of every warp, the one-sided y rows recomputed by
+    // the warp that owns them, the TMA issue; an x task that contains one-sided columns costs more.  The interior pattern
+    // rotates with the plane counter so that the tasks left over after a full round visit every warp.
+    template <class C>
+    void build_x_assignment(const Operator &op, PersPlan &plan)
+    {
+      if (!C::SPLIT || plan.d_xassign)
+        return;
+      constexpr int P = C::P, NW = C::NW, R = C::XROT;
+      const Layout &L = op.sys->L;
+      double c_yz = 4.0, c_yfix_row = 0.85, c_xfix = 1.5, c_issue = 0.3;
+      if (const char *env = std::getenv("GDM_PERS_COSTS"))
+        sscanf(env, "%lf,%lf,%lf,%lf", &c_yz, &c_yfix_row, &c_xfix, &c_issue);
+      const int                   tiles = plan.tiles_x * plan.tiles_y;
+      std::vector<unsigned short> tab((size_t)tiles * R * NW, 0);
+      for (int ty = 0; ty < plan.tiles_y; ++ty)
+        for (int tx = 0; tx < plan.tiles_x; ++tx)
+          {
+            const int x0 = plan.xorg + tx * C::TX, y0 = plan.cy0 + ty * C::TY;
+            // task costs
+            double tc[C::NWT];
+            for (int t = 0; t < C::NWT; ++t)
+              {
+                int    xb0, xb1;
+                double fill = 1.0;
+                if (t < C::NWT_FULL)
+                  xb0 = t % C::NXB, xb1 = xb0 + 1;
+                else
+                  {
+                    xb0  = (t - C::NWT_FULL) * C::XPT;
+                    xb1  = std::min(C::NXB, xb0 + C::XPT);
+                    fill = std::max(0.25, (double)(xb1 - xb0) * C::REM / 32.0);
+                  }
+                bool fix = false;
+                for (int xb = xb0; xb < xb1; ++xb)
+                  {
+                    const int gx = x0 + xb * C::RX;
+                    fix |= (gx <= P || gx + C::RX - 1 >= L.N[0] - P);
+                  }
+                tc[t] = fill + (fix ? c_xfix : 0.0);
+              }
+            for (int r = 0; r < R; ++r)
+              {
+                double load[NW];
+                for (int w = 0; w < NW; ++w)
+                  {
+                    const int gy = y0 + w * C::RY;
+                    int       nfix = 0;
+                    for (int i = 0; i < C::RY; ++i)
+                      nfix += ((gy + i <= P || gy + i >= L.N[1] - P) && gy + i >= 0 && gy + i <= L.N[1]) ? 1 : 0;
+                    load[w] = c_yz + c_yfix_row * nfix + (w == NW / 2 ? c_issue : 0.0);
+                  }
+                // tasks by decreasing cost (stable), ties among warps broken starting at warp r (rotation)
+                int order[C::NWT];
+                for (int t = 0; t < C::NWT; ++t)
+                  order[t] = t;
+                std::stable_sort(order, order + C::NWT, [&](int a, int b) { return tc[a] > tc[b]; });
+                unsigned short mask[NW] = {};
+                for (int k = 0; k < C::NWT; ++k)
+                  {
+                    int best = -1;
+                    for (int i = 0; i < NW; ++i)
+                      {
+                        const int w = (r + i) % NW;
+                        if (best < 0 || load[w] < load[best] - 1e-9)
+                          best = w;
+                      }
+                    load[best] += tc[order[k]];
+                    mask[best] |= (unsigned short)(1u << order[k]);
+                  }
+                for (int w = 0; w < NW; ++w)
+                  tab[((size_t)(ty * plan.tiles_x + tx) * R + r) * NW + w] = mask[w];
+              }
+          }
+      GDM_CUDA_CHECK(cudaMalloc(&plan.d_xassign, tab.size() * sizeof(unsigned short)));
+      GDM_CUDA_CHECK(cudaMemcpy(plan.d_xassign, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    }
+
     template <class C, int MODE>
     int launch_p(Operator &op, PersPlan &plan, double *dst, const double *src, bool accumulate, int oz0, int oz1, cudaStream_t stream,
-                 const double *dot_src, double *dot_partials)
+                 const double *dot_src, double *dot_partials, int slots_limit)
     {
       constexpr int P = C::P, W = C::W;
       Context      &ctx = *op.sys->ctx;
       const Layout &L   = op.sys->L;
       if (oz1 <= oz0)
         return 0;
-      PartitionP &part = get_partition<C>(op, plan, oz0, oz1);
+      build_x_assignment<C>(op, plan);
+      PartitionP &part = get_partition<C>(op, plan, oz0, oz1, slots_limit);
       if (part.grid <= 0)
         return 0;
       ArgsP<P> a;
@@ -1288,7 +1443,7 @@ namespace gdm
       a.nz_local = L.ln[2];
       a.kz_lo    = plan.kz_lo;
       a.kz_hi    = plan.kz_hi;
-      a.grid     = part.grid;
+      a.n_shares = part.n_shares;
       a.tabAx    = plan.d_Ae[0];
       a.tabAy    = plan.d_Ae[1];
       a.tabBx    = plan.d_Be[0];
@@ -1302,6 +1457,7 @@ namespace gdm
       a.flags    = part.d_sync + 2;
       a.scratch  = part.d_scratch;
       a.trace    = part.d_trace;
+      a.xassign  = plan.d_xassign;
       a.dot_src  = dot_src;
       a.dot_partials = dot_partials;
       const std::vector<double> *hA = plan.hAe, *hB = plan.hBe;
@@ -1352,7 +1508,7 @@ namespace gdm
       part.epoch += 1;
       a.epoch       = part.epoch;
       a.ticket_base = part.ticket_base;
-      part.ticket_base += (unsigned)part.grid;
+      part.ticket_base += (unsigned)(part.n_shares + part.grid); // every CTA draws one ticket past the last share
       const CUtensorMap &map = get_map<C>(op, plan, src);
       kern<<<part.grid, C::THREADS, smem, stream>>>(map, a);
       ctx.launches++;
@@ -1364,16 +1520,9 @@ namespace gdm
           GDM_CUDA_CHECK(cudaMemcpy(t.data(), part.d_trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
           if (FILE *f = fopen(std::getenv("GDM_PERS_TRACE"), "w"))
             {
-              fprintf(f, "# share cycles smid planes jobs first_tile_x first_tile_y\n");
+              fprintf(f, "# cta cycles smid\n");
               for (int w = 0; w < part.grid; ++w)
-                {
-                  int n = 0;
-                  for (int j = part.h_ptr[w]; j < part.h_ptr[w + 1]; ++j)
-                    n += part.h_jobs[j].k1 - part.h_jobs[j].k0;
-                  const JobP &J = part.h_jobs[part.h_ptr[w]];
-                  fprintf(f, "%d %lld %lld %d %d %d %d\n", w, t[2 * w], t[2 * w + 1], n, part.h_ptr[w + 1] - part.h_ptr[w],
-                          (J.x0 - plan.xorg) / C::TX, (J.y0 - plan.cy0) / C::TY);
-                }
+                fprintf(f, "%d %lld %lld\n", w, t[2 * w], t[2 * w + 1]);
               fclose(f);
             }
         }
@@ -1776,7 +1925,7 @@ namespace gdm
 
   // output planes [oz0, oz1) (local indices, clipped to the plan's window); returns the number of CTAs launched
   int pers_launch(Operator &op, void *p, double *dst, const double *src, bool accumulate, int oz0, int oz1, cudaStream_t stream,
-                  const double *dot_src, double *dot_partials)
+                  const double *dot_src, double *dot_partials, int slots_limit)
   {
     PersPlan &plan = *static_cast<PersPlan *>(p);
     oz0            = std::max(oz0, plan.cz0);
@@ -1785,11 +1934,11 @@ namespace gdm
     with_config(plan.cfg, [&](auto c) {
       using C = decltype(c);
       if (plan.mode == 0)
-        grid = launch_p<C, 0>(op, plan, dst, src, accumulate, oz0, oz1, stream, dot_src, dot_partials);
+        grid = launch_p<C, 0>(op, plan, dst, src, accumulate, oz0, oz1, stream, dot_src, dot_partials, slots_limit);
       else if (plan.mode == 1)
-        grid = launch_p<C, 1>(op, plan, dst, src, accumulate, oz0, oz1, stream, dot_src, dot_partials);
+        grid = launch_p<C, 1>(op, plan, dst, src, accumulate, oz0, oz1, stream, dot_src, dot_partials, slots_limit);
       else
-        grid = launch_p<C, 2>(op, plan, dst, src, accumulate, oz0, oz1, stream, dot_src, dot_partials);
+        grid = launch_p<C, 2>(op, plan, dst, src, accumulate, oz0, oz1, stream, dot_src, dot_partials, slots_limit);
     });
     return grid;
   }

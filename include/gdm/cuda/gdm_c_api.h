@@ -136,14 +136,18 @@ int      gdm_fused_partition(int aligned, int tiles_x, int tiles_y, int z0, int 
                              int32_t *n_segs);
 
 /* Work partition of the persistent fused kernel (kron3d_pers.cu; host logic, no device needed): the input planes
- * [k0, k1) of a tiles_x x tiles_y tile grid are split into at most `slots` shares (one CTA each); share w runs jobs
- * [job_ptr[w], job_ptr[w+1]) of jobs6 = {tile x, tile y, k_begin, k_end, seam_lo, seam_hi} per job.  A job with
- * seam_lo >= 0 hands its first 2p partial output planes to the job below it through scratch slot seam_lo; seam_hi is
- * the slot a job reads when it flushes.  No job is shorter than min_len planes unless it is a whole column.
+ * [k0, k1) of a tiles_x x tiles_y tile grid are split into shares; share w runs jobs [job_ptr[w], job_ptr[w+1]) of
+ * jobs6 = {tile x, tile y, k_begin, k_end, seam_lo, seam_hi} per job.  A job with seam_lo >= 0 hands its first 2p
+ * partial output planes to the job below it through scratch slot seam_lo; seam_hi is the slot a job reads when it
+ * flushes.  No job is shorter than min_len planes unless it is a whole column; a job's upper neighbour lies in a share
+ * with a larger index (the kernel hands shares out in descending order: deadlock-free seams).
+ * mode 0: tile-major sweep over at most `slots` shares; 1: equal-cost chunks cut at the same planes + sweep of the rest,
+ * weighted by `weights` (cost of a plane per tile, per mille; NULL = equal), at most `slots` shares; 2: guided levels
+ * (one share per tile and level, levels shrink towards the bottom, more shares than slots: self-scheduling).
  * Replaces the per-rank slab loop of the reference's cell iteration (system.h:703-761) inside one GPU. */
-int      gdm_pers_partition(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, int aligned,
-                            const int32_t *weights /* cost of a plane per tile, per mille; NULL = equal */, int32_t *job_ptr, int32_t cap_ptr, int32_t *jobs6, int32_t cap_jobs, int32_t *n_shares,
-                            int32_t *n_jobs);
+int      gdm_pers_partition(int tiles_x, int tiles_y, int k0, int k1, int slots, int min_len, int mode,
+                            const int32_t *weights, int32_t *job_ptr, int32_t cap_ptr, int32_t *jobs6,
+                            int32_t cap_jobs, int32_t *n_shares, int32_t *n_jobs);
 
 /* ----------------------------------------------------------- constraints */
 int gdm_constraints_create(gdm_system_t sys, gdm_constraints_t *c);

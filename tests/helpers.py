@@ -65,3 +65,34 @@ def oracle_operator(os_, oc, kind, b=None, scale=1.0):
 
 def rel_err(a, ref):
     return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-300))
+
+
+def sphere_overlay(os_, A, radius, band, gamma=0.5, centre=None):
+    """Synthetic cut-cell row set in the shape BASELINE config 5 produces (prototypes/cut_poisson_01_gdm.cc:196-329,
+    applications/wave/include/gdm/wave/stiffness.h:589-799): the nodes outside the sphere of `radius` (+ band) get
+    identity rows (wave/mass.h:246-248), the nodes within `band` of the sphere get irregular rows
+    (tensor row + a symmetric positive semi-definite penalty among the band nodes, columns to outside nodes dropped),
+    everything inside keeps its tensor-product row.  Returns (rows, rowptr, col, val, A_modified) with A_modified symmetric."""
+    import scipy.sparse as sp
+    X = os_.node_coordinates()
+    c = np.array(centre if centre is not None else [0.5 * (os_.lo[d] + os_.hi[d]) for d in range(os_.dim)])
+    dist = np.linalg.norm(X - c, axis=1) - radius
+    n = A.shape[0]
+    outside = dist > band
+    inband = np.abs(dist) <= band
+    A = sp.csr_matrix(A)
+    # penalty S = gamma * (band-to-band block of A): symmetric positive semi-definite, inside the pattern of A
+    Pb = sp.diags(inband.astype(float))
+    S = gamma * (Pb @ A @ Pb)
+    keep = sp.diags((~outside).astype(float))
+    Am = keep @ (A + S) @ keep + sp.diags(outside.astype(float))
+    Am = sp.csr_matrix(Am)
+    Am.eliminate_zeros()
+    rows = np.nonzero(inband | outside)[0]
+    rowptr, col, val = [0], [], []
+    for r in rows:
+        b, e = Am.indptr[r], Am.indptr[r + 1]
+        col.extend(Am.indices[b:e].tolist())
+        val.extend(Am.data[b:e].tolist())
+        rowptr.append(len(col))
+    return rows, rowptr, col, val, Am

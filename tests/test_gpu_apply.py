@@ -3,6 +3,8 @@ of max|y_ref| on a single apply, as BASELINE.json's north_star states)."""
 import numpy as np
 import pytest
 
+import oracle as O
+
 from helpers import make_pair, make_operator, oracle_operator, rel_err
 
 pytestmark = pytest.mark.gpu
@@ -165,3 +167,36 @@ def test_tvmult(lib, dim, p, reps, bc, kind):
     assert rel_err(y.numpy(), ref) <= 1e-12
     A.vmult(y, x)
     assert rel_err(y.numpy(), Ao @ xh) <= 1e-12
+
+
+@pytest.mark.parametrize("p,reps,kernel", [(3, [20, 19, 21], "fused"), (1, [24, 24, 24], "fused"), (3, [14, 13, 12], "generic")])
+def test_sphere_overlay_apply_diagonal_cg(lib, p, reps, kernel):
+    """BASELINE config 5 in miniature: irregular CSR rows around a sphere + identity rows outside on top of the fused
+    tensor-product apply; single apply, diagonal (Jacobi with CSR rows) and CG iteration count against the oracle matrix."""
+    import gdm_b200 as g
+    from helpers import sphere_overlay
+    gs, gc, os_, oc = make_pair(3, p, 1, reps, "none", hi=[1.0, 1.0, 1.0])
+    A = make_operator(gs, gc, "stiffness", kernel=g.capi.KERNEL_FUSED if kernel == "fused" else g.capi.KERNEL_GENERIC)
+    h = 1.0 / min(reps)
+    rows, rowptr, col, val, Am = sphere_overlay(os_, oracle_operator(os_, oc, "stiffness"), 0.3, (p + 1) * h)
+    A.attach_csr(rows, rowptr, col, val)
+    n = gs.n_dofs()
+    xh = np.random.default_rng(11).uniform(-1, 1, n)
+    x, y = g.Vector(gs, xh), g.Vector(gs)
+    A.vmult(y, x)
+    assert rel_err(y.numpy(), Am @ xh) <= TOL
+    d = g.Vector(gs)
+    A.diagonal(d)
+    assert rel_err(d.numpy(), Am.diagonal()) <= TOL
+    # CG with Jacobi on the modified (symmetric positive definite) operator; rhs supported inside the sphere
+    inside = np.linalg.norm(os_.node_coordinates() - 0.5, axis=1) < 0.3
+    bh = np.where(inside, 1.0, 0.0) * h ** 3
+    b, u = g.Vector(gs, bh), g.Vector(gs)
+    ctl = g.ReductionControl(2000, 1e-12, 1e-6)
+    P = g.PreconditionJacobi()
+    P.initialize(A)
+    g.SolverCG(ctl).solve(A, u, b, P)
+    octl = O.ReductionControl(2000, 1e-12, 1e-6)
+    uo = O.solver_cg(Am, np.zeros(n), bh, O.PreconditionJacobi(Am), octl)
+    assert abs(ctl.last_step() - octl.last_step()) <= 1
+    assert rel_err(u.numpy(), uo) <= 1e-6

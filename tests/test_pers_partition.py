@@ -39,6 +39,13 @@ CASES = [
     (8, 8, 1, 256, 592, 1, 1),
     (8, 8, 0, 68, 296, 3, 1),      # 8-GPU slab
     (17, 17, 0, 131, 148, 5, 0),
+    # guided levels (mode 2): one share per (tile, level), short levels at the bottom are handed out last
+    (8, 8, 1, 256, 296, 3, 2),
+    (8, 11, 1, 256, 296, 3, 2),
+    (16, 16, 0, 513, 148, 5, 2),
+    (2, 2, 0, 9, 296, 3, 2),
+    (3, 5, 0, 40, 7, 3, 2),
+    (8, 8, 0, 68, 296, 1, 2),
 ]
 
 
@@ -59,7 +66,7 @@ def test_partition(lib, tx, ty, k0, k1, slots, p, aligned, weighted):
     wts = edge_weights(tx, ty) if weighted else np.full(tx * ty, 1000)
     ptr, jobs = partition(lib, tx, ty, k0, k1, slots, min_len, aligned, wts if weighted else None)
     n_shares = len(ptr) - 1
-    assert 1 <= n_shares <= slots
+    assert 1 <= n_shares and (n_shares <= slots or aligned == 2)  # guided: more shares than CTAs (self-scheduling)
     assert ptr[0] == 0 and ptr[-1] == len(jobs) and np.all(np.diff(ptr) >= 1) and np.all(np.diff(ptr) <= MAXJ + 8)
     cover = np.zeros((tx * ty, k1 - k0), dtype=int)
     share_of = np.repeat(np.arange(n_shares), np.diff(ptr))
@@ -83,5 +90,16 @@ def test_partition(lib, tx, ty, k0, k1, slots, p, aligned, weighted):
     cost = np.array([sum((jobs[j][3] - jobs[j][2]) * wts[jobs[j][1] * tx + jobs[j][0]] for j in range(ptr[w], ptr[w + 1]))
                      for w in range(n_shares)]) / 1000.0
     ideal = wts.sum() / 1000.0 * (k1 - k0) / min(slots, max(1, tx * ty * (k1 - k0) // (2 * min_len)))
-    if k1 - k0 >= 4 * min_len and slots >= tx * ty:
+    if k1 - k0 >= 4 * min_len and slots >= tx * ty and aligned != 2:
         assert cost.max() <= 1.06 * ideal + min_len, (cost.max(), ideal)
+
+
+def test_guided_levels_shrink_towards_the_bottom(lib):
+    """Guided partition of the BASELINE grid: every column is cut at the same planes, the levels get shorter from the top
+    to the bottom (the bottom ones are dispensed last), none shorter than 8 planes, the top one about one ideal share."""
+    ptr, jobs = partition(lib, 8, 8, 1, 256, 296, 6, 2)
+    lv = sorted({(a, b) for (_, _, a, b, _, _) in jobs})
+    lens = [b - a for a, b in lv]
+    assert lv[0][0] == 1 and lv[-1][1] == 256 and all(lv[i][1] == lv[i + 1][0] for i in range(len(lv) - 1))
+    assert all(x <= y for x, y in zip(lens, lens[1:])) and min(lens) >= 8
+    assert 45 <= lens[-1] <= 62 and len(jobs) == 64 * len(lv)
