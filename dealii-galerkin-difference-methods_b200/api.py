@@ -207,6 +207,15 @@ class System:
         capi.check(self.lib.gdm_system_active_fe_index(self.h, int(cell), C.byref(v)))
         return v.value
 
+    def sparsity_row(self, row, flux=False):
+        """Columns of one row of `create_sparsity_pattern` / `create_flux_sparsity_pattern` (system.h:586-630), generated on
+        demand (the pattern is never stored)."""
+        n = C.c_uint64()
+        capi.check(self.lib.gdm_system_sparsity_row(self.h, int(flux), int(row), None, 0, C.byref(n)))
+        cols = (C.c_uint64 * max(n.value, 1))()
+        capi.check(self.lib.gdm_system_sparsity_row(self.h, int(flux), int(row), cols, n.value, C.byref(n)))
+        return list(cols[: n.value])
+
     def matrix_1d(self, d, kind):
         p, n = self.fe_degree, self.n_subdivisions[d]
         band = np.zeros((n + 1, 2 * p + 1))
@@ -230,6 +239,16 @@ class System:
     def make_periodicity_constraints(self, d, constraints):
         constraints._bind(self)
         capi.check(self.lib.gdm_constraints_make_periodicity(constraints.h, int(d)))
+
+    def interpolate_boundary_values(self, mapping, boundary_id, function, constraints):
+        """system.h:511-547: constrain the boundary nodes (boundary id 0 = every face) to function(point, component)."""
+        constraints._bind(self)
+
+        def cb(pt, comp, _user):
+            return float(function([pt[0], pt[1], pt[2]], comp))
+
+        fn = capi.FUNCTION_FN(cb)
+        capi.check(self.lib.gdm_constraints_interpolate_boundary_values(constraints.h, int(boundary_id), fn, None))
 
     def __del__(self):
         try:
@@ -272,6 +291,12 @@ class AffineConstraints:
     def set_zero(self, vec):
         if self.h is not None:
             capi.check(self.lib.gdm_constraints_set_zero(self.h, vec.h))
+
+    def condense_rhs(self, matrix, rhs):
+        """The right-hand side part of `distribute_local_to_global` with inhomogeneous constraints
+        (tests/poisson_02_gdm.cc:201): free rows b_i -= sum_j A_ij g_j, constrained rows b_j = diag_j g_j."""
+        if self.h is not None:
+            capi.check(self.lib.gdm_constraints_condense_rhs(self.h, matrix.h, rhs.h))
 
     def _handle_for(self, system):
         if self.h is None:

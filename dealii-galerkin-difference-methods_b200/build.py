@@ -18,8 +18,8 @@ FLAGS = [
     "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",
     "-x", "cu",
 ]
-# GDM_BUILD_EXPERIMENTAL=1: also instantiate the round-1 control-structure experiments of the fused kernel
-# (v5/v6/v7 and extra tile shapes; selectable with GDM_FUSED_FAMILY / GDM_FUSED_CFG).  Triples the build time.
+# GDM_BUILD_EXPERIMENTAL=1: also instantiate the alternative tile shapes of the persistent kernel that were measured in
+# round 2 (profiles/r2; selectable with GDM_PERS_CFG).  Doubles the build time.
 if os.environ.get("GDM_BUILD_EXPERIMENTAL", "0") == "1":
     FLAGS = FLAGS[:-2] + ["-DGDM_FUSED_EXPERIMENTAL"] + FLAGS[-2:]
 

@@ -92,14 +92,15 @@ SIGNATURES = {
     "gdm_system_matrix_1d": (C.c_int, [_H, C.c_int, C.c_int, _PD]),
     "gdm_system_layout": (C.c_int, [_H, C.POINTER(LayoutInfo)]),
     "gdm_system_halo_plan": (C.c_int, [_H, C.POINTER(C.c_int32)]),
-    "gdm_fused_partition": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
-                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "gdm_system_sparsity_row": (C.c_int, [_H, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64)]),
     "gdm_pers_partition": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gdm_constraints_create": (C.c_int, [_H, _PH]),
     "gdm_constraints_destroy": (C.c_int, [_H]),
     "gdm_constraints_make_zero_boundary": (C.c_int, [_H, C.c_int]),
     "gdm_constraints_make_periodicity": (C.c_int, [_H, C.c_int]),
+    "gdm_constraints_interpolate_boundary_values": (C.c_int, [_H, C.c_int, FUNCTION_FN, C.c_void_p]),
+    "gdm_constraints_condense_rhs": (C.c_int, [_H, _H, _H]),
     "gdm_constraints_close": (C.c_int, [_H]),
     "gdm_constraints_n_constraints": (C.c_uint64, [_H]),
     "gdm_constraints_is_constrained": (C.c_int, [_H, C.c_uint64]),

@@ -113,6 +113,11 @@ namespace gdm
     cudaFree(d_diag);
   }
 
+  Constraints::~Constraints()
+  {
+    cudaFree(d_inhom);
+  }
+
   Operator::~Operator()
   {
     for (int d = 0; d < 3; ++d)
@@ -631,6 +636,76 @@ int gdm_system_active_fe_index(gdm_system_t sys, uint64_t cell, uint32_t *fe_ind
   GDM_CATCH
 }
 
+// Sparsity patterns (include/gdm/system.h:586-630) without materialising them.  On the Cartesian grid the pattern of a
+// node is a union of boxes: with W(c) = [off(c), off(c)+p] the window of cell c in one direction and C(i) the cells whose
+// window holds node i,  I(i) = U_{c in C(i)} W(c)  (cell coupling)  and  J(i) = I(i) U U_{c in C(i)} W(c-1) U W(c+1)
+// (face neighbours, flux pattern); the row of node (i0,i1,i2) is  prod_d I_d  (create_sparsity_pattern) or
+// U_d ( J_d x prod_{e != d} I_e )  (create_flux_sparsity_pattern).  Constrained rows and columns are kept, as
+// AffineConstraints::add_entries_local_to_global does by default; periodic constraints (redirected entries) are not
+// covered here.
+namespace
+{
+  void coupling_intervals(int p, int N, int i, bool flux, int &lo, int &hi)
+  {
+    lo = N + 1;
+    hi = -1;
+    for (int c = 0; c < N; ++c)
+      {
+        const int o = gdm::window_offset(p, N, c);
+        if (i < o || i > o + p)
+          continue;
+        for (int cc = (flux ? c - 1 : c); cc <= (flux ? c + 1 : c); ++cc)
+          {
+            if (cc < 0 || cc >= N)
+              continue;
+            const int oo = gdm::window_offset(p, N, cc);
+            lo           = std::min(lo, oo);
+            hi           = std::max(hi, oo + p);
+          }
+      }
+  }
+} // namespace
+
+int gdm_system_sparsity_row(gdm_system_t sys, int flux, uint64_t row, uint64_t *cols, uint64_t cap, uint64_t *n_cols)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(n_cols);
+  const Layout &L = sys->impl.L;
+  GDM_REQUIRE(row < (uint64_t)L.n_dofs_global, GDM_ERR_INVALID, "row out of range");
+  const uint64_t node = row / L.nc;
+  int            idx[3] = {0, 0, 0};
+  idx[0] = (int)(node % L.nn[0]);
+  idx[1] = (int)((node / L.nn[0]) % L.nn[1]);
+  idx[2] = (int)(node / ((uint64_t)L.nn[0] * L.nn[1]));
+  int Il[3] = {0, 0, 0}, Ih[3] = {0, 0, 0}, Jl[3] = {0, 0, 0}, Jh[3] = {0, 0, 0};
+  for (int d = 0; d < L.dim; ++d)
+    {
+      coupling_intervals(L.p, L.N[d], idx[d], false, Il[d], Ih[d]);
+      coupling_intervals(L.p, L.N[d], idx[d], flux != 0, Jl[d], Jh[d]);
+    }
+  uint64_t n = 0;
+  // enumerate the bounding box prod_d J_d in DoF order and keep the points that lie in at least one of the boxes
+  for (int k = Jl[2]; k <= Jh[2]; ++k)
+    for (int j = Jl[1]; j <= Jh[1]; ++j)
+      for (int i = Jl[0]; i <= Jh[0]; ++i)
+        {
+          const int  q[3]  = {i, j, k};
+          int        n_out = 0; // directions in which the point leaves the cell-coupling interval
+          for (int d = 0; d < L.dim; ++d)
+            n_out += (q[d] < Il[d] || q[d] > Ih[d]) ? 1 : 0;
+          if (n_out > 1)
+            continue;
+          const uint64_t nd = (uint64_t)i + (uint64_t)L.nn[0] * ((uint64_t)j + (uint64_t)L.nn[1] * (uint64_t)k);
+          for (int c = 0; c < L.nc; ++c, ++n)
+            if (cols != nullptr && n < cap)
+              cols[n] = nd * L.nc + c;
+        }
+  *n_cols = n;
+  GDM_REQUIRE(cols == nullptr || n <= cap, GDM_ERR_INVALID, "column buffer too small");
+  GDM_CATCH
+}
+
 int gdm_system_matrix_1d(gdm_system_t sys, int d, int kind, double *band)
 {
   GDM_TRY
@@ -676,25 +751,6 @@ int gdm_system_halo_plan(gdm_system_t sys, int32_t *plan10)
                           h.send_hi_plane, h.send_hi_count, h.recv_hi_plane, h.recv_hi_count};
   for (int i = 0; i < 10; ++i)
     plan10[i] = v[i];
-  GDM_CATCH
-}
-
-int gdm_fused_partition(int aligned, int tiles_x, int tiles_y, int z0, int z1, int slots, int fe_degree, int32_t *seg_ptr,
-                        int32_t cap_ptr, int32_t *segs4, int32_t cap_segs, int32_t *n_ctas, int32_t *n_segs)
-{
-  GDM_TRY
-  GDM_ARG(n_ctas);
-  GDM_ARG(n_segs);
-  std::vector<int> ptr, segs;
-  fused_partition_host(aligned != 0, tiles_x, tiles_y, z0, z1, slots, fe_degree, ptr, segs);
-  *n_ctas = (int32_t)ptr.size() - 1;
-  *n_segs = (int32_t)(segs.size() / 4);
-  GDM_REQUIRE(seg_ptr != nullptr && segs4 != nullptr && cap_ptr >= (int32_t)ptr.size() && cap_segs >= *n_segs,
-              GDM_ERR_INVALID, "partition buffers too small");
-  for (size_t i = 0; i < ptr.size(); ++i)
-    seg_ptr[i] = ptr[i];
-  for (size_t i = 0; i < segs.size(); ++i)
-    segs4[i] = segs[i];
   GDM_CATCH
 }
 
@@ -829,6 +885,8 @@ int gdm_constraints_distribute(gdm_constraints_t c, gdm_vector_t v)
   Context   &ctx = *c->impl.sys->ctx;
   const bool no_periodic[3] = {false, false, false};
   launch_set_constrained(ctx, c->impl.sys->L, c->impl.dirichlet, no_periodic, v->impl.d, 0.0);
+  if (c->impl.d_inhom) // the boundary nodes are zero now, the inhomogeneity vector is zero everywhere else
+    blas_sadd(ctx, v->impl.d + c->impl.sys->L.own_off, 1.0, 1.0, c->impl.d_inhom + c->impl.sys->L.own_off, c->impl.sys->L.own_len);
   launch_periodic_copy(ctx, c->impl.sys->L, c->impl.periodic, v->impl.d);
   GDM_CATCH
 }
@@ -1071,6 +1129,11 @@ int gdm_operator_destroy(gdm_operator_t op)
     {
       delete static_cast<gdm_operator_s *>(op->impl.transposed);
       op->impl.transposed = nullptr;
+    }
+  if (op && op->impl.unconstrained)
+    {
+      delete static_cast<gdm_operator_s *>(op->impl.unconstrained);
+      op->impl.unconstrained = nullptr;
     }
   delete op;
   return GDM_OK;
@@ -1419,6 +1482,120 @@ int gdm_interpolate(gdm_system_t sys, gdm_function_fn f, void *user, gdm_vector_
         }
   vector_transfer(v->impl, host.data(), true);
   GDM_CUDA_CHECK(cudaStreamSynchronize(sys->impl.ctx->stream));
+  GDM_CATCH
+}
+
+// System::interpolate_boundary_values (include/gdm/system.h:511-547): every boundary node (boundary id 0: the uncoloured
+// hyper rectangle has one id for all faces) is constrained to the value of the function there.  DoFs that are already
+// constrained keep their constraint (system.h:533).
+int gdm_constraints_interpolate_boundary_values(gdm_constraints_t c, int boundary_id, gdm_function_fn f, void *user)
+{
+  GDM_TRY
+  GDM_ARG(c);
+  GDM_ARG(f);
+  Constraints  &cs = c->impl;
+  const Layout &L  = cs.sys->L;
+  GDM_REQUIRE(!cs.closed, GDM_ERR_INVALID, "constraints already closed");
+  GDM_REQUIRE(boundary_id == 0, GDM_ERR_INVALID, "the hyper rectangle has boundary id 0 on every face");
+  GDM_REQUIRE(cs.sys->ctx->device >= 0, GDM_ERR_CUDA, "description-only context: no CUDA device (no CPU fallback)");
+  for (int d = 0; d < L.dim; ++d)
+    GDM_REQUIRE(!cs.periodic[d], GDM_ERR_NOT_IMPLEMENTED, "boundary values together with periodicity");
+  bool was[3][2];
+  for (int d = 0; d < 3; ++d)
+    for (int s = 0; s < 2; ++s)
+      was[d][s] = cs.dirichlet[d][s];
+  std::vector<double> host((size_t)L.n_owned, 0.0);
+  int lo[3] = {0, 0, 0}, hi[3] = {L.nn[0], L.nn[1], L.nn[2]};
+  lo[L.pdim] = L.own0;
+  hi[L.pdim] = L.own1;
+  size_t o   = 0;
+  for (int k = lo[2]; k < hi[2]; ++k)
+    for (int j = lo[1]; j < hi[1]; ++j)
+      for (int i = lo[0]; i < hi[0]; ++i)
+        {
+          const int idx[3] = {i, j, k};
+          bool      on_new = false, on_old = false;
+          for (int d = 0; d < L.dim; ++d)
+            for (int s = 0; s < 2; ++s)
+              if (idx[d] == (s == 0 ? 0 : L.N[d]))
+                (was[d][s] ? on_old : on_new) = true;
+          const double pt[3] = {L.lo[0] + i * L.h[0], L.lo[1] + j * L.h[1], L.lo[2] + k * L.h[2]};
+          for (int cc = 0; cc < L.nc; ++cc, ++o)
+            if (on_new && !on_old)
+              host[o] = f(pt, cc, user);
+        }
+  if (!cs.d_inhom)
+    {
+      GDM_CUDA_CHECK(cudaMalloc(&cs.d_inhom, (size_t)L.size * sizeof(double)));
+      GDM_CUDA_CHECK(cudaMemset(cs.d_inhom, 0, (size_t)L.size * sizeof(double)));
+    }
+  else
+    {
+      // keep the values of earlier calls on the faces they constrained
+      Vector old;
+      old.sys  = cs.sys;
+      old.d    = cs.d_inhom;
+      old.owns = false;
+      std::vector<double> prev((size_t)L.n_owned);
+      vector_transfer(old, prev.data(), false);
+      GDM_CUDA_CHECK(cudaStreamSynchronize(cs.sys->ctx->stream));
+      for (size_t q = 0; q < host.size(); ++q)
+        if (prev[q] != 0.0)
+          host[q] = prev[q];
+    }
+  Vector tmp;
+  tmp.sys  = cs.sys;
+  tmp.d    = cs.d_inhom;
+  tmp.owns = false;
+  vector_transfer(tmp, host.data(), true);
+  GDM_CUDA_CHECK(cudaStreamSynchronize(cs.sys->ctx->stream));
+  for (int d = 0; d < L.dim; ++d)
+    cs.dirichlet[d][0] = cs.dirichlet[d][1] = true;
+  GDM_CATCH
+}
+
+// The right-hand side part of AffineConstraints::distribute_local_to_global(cell_matrix, cell_rhs, dofs, A, rhs) with
+// inhomogeneous constraints (tests/poisson_02_gdm.cc:201): free rows  b_i -= sum_j A_ij g_j  over the constrained columns j,
+// constrained rows  b_j = (diagonal the matrix keeps on row j) g_j,  so that the solve returns u_j = g_j.
+// `op` is the constrained operator; the unconstrained twin that provides A_ij g_j is created on first use.
+int gdm_constraints_condense_rhs(gdm_constraints_t c, gdm_operator_t op, gdm_vector_t rhs)
+{
+  GDM_TRY
+  GDM_ARG(c);
+  GDM_ARG(op);
+  GDM_ARG(rhs);
+  Constraints &cs = c->impl;
+  Operator    &o  = op->impl;
+  GDM_REQUIRE(cs.closed, GDM_ERR_INVALID, "constraints must be closed");
+  GDM_REQUIRE(o.sys == cs.sys && rhs->impl.sys == cs.sys, GDM_ERR_INVALID, "constraints/operator/vector system mismatch");
+  if (!cs.d_inhom)
+    return GDM_OK; // homogeneous: nothing to lift
+  GDM_REQUIRE(!o.csr, GDM_ERR_NOT_IMPLEMENTED, "boundary values with CSR overlay rows");
+  Context      &ctx = *cs.sys->ctx;
+  const Layout &L   = cs.sys->L;
+  if (!o.unconstrained)
+    {
+      gdm_operator_desc desc   = o.desc;
+      desc.constrained_diagonal = GDM_DIAG_ZERO;
+      gdm_operator_t t          = nullptr;
+      const int      rc         = gdm_operator_create(reinterpret_cast<gdm_system_s *>(o.sys), nullptr, &desc, &t);
+      if (rc != GDM_OK)
+        return rc;
+      o.unconstrained = t;
+    }
+  Vector g;
+  g.sys  = cs.sys;
+  g.d    = cs.d_inhom;
+  g.owns = false;
+  Vector t;
+  t.sys  = cs.sys;
+  t.d    = ctx.acquire((size_t)L.size);
+  t.owns = false;
+  operator_apply(static_cast<gdm_operator_s *>(o.unconstrained)->impl, t, g, false);
+  blas_sadd(ctx, rhs->impl.d + L.own_off, 1.0, -1.0, t.d + L.own_off, L.own_len);
+  ctx.release(t.d);
+  // constrained rows: the diagonal deal.II keeps there times the boundary value
+  launch_constrained_rows(ctx, L, o, rhs->impl.d, cs.d_inhom, false);
   GDM_CATCH
 }
 

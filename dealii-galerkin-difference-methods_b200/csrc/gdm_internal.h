@@ -142,6 +142,10 @@ namespace gdm
     bool    dirichlet[3][2] = {{false, false}, {false, false}, {false, false}};
     bool    periodic[3] = {false, false, false};
     bool    closed = false;
+    // inhomogeneous Dirichlet values (System::interpolate_boundary_values, system.h:511-547): a vector that holds g at
+    // the constrained boundary nodes and zero elsewhere (nullptr: all constraints homogeneous)
+    double *d_inhom = nullptr;
+    ~Constraints();
   };
 
   struct Vector
@@ -185,6 +189,8 @@ namespace gdm
     int     kernel_used = GDM_KERNEL_GENERIC;
     std::unique_ptr<CsrOverlay> csr;
     void   *fused = nullptr;          // FusedPlan* (kron3d.cu)
+    void   *unconstrained = nullptr;  // gdm_operator_s* of the same operator without constraints (lifting of inhomogeneous
+                                      // Dirichlet values into the right-hand side), created on first use
     void   *transposed = nullptr;     // gdm_operator_s* of the transposed advection operator (Tvmult), created on first use
     double *tmp = nullptr;            // vmult_add with CSR overlay
     double *host_src = nullptr, *host_dst = nullptr; // staging of vmult_host (padded layout)
@@ -211,7 +217,7 @@ namespace gdm
   // src * dst over its rows to dot_partials[b] (fused dot product of the apply)
   int  launch_constrained_rows(Context &ctx, const Layout &L, const Operator &op, double *dst,
                                const double *src, bool accumulate, int plane_lo = -1, int plane_hi = -1,
-                               double *dot_partials = nullptr);
+                               double *dot_partials = nullptr, cudaStream_t stream = nullptr /* nullptr: ctx.stream */);
   // upper bound of the blocks launch_constrained_rows uses (to size partial buffers)
   int  constrained_rows_max_blocks(const Layout &L);
   void launch_csr_overlay(Context &ctx, const CsrOverlay &csr, double *dst, const double *src,
@@ -237,16 +243,12 @@ namespace gdm
   bool fused_supports_dot(const Operator &op);
   // output planes [z0, z1) only (local plane indices; no ghost import): building block of the pipelined host-buffer apply
   void fused_apply_window(Operator &op, double *dst, const double *src, int z0, int z1);
-  // host logic of the static work partition of the fused kernels (v5/v7): CTA b runs segments
-  // [seg_ptr[b], seg_ptr[b+1]) of segs4 = {tile x, tile y, z0, z1} x n
-  void fused_partition_host(bool aligned, int tiles_x, int tiles_y, int z0, int z1, int slots, int p, std::vector<int> &seg_ptr,
-                            std::vector<int> &segs4);
-
   // kron3d_pers.cu -- persistent ramp-free fused kernel (default for dim == 3, scalar, non-periodic)
   bool  pers_supported(const Operator &op);
   void *pers_plan_create(Operator &op); // nullptr: not applicable to this operator
   void  pers_plan_destroy(void *plan);
   int   pers_max_grid(const Operator &op, const void *plan);
+  void  pers_window(const void *plan, int &cz0, int &cz1); // output planes of the whole slab (local indices)
   // output planes [oz0, oz1) (local indices); dot_partials != nullptr: CTA w leaves its share of <dot_src, A src> in
   // dot_partials[w]; returns the number of CTAs launched
   // slots_limit > 0: use at most that many CTAs (launches that share the GPU: slab faces beside the interior planes)

@@ -598,8 +598,11 @@ namespace gdm
   } // namespace
 
   int launch_constrained_rows(Context &ctx, const Layout &L, const Operator &op, double *dst,
-                              const double *src, bool accumulate, int plane_lo, int plane_hi, double *dot_partials)
+                              const double *src, bool accumulate, int plane_lo, int plane_hi, double *dot_partials,
+                              cudaStream_t stream)
   {
+    if (stream == nullptr)
+      stream = ctx.stream;
     FaceK a;
     a.dst = dst;
     a.src = src;
@@ -639,7 +642,7 @@ namespace gdm
     const int     th = 128;
     a.dot_partials = dot_partials;
     const unsigned blocks = (unsigned)((n + th - 1) / th);
-    constrained_rows_kernel<<<blocks, th, 0, ctx.stream>>>(a);
+    constrained_rows_kernel<<<blocks, th, 0, stream>>>(a);
     ctx.launches++;
     GDM_CUDA_CHECK(cudaGetLastError());
     return (int)blocks;

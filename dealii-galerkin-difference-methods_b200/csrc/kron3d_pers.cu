@@ -818,6 +818,9 @@ namespace gdm
                 c.out += g.plane;
               }
           }
+            // the last plane of the share had no x pass of a next plane: its sequence number stays free for the first
+            // plane of the next share (every sequence number is used exactly once: the mbarrier phases depend on it)
+            --seq;
           } // shares
         if (g.trace != nullptr && tid == 0)
           {
@@ -1254,12 +1257,14 @@ namespace gdm
             weights[(size_t)ty * plan.tiles_x + tx] = (xe && ye) ? wxy : (xe ? wx : (ye ? wy : 1000));
           }
       (void)env_L;
-      // partition mode: guided self-scheduling by default; GDM_PERS_MODE=static: one weighted share per CTA
-      int         mode   = 2;
+      // partition mode: one weighted share per CTA (static).  GDM_PERS_MODE=guided selects the self-scheduled level
+      // partition (more shares than CTAs); it is NOT a supported mode: on B200 every launch with more shares than CTAs
+      // stalled (profiles/r2/session_h_guided_stall.txt), cause not found, so it stays a diagnostic switch.
+      int         mode   = aligned ? 1 : 0;
       double      gk     = 1.0;
       int         gmin   = 8;
       if (const char *env = std::getenv("GDM_PERS_MODE"))
-        mode = (env[0] == 's') ? (aligned ? 1 : 0) : 2;
+        mode = (env[0] == 'g') ? 2 : mode;
       if (const char *env = std::getenv("GDM_PERS_GUIDE"))
         sscanf(env, "%lf,%d", &gk, &gmin);
       pers_partition_host(plan.tiles_x, plan.tiles_y, k0, std::max(k0, k1), slots, min_len, mode, weights.data(), ptr, j6, gk, gmin);

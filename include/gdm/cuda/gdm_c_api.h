@@ -60,6 +60,8 @@ typedef struct gdm_context_s     *gdm_context_t;
 typedef struct gdm_system_s      *gdm_system_t;
 typedef struct gdm_constraints_s *gdm_constraints_t;
 typedef struct gdm_operator_s    *gdm_operator_t;
+/* scalar function of a point (dealii::Function<dim>::value): point[dim], component */
+typedef double (*gdm_function_fn)(const double *point, int component, void *user);
 typedef struct gdm_vector_s      *gdm_vector_t;
 typedef struct gdm_rk_s          *gdm_rk_t;
 
@@ -108,6 +110,13 @@ int      gdm_system_dofs_per_cell(gdm_system_t sys);
 int      gdm_system_get_dof_indices(gdm_system_t sys, uint64_t cell, uint64_t *out);
 /* system.h:404-424 */
 int      gdm_system_active_fe_index(gdm_system_t sys, uint64_t cell, uint32_t *fe_index);
+/* One row of System::create_sparsity_pattern (flux = 0, system.h:586-599) or create_flux_sparsity_pattern (flux != 0,
+ * system.h:602-630): the global DoF indices the row couples to, ascending.  The pattern is never stored (343 entries per
+ * row at p = 3 in 3D): rows are generated on demand from the per-direction window rules.  cols may be NULL to query the
+ * length only; constrained rows/columns are kept (AffineConstraints::add_entries_local_to_global default); periodic
+ * redirections are not included. */
+int gdm_system_sparsity_row(gdm_system_t sys, int flux, uint64_t row, uint64_t *cols, uint64_t cap, uint64_t *n_cols);
+
 /* Physical 1D band matrix of direction d without constraints:
  * kind 0 = mass (h*M1), 1 = stiffness (K1/h), 2 = convection (C1, row = test fn).
  * band[(row*(2p+1)) + tap], column = row + tap - p, rows 0..N_d. */
@@ -125,16 +134,6 @@ int      gdm_system_layout(gdm_system_t sys, gdm_layout_info *info);
  * direction): plan10 = {prev_rank, next_rank, send_lo_plane, send_lo_count, recv_lo_plane, recv_lo_count,
  * send_hi_plane, send_hi_count, recv_hi_plane, recv_hi_count}; ranks are -1 where there is no neighbour. */
 int      gdm_system_halo_plan(gdm_system_t sys, int32_t *plan10);
-/* Host logic of the fused kernels' static work partition (no device needed; exposed for tests and tools):
- * the (tile, plane) work of output planes [z0, z1) of a tiles_x x tiles_y tile grid is split into at most `slots`
- * CTAs; CTA b runs segments [seg_ptr[b], seg_ptr[b+1]) of segs4 = {tile x, tile y, z_begin, z_end} per segment.
- * aligned != 0: every tile column is cut at the same planes (kron3d_v7), else tile-major linear sweep (kron3d_v5).
- * Replaces the per-rank slab loop of the reference's cell iteration (system.h:703-761) inside one GPU.
- * Returns GDM_ERR_INVALID if the capacities are too small; *n_ctas / *n_segs are always set. */
-int      gdm_fused_partition(int aligned, int tiles_x, int tiles_y, int z0, int z1, int slots, int fe_degree,
-                             int32_t *seg_ptr, int32_t cap_ptr, int32_t *segs4, int32_t cap_segs, int32_t *n_ctas,
-                             int32_t *n_segs);
-
 /* Work partition of the persistent fused kernel (kron3d_pers.cu; host logic, no device needed): the input planes
  * [k0, k1) of a tiles_x x tiles_y tile grid are split into shares; share w runs jobs [job_ptr[w], job_ptr[w+1]) of
  * jobs6 = {tile x, tile y, k_begin, k_end, seam_lo, seam_hi} per job.  A job with seam_lo >= 0 hands its first 2p
@@ -156,7 +155,14 @@ int gdm_constraints_destroy(gdm_constraints_t c);
 int gdm_constraints_make_zero_boundary(gdm_constraints_t c, int surface);
 /* node N_d == node 0 in direction d, weight 1 (system.h:427-463) */
 int gdm_constraints_make_periodicity(gdm_constraints_t c, int d);
+/* System::interpolate_boundary_values (system.h:511-547): constrains every boundary node (boundary id 0) to f there;
+ * DoFs that are already constrained keep their constraint.  Call before gdm_constraints_close. */
+int gdm_constraints_interpolate_boundary_values(gdm_constraints_t c, int boundary_id, gdm_function_fn f, void *user);
 int gdm_constraints_close(gdm_constraints_t c);
+/* Right-hand side part of AffineConstraints::distribute_local_to_global with inhomogeneous constraints
+ * (tests/poisson_02_gdm.cc:201): free rows b_i -= sum_j A_ij g_j, constrained rows b_j = diag_j g_j.  No-op for
+ * homogeneous constraints.  After the solve, gdm_constraints_distribute writes g into the constrained DoFs. */
+int gdm_constraints_condense_rhs(gdm_constraints_t c, gdm_operator_t op, gdm_vector_t rhs);
 uint64_t gdm_constraints_n_constraints(gdm_constraints_t c);
 int gdm_constraints_is_constrained(gdm_constraints_t c, uint64_t dof);
 /* AffineConstraints::distribute / set_zero on a device vector */
@@ -262,7 +268,6 @@ int gdm_rk_evolve_one_time_step(gdm_rk_t rk, gdm_rk_rhs_fn f, void *user, double
                                 gdm_vector_t *y, double *t_new);
 
 /* -------------------------------------------------------------- vector tools */
-typedef double (*gdm_function_fn)(const double *point, int component, void *user);
 int gdm_interpolate(gdm_system_t sys, gdm_function_fn f, void *user, gdm_vector_t v);
 /* cellwise L2 error (length n_cells of the locally owned cells' global numbering;
  * cells of other ranks are left 0) and its global l2 sum over all ranks */

@@ -23,6 +23,7 @@
 // Everything computes on the GPU through libgdm_b200.so; there is no host fallback.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <functional>
@@ -152,6 +153,45 @@ namespace GDM
           out[v][k][i] = c[(v * (p + 1) + k) * (p + 1) + i];
     return out;
   }
+
+  // fe.h:339-397 -- lexicographic index <-> multi-index, x fastest: the layout of the global vector
+  template <int dim>
+  std::array<unsigned int, dim> index_to_indices(const unsigned int index, const std::array<unsigned int, dim> Ns)
+  {
+    std::array<unsigned int, dim> indices{};
+    unsigned int                  r = index;
+    for (int d = 0; d < dim; ++d)
+      {
+        indices[d] = (d + 1 < dim) ? r % Ns[d] : r;
+        r /= Ns[d];
+      }
+    return indices;
+  }
+  template <int dim>
+  std::array<unsigned int, dim> index_to_indices(const unsigned int index, const unsigned int N)
+  {
+    std::array<unsigned int, dim> Ns;
+    Ns.fill(N);
+    return index_to_indices<dim>(index, Ns);
+  }
+  template <int dim>
+  unsigned int indices_to_index(const std::array<unsigned int, dim> indices, const std::array<unsigned int, dim> Ns)
+  {
+    unsigned int index = 0, stride = 1;
+    for (int d = 0; d < dim; ++d)
+      {
+        index += indices[d] * stride;
+        stride *= Ns[d];
+      }
+    return index;
+  }
+  template <int dim>
+  unsigned int indices_to_index(const std::array<unsigned int, dim> index, const unsigned int N)
+  {
+    std::array<unsigned int, dim> Ns;
+    Ns.fill(N);
+    return indices_to_index<dim>(index, Ns);
+  }
 } // namespace GDM
 
 namespace dealii
@@ -187,6 +227,14 @@ namespace dealii
     {
       if (h)
         internal::check(gdm_constraints_set_zero(h, v.handle()));
+    }
+    // the right-hand side part of distribute_local_to_global(cell_matrix, cell_rhs, dofs, A, rhs) with inhomogeneous
+    // constraints (tests/poisson_02_gdm.cc:201): b_i -= sum_j A_ij g_j on free rows, b_j = diag_j g_j on constrained rows
+    template <class MatrixType, class VectorType>
+    void condense_rhs(const MatrixType &A, VectorType &rhs) const
+    {
+      if (h)
+        internal::check(gdm_constraints_condense_rhs(h, A.handle(), rhs.handle()));
     }
     // used by GDM::System
     void bind(gdm_system_t sys) const
@@ -316,13 +364,56 @@ namespace dealii
   };
 
   // ---------------------------------------------------------------------------- SparseMatrix (operator)
+  // The operator is matrix free: a sparsity pattern is a *view* whose rows are generated on demand by the C ABI
+  // (gdm_system_sparsity_row; System::create_sparsity_pattern / create_flux_sparsity_pattern, system.h:586-630).  At the
+  // BASELINE size the stored pattern would need 70 GB; row_length / column_number / n_nonzero_elements work at any size.
   struct DynamicSparsityPattern
   {
     explicit DynamicSparsityPattern(std::size_t = 0) {}
+    template <class IndexSet>
+    explicit DynamicSparsityPattern(const IndexSet &)
+    {}
+    void bind(gdm_system_t s, bool flux_, std::size_t n)
+    {
+      sys    = s;
+      flux   = flux_;
+      n_dofs = n;
+    }
+    std::size_t n_rows() const { return n_dofs; }
+    std::size_t n_cols() const { return n_dofs; }
+    unsigned int row_length(const std::size_t row) const
+    {
+      uint64_t n = 0;
+      internal::check(gdm_system_sparsity_row(sys, flux ? 1 : 0, row, nullptr, 0, &n));
+      return (unsigned int)n;
+    }
+    std::vector<unsigned long long> row(const std::size_t r) const
+    {
+      uint64_t n = row_length(r);
+      std::vector<uint64_t> c(n);
+      internal::check(gdm_system_sparsity_row(sys, flux ? 1 : 0, r, c.data(), n, &n));
+      return std::vector<unsigned long long>(c.begin(), c.end());
+    }
+    unsigned long long column_number(const std::size_t r, const unsigned int k) const { return row(r)[k]; }
+    bool exists(const std::size_t r, const std::size_t c) const
+    {
+      const auto cols = row(r);
+      return std::binary_search(cols.begin(), cols.end(), (unsigned long long)c);
+    }
+    unsigned long long n_nonzero_elements() const
+    {
+      unsigned long long n = 0;
+      for (std::size_t r = 0; r < n_dofs; ++r)
+        n += row_length(r);
+      return n;
+    }
+    gdm_system_t sys = nullptr;
+    bool         flux = false;
+    std::size_t  n_dofs = 0;
   };
-  struct SparsityPattern
+  struct SparsityPattern : DynamicSparsityPattern
   {
-    void copy_from(const DynamicSparsityPattern &) {}
+    void copy_from(const DynamicSparsityPattern &d) { static_cast<DynamicSparsityPattern &>(*this) = d; }
   };
 
   template <typename Number = double>
@@ -618,9 +709,35 @@ namespace GDM
       c.bind(h);
       internal::check(gdm_constraints_make_periodicity(c.handle(), (int)d));
     }
+    // system.h:511-547: boundary nodes (boundary id 0 = every face of the hyper rectangle) take the value of fu
+    void interpolate_boundary_values(const hp::MappingCollection<dim> &, const unsigned int bid, const Function<dim> &fu,
+                                     AffineConstraints<double> &c) const
+    {
+      c.bind(h);
+      const Function<dim> *f = &fu;
+      internal::check(gdm_constraints_interpolate_boundary_values(
+        c.handle(), (int)bid,
+        [](const double *pt, int comp, void *user) -> double {
+          Point<dim> p;
+          for (int d = 0; d < dim; ++d)
+            p[d] = pt[d];
+          return (*static_cast<const Function<dim> **>(user))->value(p, comp);
+        },
+        &f));
+    }
+    // system.h:586-599 / 602-630: the pattern object becomes a view of this system (rows on demand)
     template <class SP>
-    void create_sparsity_pattern(const AffineConstraints<double> &, SP &) const
-    {} // matrix free: no pattern (system.h:586-599)
+    void create_sparsity_pattern(const AffineConstraints<double> &, SP &dsp) const
+    {
+      dsp.bind(h, false, n_dofs());
+    }
+    template <class SP>
+    void create_flux_sparsity_pattern(const AffineConstraints<double> &, SP &dsp) const
+    {
+      if (!add_ghost_layer)
+        throw ExcNotImplemented("create_flux_sparsity_pattern needs add_ghost_layer (system.h:605)");
+      dsp.bind(h, true, n_dofs());
+    }
     void get_dof_indices(unsigned long long cell, std::vector<unsigned long long> &out) const
     {
       out.resize(gdm_system_dofs_per_cell(h));

@@ -248,6 +248,32 @@ class System:
                     constraints.add_line(i1 * nc + c)
                     constraints.add_entry(i1 * nc + c, i0 * nc + c, 1.0)
 
+    # ---- sparsity patterns (`system.h:586-630`), literal cell loops
+    def create_sparsity_pattern(self, constraints=None, flux=False):
+        """[row] -> sorted list of columns.  `create_sparsity_pattern` couples the DoFs of every cell with each other;
+        `create_flux_sparsity_pattern` (flux=True) adds, for every interior face, the DoFs of the cell (rows) x the
+        DoFs of the face neighbour (columns).  Constrained rows/columns are kept (deal.II's
+        `add_entries_local_to_global` default `keep_constrained_entries = true`); constraints with entries (periodic)
+        would add the redirected pairs as well -- not modelled (no caller on the path uses them with a flux pattern)."""
+        rows = [set() for _ in range(self.n_dofs())]
+        ns = self.n_subdivisions
+        for cell in range(self.n_cells()):
+            dofs = self.get_dof_indices(cell)
+            for i in dofs:
+                rows[i].update(dofs)
+            if flux:
+                idx = self.cell_indices(cell)
+                for d in range(self.dim):
+                    for s in (-1, 1):
+                        nb = list(idx)
+                        nb[d] += s
+                        if nb[d] < 0 or nb[d] >= ns[d]:
+                            continue  # at_boundary
+                        nd = self.get_dof_indices(indices_to_index(nb, ns))
+                        for i in dofs:
+                            rows[i].update(nd)
+        return [sorted(r) for r in rows]
+
     # ---- slab partition (`system.h:720-757`)
     def partition_stride(self):
         return (self.n_subdivisions[-1] + self.n_ranks - 1) // self.n_ranks

@@ -200,3 +200,40 @@ def test_sphere_overlay_apply_diagonal_cg(lib, p, reps, kernel):
     uo = O.solver_cg(Am, np.zeros(n), bh, O.PreconditionJacobi(Am), octl)
     assert abs(ctl.last_step() - octl.last_step()) <= 1
     assert rel_err(u.numpy(), uo) <= 1e-6
+
+
+@pytest.mark.parametrize("dim,p,reps,kernel", [(2, 3, [9, 8], "generic"), (3, 3, [10, 9, 12], "fused"), (3, 5, [12, 12, 12], "fused")])
+def test_inhomogeneous_dirichlet(lib, dim, p, reps, kernel):
+    """System::interpolate_boundary_values (system.h:511-547) + the rhs part of distribute_local_to_global: the harmonic
+    polynomial g = x^2 - y^2 (+ z) lies in the GDM space (degree <= p), so -Laplace u = 0, u = g on the boundary returns
+    the interpolant of g; the condensed right-hand side is checked against the oracle's matrices."""
+    import gdm_b200 as g
+    hi = [1.0 + 0.25 * d for d in range(dim)]
+    gs = g.System(dim, p, 1)
+    gs.subdivided_hyper_rectangle(reps, [0.0] * dim, hi)
+    so = O.System(dim, p)
+    so.subdivided_hyper_rectangle(reps, [0.0] * dim, hi)
+    gfun = lambda pt, c=0: pt[0] ** 2 - pt[1] ** 2 + (0.5 * pt[2] if dim == 3 else 0.0)
+    gc = g.AffineConstraints()
+    gs.interpolate_boundary_values(g.MappingQ1(), 0, gfun, gc)
+    gc.close()
+    co = O.Constraints()
+    so.make_zero_boundary_constraints(co)
+    co.close()
+    A = make_operator(gs, gc, "stiffness", kernel=g.capi.KERNEL_FUSED if kernel == "fused" else g.capi.KERNEL_GENERIC)
+    # oracle: lifting with the unconstrained matrix, deal.II's diagonal on the constrained rows
+    Au = O.kron_unconstrained(so, "stiffness")
+    Ac = O.kron_operator(so, co, "stiffness")
+    X = so.node_coordinates()
+    gh = np.array([gfun(list(x) + [0.0] * (3 - dim)) for x in X])
+    con = co.constrained_mask(so.n_dofs())
+    gb = np.where(con, gh, 0.0)
+    rhs_ref = np.where(con, Ac.diagonal() * gb, -(Au @ gb))
+    rhs = g.Vector(gs)
+    gc.condense_rhs(A, rhs)
+    assert rel_err(rhs.numpy(), rhs_ref) <= TOL
+    u = g.Vector(gs)
+    ctl = g.ReductionControl(2000, 1e-14, 1e-12)
+    g.SolverCG(ctl).solve(A, u, rhs, g.PreconditionIdentity())
+    gc.distribute(u)
+    assert np.abs(u.numpy() - gh).max() <= 1e-9 * np.abs(gh).max()

@@ -30,13 +30,10 @@ FUSED_CASES = [
 
 @pytest.mark.parametrize("p,reps,bc", FUSED_CASES)
 @pytest.mark.parametrize("kind", ["mass", "stiffness", "advection", "advection_t"])
-@pytest.mark.parametrize("lz", [None, 8])
-def test_fused_apply_matches_oracle(lib, monkeypatch, p, reps, bc, kind, lz):
+@pytest.mark.parametrize("mode", ["guided", "static"])
+def test_fused_apply_matches_oracle(lib, monkeypatch, p, reps, bc, kind, mode):
     import gdm_b200 as g
-    if lz is not None:
-        monkeypatch.setenv("GDM_FUSED_LZ", str(lz))
-    else:
-        monkeypatch.delenv("GDM_FUSED_LZ", raising=False)
+    monkeypatch.setenv("GDM_PERS_MODE", mode)  # self-scheduled guided shares (default) / one weighted share per CTA
     gs, gc, os_, oc = make_pair(3, p, 1, reps, bc)
     b = [1.0, 0.15, -0.05]
     scale = -0.5 if kind == "advection" else 1.0

@@ -139,3 +139,23 @@ def test_error_reporting(lib):
     assert lib.gdm_system_create(ctx, C.byref(d), C.byref(h)) == capi.ERR_INVALID
     assert b"n_subdivisions" in lib.gdm_last_error()
     lib.gdm_context_destroy(ctx)
+
+
+@pytest.mark.parametrize("dim,p,reps,nc", [(1, 3, [9], 1), (1, 5, [11], 1), (2, 3, [7, 6], 1), (2, 1, [4, 5], 2), (2, 5, [11, 12], 1),
+                                           (3, 3, [7, 6, 8], 1), (3, 1, [3, 4, 3], 1)])
+@pytest.mark.parametrize("flux", [False, True])
+def test_sparsity_pattern_rows(lib, dim, p, reps, nc, flux):
+    """System::create_sparsity_pattern / create_flux_sparsity_pattern (system.h:586-630): the rows generated on demand
+    by the C ABI (boxes from the per-direction window rules) equal the oracle's literal cell / face loops."""
+    import gdm_b200 as g
+    import oracle as O
+    desc_ctx = g.Context(device=-1)
+    gs = g.System(dim, p, nc, add_ghost_layer=flux, context=desc_ctx)
+    gs.subdivided_hyper_rectangle(reps, [0.0] * dim, [1.0] * dim)
+    so = O.System(dim, p, nc)
+    so.subdivided_hyper_rectangle(reps, [0.0] * dim, [1.0] * dim)
+    ref = so.create_sparsity_pattern(flux=flux)
+    for row in range(so.n_dofs()):
+        assert gs.sparsity_row(row, flux) == ref[row], row
+    if dim == 3 and p == 3 and not flux:  # interior rows couple (2p+1)^3 = 343 nodes (SURVEY a6)
+        assert max(len(r) for r in ref) == 343
