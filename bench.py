@@ -301,10 +301,10 @@ def run_ours(args):
         return
     peak, which = peaks()
     achieved = ALG_BYTES_PER_DOF * (total_dofs / world) / (ms / args.steps * 1e-3) / 1e9
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
-    # (profiles/r1/traffic.json; only valid for the BASELINE grid on one GPU)
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload and this
+    # kernel configuration (profiles/r2/traffic.json; only valid for the BASELINE grid on one GPU)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1", "traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2", "traffic.json")
     if os.path.exists(tpath) and world == 1 and n == 256 and p == 3:
         tj = json.load(open(tpath))
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
@@ -316,7 +316,7 @@ def run_ours(args):
     fp64["frac"] = fp64["achieved"] / fp64["peak"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)",
-                "kernel": "kron3d_kernel (fused TMA-staged tensor-product apply)" if A.kernel_used() == 2 else "generic band passes",
+                "kernel": "kron3d_pers_kernel (persistent fused TMA-staged tensor-product apply)" if A.kernel_used() == 2 else "generic band passes",
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_DOF * total_dofs / world,
                 "second_roof": fp64,
                 "note": "duration = CUDA-event time of the timed region / steps (includes the constrained-face kernels)"}

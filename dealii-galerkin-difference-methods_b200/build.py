@@ -22,6 +22,20 @@ FLAGS = [
 # round 2 (profiles/r2; selectable with GDM_PERS_CFG).  Doubles the build time.
 if os.environ.get("GDM_BUILD_EXPERIMENTAL", "0") == "1":
     FLAGS = FLAGS[:-2] + ["-DGDM_FUSED_EXPERIMENTAL"] + FLAGS[-2:]
+# GDM_BUILD_WATCHDOG=1: diagnostic library libgdm_b200_wd.so whose persistent kernel bounds and records every wait
+# (select it at run time with GDM_B200_LIB=<path>); the product library is not touched.
+BUILD_DIR = "build"
+if os.environ.get("GDM_BUILD_WATCHDOG", "0") == "1":
+    FLAGS = FLAGS[:-2] + ["-DGDM_PERS_WATCHDOG"] + FLAGS[-2:]
+    LIB = os.path.join(HERE, "libgdm_b200_wd.so")
+    BUILD_DIR = "build_wd"
+
+
+# GDM_BUILD_DEFINES="-DX -DY" GDM_BUILD_SUFFIX=_x: A/B builds of kernel variants (libgdm_b200_x.so, selected with GDM_B200_LIB)
+if os.environ.get("GDM_BUILD_SUFFIX"):
+    FLAGS = FLAGS[:-2] + os.environ.get("GDM_BUILD_DEFINES", "").split() + FLAGS[-2:]
+    LIB = os.path.join(HERE, "libgdm_b200" + os.environ["GDM_BUILD_SUFFIX"] + ".so")
+    BUILD_DIR = "build" + os.environ["GDM_BUILD_SUFFIX"]
 
 
 def _stamp():
@@ -37,15 +51,15 @@ def _stamp():
 
 
 def build(force=False, verbose=False):
-    stamp_file = os.path.join(HERE, "build", "stamp")
+    stamp_file = os.path.join(HERE, BUILD_DIR, "stamp")
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return LIB
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(os.path.join(HERE, BUILD_DIR), exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.rsplit(".", 1)[0] + ".o")
+        obj = os.path.join(HERE, BUILD_DIR, src.rsplit(".", 1)[0] + ".o")
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

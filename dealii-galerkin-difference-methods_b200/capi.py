@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgdm_b200.so")
+# GDM_B200_LIB: load a diagnostic build (libgdm_b200_wd.so, build.py) instead of the product library
+LIB_PATH = os.environ.get("GDM_B200_LIB") or os.path.join(HERE, "libgdm_b200.so")
 
 
 class GdmError(RuntimeError):

@@ -1298,11 +1298,14 @@ int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *s
   vd.d    = o.host_dst;
   vs.owns = vd.owns = false;
   const Layout &L = sys.L;
-  if (o.kernel_used == GDM_KERNEL_FUSED && L.n_ranks == 1 && !o.csr && L.ln[2] >= 16 * L.p &&
+  const int own_lo = L.own0 - L.loc0, own_hi = L.own1 - L.loc0; // owned planes (local indices); the host buffers hold these
+  if (o.kernel_used == GDM_KERNEL_FUSED && !o.csr && own_hi - own_lo >= 16 * L.p &&
       !(o.periodic[0] || o.periodic[1] || o.periodic[2]))
     {
       // Pipelined over z chunks: H2D of chunk c+1, apply of the planes whose inputs have arrived and D2H
       // of finished planes overlap on three streams (PCIe is full duplex; the apply hides behind it).
+      // Several ranks: the P output planes next to a neighbouring slab need its ghost planes; they are applied after the
+      // last chunk has arrived and the ghost planes have been exchanged (one short tail instead of a serial path).
       if (!ctx.h2d_stream)
         {
           GDM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx.h2d_stream, cudaStreamNonBlocking));
@@ -1311,9 +1314,10 @@ int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *s
             for (int j = 0; j < 32; ++j)
               GDM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx.ev_pipe[i][j], cudaEventDisableTiming));
         }
-      const int    nz = L.ln[2], P = L.p;
-      const int    n_chunks = std::min(16, std::max(2, nz / (8 * P)));
-      const int    cz = (nz + n_chunks - 1) / n_chunks;
+      const int    nz = L.ln[2], P = L.p, n_own = own_hi - own_lo;
+      const bool   nb_lo = own_lo > 0, nb_hi = own_hi < nz; // neighbouring slabs (ghost planes below / above)
+      const int    n_chunks = std::min(16, std::max(2, n_own / (8 * P)));
+      const int    cz = (n_own + n_chunks - 1) / n_chunks;
       const size_t plane_host = (size_t)L.ln[0] * L.nc * L.ln[1];
       if (!o.stage_src)
         {
@@ -1324,29 +1328,44 @@ int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *s
       GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_a, ctx.stream));
       GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.h2d_stream, ctx.ev_a, 0));
       GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.d2h_stream, ctx.ev_a, 0));
-      int done = 0; // output planes [0, done) have been launched
+      // output planes [z0, z1) (local indices): apply, repack, copy to the host behind the apply
+      auto window = [&](int z0, int z1, int ev) {
+        if (z1 <= z0)
+          return;
+        fused_apply_window(o, o.host_dst, o.host_src, z0, z1);
+        launch_repack(ctx, L, o.host_dst, o.stage_dst, z0, z1, false);
+        GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_pipe[1][ev], ctx.stream));
+        GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.d2h_stream, ctx.ev_pipe[1][ev], 0));
+        GDM_CUDA_CHECK(cudaMemcpyAsync(dst_host + (size_t)(z0 - own_lo) * plane_host, o.stage_dst + (size_t)z0 * plane_host,
+                                       (size_t)(z1 - z0) * plane_host * sizeof(double), cudaMemcpyDeviceToHost, ctx.d2h_stream));
+      };
+      int done = nb_lo ? own_lo + P : own_lo; // output planes [.., done) have been launched
       for (int c = 0; c < n_chunks; ++c)
         {
-          const int c0 = c * cz, c1 = std::min(nz, c0 + cz);
+          const int c0 = own_lo + c * cz, c1 = std::min(own_hi, c0 + cz);
           if (c1 <= c0)
             break;
           // contiguous 1D copy (row-wise 2D copies of 2 KB rows reach only a fraction of the PCIe rate)
-          GDM_CUDA_CHECK(cudaMemcpyAsync(o.stage_src + (size_t)c0 * plane_host, src_host + (size_t)c0 * plane_host,
+          GDM_CUDA_CHECK(cudaMemcpyAsync(o.stage_src + (size_t)c0 * plane_host, src_host + (size_t)(c0 - own_lo) * plane_host,
                                          (size_t)(c1 - c0) * plane_host * sizeof(double), cudaMemcpyHostToDevice, ctx.h2d_stream));
           GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_pipe[0][c], ctx.h2d_stream));
           GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, ctx.ev_pipe[0][c], 0));
           launch_repack(ctx, L, o.host_src, o.stage_src, c0, c1, true);
-          const int upto = (c1 == nz) ? nz : c1 - P; // outputs whose inputs (up to +P planes) are on the device
+          // outputs whose inputs (up to +P planes) are on the device
+          const int upto = (c1 == own_hi) ? (nb_hi ? own_hi - P : own_hi) : c1 - P;
           if (upto > done)
             {
-              fused_apply_window(o, o.host_dst, o.host_src, done, upto);
-              launch_repack(ctx, L, o.host_dst, o.stage_dst, done, upto, false);
-              GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_pipe[1][c], ctx.stream));
-              GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.d2h_stream, ctx.ev_pipe[1][c], 0));
-              GDM_CUDA_CHECK(cudaMemcpyAsync(dst_host + (size_t)done * plane_host, o.stage_dst + (size_t)done * plane_host,
-                                             (size_t)(upto - done) * plane_host * sizeof(double), cudaMemcpyDeviceToHost, ctx.d2h_stream));
+              window(done, upto, c);
               done = upto;
             }
+        }
+      if (nb_lo || nb_hi)
+        {
+          comm_halo_exchange(ctx, L, o.host_src);
+          if (nb_lo)
+            window(own_lo, own_lo + P, 16);
+          if (nb_hi)
+            window(own_hi - P, own_hi, 17);
         }
       GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.d2h_stream));
       GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));

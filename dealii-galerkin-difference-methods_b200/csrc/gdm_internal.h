@@ -248,6 +248,7 @@ namespace gdm
   void *pers_plan_create(Operator &op); // nullptr: not applicable to this operator
   void  pers_plan_destroy(void *plan);
   int   pers_max_grid(const Operator &op, const void *plan);
+  int   pers_max_partials(const Operator &op, const void *plan);
   void  pers_window(const void *plan, int &cz0, int &cz1); // output planes of the whole slab (local indices)
   // output planes [oz0, oz1) (local indices); dot_partials != nullptr: CTA w leaves its share of <dot_src, A src> in
   // dot_partials[w]; returns the number of CTAs launched

@@ -48,7 +48,7 @@ namespace gdm
       double *dp = nullptr;
       if (plan.dot_cursor >= 0)
         {
-          GDM_REQUIRE(!accumulate && (size_t)(plan.dot_cursor + pers_max_grid(op, plan.pers)) <= plan.dot_cap, GDM_ERR_INTERNAL,
+          GDM_REQUIRE(!accumulate && (size_t)(plan.dot_cursor + pers_max_partials(op, plan.pers)) <= plan.dot_cap, GDM_ERR_INTERNAL,
                       "fused dot: partial buffer too small");
           dp = plan.d_dot + plan.dot_cursor;
         }
@@ -104,8 +104,8 @@ namespace gdm
     if (want_dot)
       {
         GDM_REQUIRE(!accumulate, GDM_ERR_INTERNAL, "fused dot product with accumulation");
-        // partial sums: one per CTA of the (up to three) tile launches, then one per block of the face kernel
-        const size_t need = (size_t)3 * pers_max_grid(op, plan.pers) + (size_t)constrained_rows_max_blocks(L) + 64;
+        // partial sums: one per share of the (up to three) tile launches, then one per block of the face kernel
+        const size_t need = (size_t)3 * pers_max_partials(op, plan.pers) + (size_t)constrained_rows_max_blocks(L) + 64;
         if (need > plan.dot_cap)
           {
             GDM_CUDA_CHECK(cudaDeviceSynchronize());

@@ -23,6 +23,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <cstdio>
 #include <map>
 #include <tuple>
 #include <type_traits>
@@ -80,6 +82,33 @@ namespace gdm
     {
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
     }
+
+#ifdef GDM_PERS_WATCHDOG
+    // Diagnostic build (GDM_BUILD_WATCHDOG=1, libgdm_b200_wd.so): every wait of the kernel is bounded; the first waits
+    // that time out are recorded in mapped host memory, then all waits are abandoned so that the launch ends (with wrong
+    // results) and the host can print what was being waited for.  Each CTA also publishes its progress, so a launch that
+    // hangs somewhere else can still be inspected from the host while it hangs.
+    struct WdHost
+    {
+      unsigned count, abort;
+      int      rec[64][8];    // {code, cta, warp, q, share, seq, parity, aux}
+      int      prog[2048][4]; // per CTA: {share, shares done, marker, seq}
+    };
+    __device__ __forceinline__ bool wd_try(uint32_t bar, unsigned parity)
+    {
+      unsigned ok;
+      asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+      return ok != 0u;
+    }
+#endif
 
     // ------------------------------------------------------------------ configuration
     // SPLIT_ = 1: no CTA barrier in the plane loop; the x pass -> y/z pass hand-over runs through full/empty mbarriers
@@ -152,8 +181,11 @@ namespace gdm
       int          *error;   // set if a seam wait timed out
       long long    *trace;   // diagnostic (GDM_PERS_TRACE): per share {clock cycles, SM id}
       const unsigned short *xassign; // SPLIT: x tasks of warp w at plane q of tile t: xassign[(t * XROT + q % XROT) * NW + w] (bit mask)
-      const double *dot_src; // fused dot product <src, A src>: every CTA writes its sum to dot_partials[share]
+      const double *dot_src; // fused dot product <src, A src>: the sum over the points of share w goes to dot_partials[w]
       double       *dot_partials;
+#ifdef GDM_PERS_WATCHDOG
+      WdHost       *wd;
+#endif
     };
 
     template <class C, bool HASB>
@@ -266,6 +298,56 @@ namespace gdm
         else
           cur[1] = ik + 1;
       }
+      // every mbarrier wait of the kernel goes through here (code: 1 a/r full, 2 a/r empty, 3 TMA stage)
+      __device__ __forceinline__ void wait(const uint32_t bar, const unsigned parity, [[maybe_unused]] const int code, [[maybe_unused]] const int q)
+      {
+#ifdef GDM_PERS_WATCHDOG
+        const long long t0 = clock64();
+        for (;;)
+          {
+            if (wd_try(bar, parity))
+              return;
+            // (the mapped host flag is only read once a wait is already very long: the timing of a healthy launch is
+            // that of the product build)
+            const long long dt = clock64() - t0;
+            if (dt > (1ll << 22))
+              {
+                if (*(volatile unsigned *)&g.wd->abort != 0u)
+                  return;
+                if (dt > (1ll << 28))
+                  {
+                    if (lane == 0)
+                      wd_record(code, q, (int)parity, 0);
+                    return;
+                  }
+              }
+          }
+#else
+        mbar_wait(bar, parity);
+#endif
+      }
+#ifdef GDM_PERS_WATCHDOG
+      int cur_share = -1, shares_done = 0;
+      __device__ __forceinline__ void wd_record(const int code, const int q, const int parity, const int aux)
+      {
+        const unsigned slot = atomicAdd(&g.wd->count, 1u);
+        if (slot < 64u)
+          {
+            int *r = g.wd->rec[slot];
+            r[0] = code, r[1] = (int)blockIdx.x, r[2] = warp, r[3] = q, r[4] = cur_share, r[5] = seq, r[6] = parity, r[7] = aux;
+          }
+        __threadfence_system();
+        *(volatile unsigned *)&g.wd->abort = 1u;
+      }
+      __device__ __forceinline__ void wd_progress(const int k1)
+      {
+        if (tid == 0 && blockIdx.x < 2048)
+          {
+            volatile int *pr = g.wd->prog[blockIdx.x];
+            pr[0] = cur_share, pr[1] = shares_done, pr[2] = k1, pr[3] = seq;
+          }
+      }
+#endif
       // stage / parity of the TMA ring and a/r buffers of plane sequence number q
       __device__ __forceinline__ int      stage_of(const int q) const { return q % S; }
       __device__ __forceinline__ unsigned parity_of(const int q) const { return (unsigned)(q / S) & 1u; }
@@ -285,7 +367,7 @@ namespace gdm
       {
         if constexpr (SPLIT)
           {
-            mbar_wait(bar_full(q), (unsigned)(q / NAB) & 1u);
+            wait(bar_full(q), (unsigned)(q / NAB) & 1u, 1, q);
             if (tid == ISSUE_TID)
               issue(stage_of(q));
           }
@@ -410,8 +492,8 @@ namespace gdm
         const int st = stage_of(q);
         if constexpr (SPLIT)
           if (q >= NAB)
-            mbar_wait(bar_empty(q), (unsigned)(q / NAB - 1) & 1u); // the y/z pass of plane q - NAB has released the buffer
-        mbar_wait(bar0 + 8 * st, parity_of(q));
+            wait(bar_empty(q), (unsigned)(q / NAB - 1) & 1u, 2, q); // the y/z pass of plane q - NAB has released the buffer
+        wait(bar0 + 8 * st, parity_of(q), 3, q);
         const int in_off = st * C::STAGE_DOUBLES, a_off = ab_of(q);
         if constexpr (SPLIT)
           {
@@ -640,9 +722,10 @@ namespace gdm
           }
       }
 
-      // fast planes [ka, kb): stored to dst, Toeplitz in z, followed by another plane of this job; INNER tiles touch no
-      // one-sided row in x or y and store every row and column: their plane body has no data-dependent branch
-      template <bool INNER>
+      // fast planes [ka, kb): Toeplitz in z, followed by another plane of this job; INNER tiles touch no one-sided row in
+      // x or y and store every row and column: their plane body has no data-dependent branch.  SCR: the planes are the
+      // first 2P of a job that hands its partial sums down (emitted into the scratch slot instead of dst).
+      template <bool INNER, bool SCR>
       __device__ __forceinline__ void fast_planes(JobCtx &c, const int ka, const int kb)
       {
         for (int k = ka; k < kb; ++k)
@@ -652,7 +735,15 @@ namespace gdm
             yz_acquire(seq - 1);
             yz_rows<!INNER, true>(g.Az, g.Bz, ab_of(seq - 1), c.gy_first, res);
             yz_release(seq - 1);
-            store_rows<INNER>(c.out, res, c.nst);
+            if constexpr (SCR)
+              {
+#pragma unroll
+                for (int i = 0; i < RY; ++i)
+                  __stcg(c.sp + i * TX, res[i]);
+                c.sp += TY * TX;
+              }
+            else
+              store_rows<INNER>(c.out, res, c.nst);
             if constexpr (!SPLIT)
               {
                 __syncthreads();
@@ -661,6 +752,17 @@ namespace gdm
               }
             ++seq;
             c.out += g.plane;
+          }
+        if constexpr (SCR)
+          {
+            // the partial planes of the seam are complete: raise the flag of this job
+            if constexpr (SPLIT)
+              __syncthreads();
+            if (tid == ISSUE_TID)
+              {
+                __threadfence();
+                st_release(g.flags + c.J.seam_lo, g.epoch);
+              }
           }
       }
 
@@ -720,8 +822,17 @@ namespace gdm
           break;
         jb    = __ldg(g.job_ptr + share);
         njobs = __ldg(g.job_ptr + share + 1) - jb;
+#ifdef GDM_PERS_WATCHDOG
+        cur_share = share;
+        wd_progress(-1);
+#endif
         if (njobs <= 0)
-          continue;
+          {
+            if constexpr (DOT)
+              if (tid == 0)
+                g.dot_partials[share] = 0.0;
+            continue;
+          }
         JobP Jn = load_job(jb); // next job of the compute loop (every thread); the issuer keeps its own cursor
         if (tid == ISSUE_TID)
           {
@@ -766,11 +877,20 @@ namespace gdm
             const int fb = min(c.J.k1 - 1, g.kz_hi);
             if (fb > fa)
               {
-                slow_planes(c, c.J.k0, fa);
-                if (inner)
-                  fast_planes<true>(c, fa, fb);
+                if (c.J.seam_lo >= 0 && c.J.k0 >= g.kz_lo && fa == c.k_scr)
+                  {
+                    // the 2P partial planes of the seam run the fast body as well
+                    if (inner)
+                      fast_planes<true, true>(c, c.J.k0, c.k_scr);
+                    else
+                      fast_planes<false, true>(c, c.J.k0, c.k_scr);
+                  }
                 else
-                  fast_planes<false>(c, fa, fb);
+                  slow_planes(c, c.J.k0, fa);
+                if (inner)
+                  fast_planes<true, false>(c, fa, fb);
+                else
+                  fast_planes<false, false>(c, fa, fb);
                 slow_planes(c, fb, c.J.k1);
               }
             else
@@ -786,6 +906,18 @@ namespace gdm
                     while (ld_acquire(f) != g.epoch)
                       {
                         __nanosleep(64);
+#ifdef GDM_PERS_WATCHDOG
+                        if (clock64() - t0 > (1ll << 22))
+                          {
+                            if (*(volatile unsigned *)&g.wd->abort != 0u)
+                              break;
+                            if (clock64() - t0 > (1ll << 28))
+                              {
+                                wd_record(9, c.J.seam_hi, (int)ld_acquire(f), (int)g.epoch);
+                                break;
+                              }
+                          }
+#endif
                         if (clock64() - t0 > (1ll << 32))
                           {
                             *g.error = 1;
@@ -821,6 +953,30 @@ namespace gdm
             // the last plane of the share had no x pass of a next plane: its sequence number stays free for the first
             // plane of the next share (every sequence number is used exactly once: the mbarrier phases depend on it)
             --seq;
+#ifdef GDM_PERS_WATCHDOG
+            ++shares_done;
+            wd_progress(-2);
+#endif
+            // fused dot product: one partial sum per SHARE, reduced in a fixed order (which CTA runs a share depends on
+            // the ticket order, the value of the share's sum does not: bitwise reproducible)
+            if constexpr (DOT)
+              {
+                double *red = smem + OFF_MISC + 8;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                  dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+                if (lane == 0)
+                  red[warp] = dsum;
+                dsum = 0.0;
+                __syncthreads(); // (the barrier at the top of the share loop separates this use of red[] from the next)
+                if (tid == 0)
+                  {
+                    double t = 0.0;
+                    for (int w = 0; w < C::NW; ++w)
+                      t += red[w];
+                    g.dot_partials[share] = t;
+                  }
+              }
           } // shares
         if (g.trace != nullptr && tid == 0)
           {
@@ -828,23 +984,6 @@ namespace gdm
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             g.trace[2 * blockIdx.x]     = clock64() - t_start;
             g.trace[2 * blockIdx.x + 1] = (long long)smid;
-          }
-        if constexpr (DOT)
-          {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-              dsum += __shfl_down_sync(0xffffffffu, dsum, o);
-            __syncthreads(); // shared memory is no longer read by anyone
-            if (lane == 0)
-              smem[warp] = dsum;
-            __syncthreads();
-            if (tid == 0)
-              {
-                double t = 0.0;
-                for (int w = 0; w < C::NW; ++w)
-                  t += smem[w];
-                g.dot_partials[blockIdx.x] = t;
-              }
           }
       }
     };
@@ -1258,8 +1397,9 @@ namespace gdm
           }
       (void)env_L;
       // partition mode: one weighted share per CTA (static).  GDM_PERS_MODE=guided selects the self-scheduled level
-      // partition (more shares than CTAs); it is NOT a supported mode: on B200 every launch with more shares than CTAs
-      // stalled (profiles/r2/session_h_guided_stall.txt), cause not found, so it stays a diagnostic switch.
+      // partition (more shares than CTAs; the ticket order keeps it deadlock free).  Measured on B200 (profiles/r2/
+      // sessions_k_to_t.md) it balances the CTAs but loses more at the share switches (pipeline refill, seam hand-over)
+      // than it gains: 125-129 vs 133 GDoF/s; it stays a diagnostic switch.
       int         mode   = aligned ? 1 : 0;
       double      gk     = 1.0;
       int         gmin   = 8;
@@ -1496,6 +1636,7 @@ namespace gdm
       void (*kern)(const CUtensorMap, const ArgsP<P>) = nullptr;
       const bool dot = dot_partials != nullptr;
       GDM_REQUIRE(!(dot && accumulate), GDM_ERR_INTERNAL, "fused dot product with accumulation");
+      GDM_REQUIRE(!dot || part.n_shares <= pers_max_partials(op, &plan), GDM_ERR_INTERNAL, "fused dot product: too many shares");
       if (dot)
         kern = kron3d_pers_kernel<C, MODE, false, true>;
       else if (accumulate)
@@ -1510,6 +1651,15 @@ namespace gdm
           GDM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           attr = true;
         }
+#ifdef GDM_PERS_WATCHDOG
+      static WdHost *wd_host = nullptr;
+      if (!wd_host)
+        {
+          GDM_CUDA_CHECK(cudaHostAlloc(&wd_host, sizeof(WdHost), cudaHostAllocMapped));
+          memset(wd_host, 0, sizeof(WdHost));
+        }
+      GDM_CUDA_CHECK(cudaHostGetDevicePointer(&a.wd, wd_host, 0));
+#endif
       part.epoch += 1;
       a.epoch       = part.epoch;
       a.ticket_base = part.ticket_base;
@@ -1518,6 +1668,33 @@ namespace gdm
       kern<<<part.grid, C::THREADS, smem, stream>>>(map, a);
       ctx.launches++;
       GDM_CUDA_CHECK(cudaGetLastError());
+#ifdef GDM_PERS_WATCHDOG
+      {
+        // wait for the launch (up to 20 s); print what the kernel recorded and, if it still runs, where every CTA stands
+        const double t0   = (double)clock() / CLOCKS_PER_SEC;
+        bool         done = false;
+        while (!(done = (cudaStreamQuery(stream) == cudaSuccess)) && (double)clock() / CLOCKS_PER_SEC - t0 < 20.0)
+          {}
+        volatile WdHost *w   = wd_host;
+        const unsigned   cnt = w->count;
+        if (!done || cnt > 0)
+          {
+            fprintf(stderr, "[gdm watchdog] launch %u of partition (%d shares, grid %d): %s, %u waits timed out\n", part.epoch, part.n_shares,
+                    part.grid, done ? "finished" : "STILL RUNNING after 20 s", cnt);
+            for (unsigned i = 0; i < std::min(cnt, 64u); ++i)
+              fprintf(stderr, "  wait code %d (1 full, 2 empty, 3 tma, 9 seam flag) cta %d warp %d q %d share %d seq %d parity/flag %d aux %d\n",
+                      w->rec[i][0], w->rec[i][1], w->rec[i][2], w->rec[i][3], w->rec[i][4], w->rec[i][5], w->rec[i][6], w->rec[i][7]);
+            for (int b = 0; b < std::min(part.grid, 2048); ++b)
+              fprintf(stderr, "  cta %d: share %d, %d shares done, marker %d, seq %d\n", b, w->prog[b][0], w->prog[b][1], w->prog[b][2],
+                      w->prog[b][3]);
+            fflush(stderr);
+            if (!done)
+              abort();
+            memset(wd_host, 0, sizeof(WdHost));
+            throw Error(GDM_ERR_INTERNAL, "persistent kernel watchdog: a wait timed out (see stderr)");
+          }
+      }
+#endif
       if (part.d_trace != nullptr) // diagnostic: per-share cycles and SM of this launch -> file named by GDM_PERS_TRACE
         {
           GDM_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1531,7 +1708,7 @@ namespace gdm
               fclose(f);
             }
         }
-      return part.grid;
+      return part.n_shares;
     }
   } // namespace
 
@@ -1928,7 +2105,14 @@ namespace gdm
     return slots;
   }
 
-  // output planes [oz0, oz1) (local indices, clipped to the plan's window); returns the number of CTAs launched
+  // upper bound of the number of shares (= fused-dot partial sums) of one launch
+  int pers_max_partials(const Operator &op, const void *p)
+  {
+    return std::max(pers_max_grid(op, p), 8192);
+  }
+
+  // output planes [oz0, oz1) (local indices, clipped to the plan's window); returns the number of shares of the launch
+  // (= the number of fused-dot partial sums it wrote)
   int pers_launch(Operator &op, void *p, double *dst, const double *src, bool accumulate, int oz0, int oz1, cudaStream_t stream,
                   const double *dot_src, double *dot_partials, int slots_limit)
   {
