@@ -6,9 +6,9 @@
 // Replaces the assembled SparseMatrix::vmult of the reference (343 nnz/row at p=3: tests/poisson_02_gdm.cc:215,
 // applications/wave/include/gdm/wave/problem.h:486-488).  This file decides what is launched where:
 //   * one GPU: the constrained-row (Dirichlet face) kernel runs beside the tile kernel on the second stream;
-//   * several GPUs (slab partition, include/gdm/system.h:720-757): the ghost import runs on the communication stream,
-//     the slab-face planes are launched behind it with a small share of the CTA slots, the interior planes run at once
-//     on the main stream with the remaining slots, so the faces find free slots the moment the ghosts arrive;
+//   * several GPUs (slab partition, include/gdm/system.h:720-757): the ghost import (NCCL send/recv of p contiguous
+//     planes per neighbour) runs first, then one launch over all owned planes; an overlapped schedule (slab faces
+//     behind the exchange, interior planes at once) is kept behind GDM_FUSED_OVERLAP=1, it measured slower;
 //   * periodic directions: C^T A C x = fold(A(dup x)): the input is patched in place (node N := node 0),
 //     the tile kernel applies the plain one-sided operator, rows N are folded into rows 0 and the input is restored;
 //   * fused dot product <src, A src> (CG: p . A p): per-CTA partial sums of the tile launches + the face kernel, summed
@@ -136,7 +136,13 @@ namespace gdm
       {
         // overlap the ghost import (NCCL on the comm stream) with the planes that do not need it
         const int  lo = L.own0 - L.loc0, hi = L.own1 - L.loc0; // owned planes (local indices)
-        const bool thick = (hi - lo) > 4 * P;
+        // Default: ghost import first, then ONE launch over all planes (0.155 ms per apply on 2 B200 at 257^3 per GPU).
+        // GDM_FUSED_OVERLAP=1 selects the overlapped schedule below (slab faces behind the exchange on the communication
+        // stream, interior planes on the main stream).  With a persistent kernel that fills every CTA slot it is SLOWER
+        // (0.30 ms, profiles/r2/session_v_2gpu.txt): the face launches redo 2p ramp planes for p output planes on a
+        // handful of slots, and NCCL's copy kernels compete with the resident CTAs for an SM.
+        const char *env_ov = std::getenv("GDM_FUSED_OVERLAP");
+        const bool  thick  = (hi - lo) > 4 * P && (env_ov && env_ov[0] == '1');
         GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_a, ctx.stream));
         GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.comm_stream, ctx.ev_a, 0));
         comm_halo_exchange(ctx, L, const_cast<double *>(src), ctx.comm_stream);
