@@ -78,6 +78,8 @@ namespace gdm
       cudaFree(d_partials);
     if (d_sums)
       cudaFree(d_sums);
+    if (d_cg_status)
+      cudaFree(d_cg_status);
     if (d_counters)
       cudaFree(d_counters);
     if (h_pinned)
@@ -537,6 +539,23 @@ int gdm_system_create(gdm_context_t ctx, const gdm_system_desc *desc, gdm_system
   make_layout(*desc, s->impl.L);
   GDM_REQUIRE(desc->n_ranks == 1 || ctx->impl.device < 0 || ctx->impl.n_ranks == desc->n_ranks, GDM_ERR_INVALID,
               "system n_ranks does not match the context communicator (call gdm_context_comm_init first)");
+  GDM_REQUIRE(desc->n_ranks == 1 || ctx->impl.device < 0 || ctx->impl.rank == desc->rank, GDM_ERR_INVALID,
+              "system rank does not match the rank of the context communicator");
+  if (desc->n_ranks > 1 && ctx->impl.device >= 0) // (description-only contexts never exchange)
+    {
+      // every rank checks EVERY slab: a slab thinner than the ghost zone must fail identically on all ranks, not only
+      // on the rank that owns it (its neighbours would otherwise enter the exchange and wait for it forever)
+      for (int r = 0; r < desc->n_ranks; ++r)
+        {
+          gdm_system_desc dr = *desc;
+          dr.rank            = r;
+          Layout Lr;
+          make_layout(dr, Lr);
+          const int own = Lr.own1 - Lr.own0;
+          GDM_REQUIRE(own <= 0 || own >= Lr.ghost, GDM_ERR_NOT_IMPLEMENTED,
+                      "slab of rank " + std::to_string(r) + " is thinner than the ghost zone: use fewer ranks or a larger grid");
+        }
+    }
   *out = s.release();
   GDM_CATCH
 }

@@ -452,17 +452,17 @@ namespace gdm
     CgK      k;
   };
 
+  // one status record per context, reused by every solve (no cudaMalloc / cudaFree -- which synchronises the device --
+  // per solve: the RK loops do four mass solves per step)
   void *cg_status_alloc(Context &ctx)
   {
-    CgStatus *d;
-    GDM_CUDA_CHECK(cudaMalloc(&d, sizeof(CgStatus)));
-    GDM_CUDA_CHECK(cudaMemsetAsync(d, 0, sizeof(CgStatus), ctx.stream));
-    return d;
+    if (!ctx.d_cg_status)
+      GDM_CUDA_CHECK(cudaMalloc(&ctx.d_cg_status, sizeof(CgStatus)));
+    GDM_CUDA_CHECK(cudaMemsetAsync(ctx.d_cg_status, 0, sizeof(CgStatus), ctx.stream));
+    return ctx.d_cg_status;
   }
-  void cg_status_free(void *p)
-  {
-    cudaFree(p);
-  }
+  void cg_status_free(void *)
+  {}
   void cg_status_read(Context &ctx, void *d_status, int &done, unsigned &last_step, double &last_value, double &initial)
   {
     CgStatus *h = reinterpret_cast<CgStatus *>(ctx.h_pinned + 8);

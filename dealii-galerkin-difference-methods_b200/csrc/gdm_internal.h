@@ -91,6 +91,7 @@ namespace gdm
     // reduction scratch
     double  *d_partials = nullptr; // [n_slots][max_blocks]
     double  *d_sums = nullptr;     // small array of device scalars
+    void    *d_cg_status = nullptr; // status record of the CG solves (blas1.cu)
     unsigned *d_counters = nullptr;
     double  *h_pinned = nullptr;   // pinned host mirror for scalars
     size_t   partial_capacity = 0;
