@@ -86,6 +86,8 @@ namespace gdm
       cudaFreeHost(h_pinned);
     if (comm_stream)
       cudaStreamDestroy(comm_stream);
+    if (face_stream)
+      cudaStreamDestroy(face_stream);
     if (h2d_stream)
       {
         cudaStreamDestroy(h2d_stream);
@@ -450,6 +452,9 @@ int gdm_context_create(int device, void *stream, gdm_context_t *out)
     int lo_prio = 0, hi_prio = 0;
     GDM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
     GDM_CUDA_CHECK(cudaStreamCreateWithPriority(&ctx.comm_stream, cudaStreamNonBlocking, hi_prio));
+    // lowest priority: the constrained-row (face) kernel of an apply must not take CTA slots from the persistent tile
+    // kernel at its start; its blocks run as the first tile CTAs retire (kron3d.cu)
+    GDM_CUDA_CHECK(cudaStreamCreateWithPriority(&ctx.face_stream, cudaStreamNonBlocking, lo_prio));
   }
   GDM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx.ev_a, cudaEventDisableTiming));
   GDM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx.ev_b, cudaEventDisableTiming));
@@ -1335,7 +1340,9 @@ int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *s
         }
       const int    nz = L.ln[2], P = L.p, n_own = own_hi - own_lo;
       const bool   nb_lo = own_lo > 0, nb_hi = own_hi < nz; // neighbouring slabs (ghost planes below / above)
-      const int    n_chunks = std::min(16, std::max(2, n_own / (8 * P)));
+      // chunks of about 4p planes: the first H2D chunk and the last D2H chunk are the only transfers nothing overlaps
+      // with (21 chunks at 257 planes, p = 3; event slots 28 and 29 serve the slab-face windows)
+      const int    n_chunks = std::min(28, std::max(2, n_own / (4 * P)));
       const int    cz = (n_own + n_chunks - 1) / n_chunks;
       const size_t plane_host = (size_t)L.ln[0] * L.nc * L.ln[1];
       if (!o.stage_src)
@@ -1382,9 +1389,9 @@ int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *s
         {
           comm_halo_exchange(ctx, L, o.host_src);
           if (nb_lo)
-            window(own_lo, own_lo + P, 16);
+            window(own_lo, own_lo + P, 28);
           if (nb_hi)
-            window(own_hi - P, own_hi, 17);
+            window(own_hi - P, own_hi, 29);
         }
       GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.d2h_stream));
       GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));

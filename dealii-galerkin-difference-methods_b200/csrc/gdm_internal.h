@@ -83,6 +83,7 @@ namespace gdm
     int          device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t comm_stream = nullptr;
+    cudaStream_t face_stream = nullptr; // lowest priority (constrained-row kernel beside the persistent tile kernel)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr; // host-buffer pipeline (created on first use)
     cudaEvent_t  ev_pipe[2][32] = {};
     cudaEvent_t  ev_a = nullptr, ev_b = nullptr;

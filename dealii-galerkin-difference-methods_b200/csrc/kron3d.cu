@@ -173,12 +173,21 @@ namespace gdm
     else
       {
         // Dirichlet faces (skipped by the tiles) and deal.II's constrained diagonal: disjoint outputs, so the small face
-        // kernel runs beside the tile kernel on the second stream instead of after it
+        // kernel runs beside the tile kernel.  The tile kernel is launched FIRST and the face kernel goes to a stream of
+        // the lowest priority: the persistent CTAs take every slot at once and the face blocks run as the first CTAs
+        // retire (in the tail of the launch).  Launched first on a high-priority stream, as in round 1, the face blocks
+        // delayed a few persistent CTAs and with them the whole launch (0.128 vs 0.120 ms, profiles/r2/launches_bench.csv).
+        const char *env_fo = std::getenv("GDM_FACE_ORDER");
+        const bool  first  = env_fo && env_fo[0] == 'f'; // diagnostic: the round-1 order
         GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_a, ctx.stream));
-        GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.comm_stream, ctx.ev_a, 0));
-        face_blocks = launch_constrained_rows(ctx, L, op, dst, src, accumulate, -1, -1, face_partials, ctx.comm_stream);
-        GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_b, ctx.comm_stream));
-        launch_tiles(op, plan, dst, src, accumulate, plan.cz0, plan.cz1, ctx.stream, 0);
+        cudaStream_t fs = first ? ctx.comm_stream : ctx.face_stream;
+        if (!first)
+          launch_tiles(op, plan, dst, src, accumulate, plan.cz0, plan.cz1, ctx.stream, 0);
+        GDM_CUDA_CHECK(cudaStreamWaitEvent(fs, ctx.ev_a, 0));
+        face_blocks = launch_constrained_rows(ctx, L, op, dst, src, accumulate, -1, -1, face_partials, fs);
+        GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_b, fs));
+        if (first)
+          launch_tiles(op, plan, dst, src, accumulate, plan.cz0, plan.cz1, ctx.stream, 0);
         GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, ctx.ev_b, 0));
         finish_dot();
         return;
