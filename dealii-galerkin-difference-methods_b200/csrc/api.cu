@@ -100,6 +100,8 @@ namespace gdm
       cudaEventDestroy(ev_a);
     if (ev_b)
       cudaEventDestroy(ev_b);
+    if (ev_c)
+      cudaEventDestroy(ev_c);
   }
 
   Vector::~Vector()
@@ -458,6 +460,7 @@ int gdm_context_create(int device, void *stream, gdm_context_t *out)
   }
   GDM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx.ev_a, cudaEventDisableTiming));
   GDM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx.ev_b, cudaEventDisableTiming));
+  GDM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx.ev_c, cudaEventDisableTiming));
   *out = c.release();
   GDM_CATCH
 }
@@ -1340,9 +1343,9 @@ int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *s
         }
       const int    nz = L.ln[2], P = L.p, n_own = own_hi - own_lo;
       const bool   nb_lo = own_lo > 0, nb_hi = own_hi < nz; // neighbouring slabs (ghost planes below / above)
-      // chunks of about 4p planes: the first H2D chunk and the last D2H chunk are the only transfers nothing overlaps
-      // with (21 chunks at 257 planes, p = 3; event slots 28 and 29 serve the slab-face windows)
-      const int    n_chunks = std::min(28, std::max(2, n_own / (4 * P)));
+      // chunks of about 8p planes (4p planes measured no faster: 4.46 vs 4.58 GDoF/s; the PCIe rate of the box with both
+      // directions busy bounds the path at 6.2 GDoF/s, tools/pcie_probe.py); event slots 28 and 29: slab-face windows
+      const int    n_chunks = std::min(28, std::max(2, n_own / (8 * P)));
       const int    cz = (n_own + n_chunks - 1) / n_chunks;
       const size_t plane_host = (size_t)L.ln[0] * L.nc * L.ln[1];
       if (!o.stage_src)

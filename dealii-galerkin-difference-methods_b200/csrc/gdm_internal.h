@@ -87,6 +87,7 @@ namespace gdm
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr; // host-buffer pipeline (created on first use)
     cudaEvent_t  ev_pipe[2][32] = {};
     cudaEvent_t  ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t  ev_c = nullptr; // face kernel done (kron3d.cu, several ranks)
     int          sm_count = 148;
     uint64_t     launches = 0;
     // reduction scratch
@@ -251,6 +252,7 @@ namespace gdm
   void  pers_plan_destroy(void *plan);
   int   pers_max_grid(const Operator &op, const void *plan);
   int   pers_max_partials(const Operator &op, const void *plan);
+  void  pers_tune(Operator &op, void *plan); // plan search at operator creation (measured; kron3d_pers.cu)
   void  pers_window(const void *plan, int &cz0, int &cz1); // output planes of the whole slab (local indices)
   // output planes [oz0, oz1) (local indices); dot_partials != nullptr: CTA w leaves its share of <dot_src, A src> in
   // dot_partials[w]; returns the number of CTAs launched

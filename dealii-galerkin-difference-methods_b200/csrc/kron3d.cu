@@ -73,6 +73,7 @@ namespace gdm
     plan->pers = pers_plan_create(op);
     GDM_REQUIRE(plan->pers != nullptr, GDM_ERR_INTERNAL, "fused kernel: plan creation failed for a supported operator");
     pers_window(plan->pers, plan->cz0, plan->cz1);
+    pers_tune(op, plan->pers);
   }
 
   void fused_plan_destroy(Operator &op)
@@ -164,8 +165,21 @@ namespace gdm
         else
           {
             GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_b, ctx.comm_stream));
+            if (!periodic)
+              {
+                // the constrained rows only read owned values: their kernel runs while the ghost planes are in flight
+                GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.face_stream, ctx.ev_a, 0));
+                face_blocks = launch_constrained_rows(ctx, L, op, dst, src, accumulate, -1, -1, face_partials, ctx.face_stream);
+                GDM_CUDA_CHECK(cudaEventRecord(ctx.ev_c, ctx.face_stream));
+              }
             GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, ctx.ev_b, 0));
             launch_tiles(op, plan, dst, src, accumulate, plan.cz0, plan.cz1, ctx.stream, 0);
+            if (!periodic)
+              {
+                GDM_CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, ctx.ev_c, 0));
+                finish_dot();
+                return;
+              }
           }
       }
     else if (periodic)

@@ -171,6 +171,9 @@ namespace gdm
       const double *tabAx, *tabBx, *tabAy, *tabBy; // row tables [node][2P+1]
       double        Ax[P + 1], Bx[P + 1], Ay[P + 1], By[P + 1]; // interior taps by distance
       double        Az[2 * P + 1], Bz[2 * P + 1];               // interior scatter row, scale folded in
+      // one-sided rows of A/B in x and y (row class c: node c for c <= P, node N-P+(c-P-1) above): in the constant bank,
+      // the row class is warp-uniform where they are used
+      double        tbx[2][2 * (P + 1)][2 * P + 1], tby[2][2 * (P + 1)][2 * P + 1];
       double        sigma;                                      // tap split: sum_d alpha_d
       const double *zt;                                         // scatter rows of the non-Toeplitz plane classes [class][field][W+1]
       const JobP   *jobs;
@@ -447,8 +450,8 @@ namespace gdm
                     if ((gxx <= P || gxx >= g.nx - P) && gxx >= 0 && gxx <= g.nx)
                       {
                         const int     rc = (gxx <= P) ? gxx : gxx - (g.nx - P) + P + 1;
-                        const double *ta = smem + OFF_TB + (0 * NBT + rc) * WP;
-                        const double *tb = smem + OFF_TB + (1 * NBT + rc) * WP;
+                        const double *ta = g.tbx[0][rc];
+                        const double *tb = g.tbx[1][rc];
                         // two partial sums per row: the one-sided rows sit on the critical path of their warp
                         double ra = 0.0, rbv = 0.0, ra2 = 0.0, rbv2 = 0.0;
 #pragma unroll
@@ -587,8 +590,8 @@ namespace gdm
                   if ((gy <= P || gy >= g.ny - P) && gy <= g.ny)
                     {
                       const int     rc = (gy <= P) ? gy : gy - (g.ny - P) + P + 1;
-                      const double *ta = smem + OFF_TB + (2 * NBT + rc) * WP;
-                      const double *tb = smem + OFF_TB + (3 * NBT + rc) * WP;
+                      const double *ta = g.tby[0][rc];
+                      const double *tb = g.tby[1][rc];
                       t1 = 0.0;
                       t2 = 0.0;
                       double t1b = 0.0, t2b = 0.0, t2c = 0.0, t2d = 0.0; // independent partial sums (short chains)
@@ -1043,6 +1046,8 @@ namespace gdm
       double  *d_Ae[2] = {nullptr, nullptr};
       double  *d_Be[2] = {nullptr, nullptr};
       unsigned short *d_xassign = nullptr; // SPLIT configurations: x task masks [tile][rotation][warp]
+      int      wx = 1300, wy = 1400, wxy = 1600; // per-mille plane cost of tiles with one-sided rows in x / y / both
+      bool     tuned = false;
       bool     periodic[3] = {false, false, false};
       double  *d_save = nullptr; // periodic: saved values of the patched nodes
       int64_t  n_save = 0;
@@ -1382,7 +1387,8 @@ namespace gdm
       // cost of a plane per tile (per mille of an interior tile): tiles that touch one-sided rows in x / y or store
       // partial rows run the general plane body and wait for the warps that recompute the boundary rows
       // (measured on B200, profiles/r2/pers_trace_*.txt).  GDM_PERS_WEIGHTS="x,y,xy" overrides (per mille).
-      int wx = 1250, wy = 1250, wxy = 1400;
+      // Defaults in PersPlan; pers_tune() replaces them at operator creation by the best of a few measured candidates.
+      int wx = plan.wx, wy = plan.wy, wxy = plan.wxy;
       if (const char *env = std::getenv("GDM_PERS_WEIGHTS"))
         sscanf(env, "%d,%d,%d", &wx, &wy, &wxy);
       const Layout    &L = op.sys->L;
@@ -1594,6 +1600,19 @@ namespace gdm
       a.tabBx    = plan.d_Be[0];
       a.tabBy    = plan.d_Be[1];
       a.sigma    = plan.sigma;
+      for (int d = 0; d < 2; ++d)
+        for (int f = 0; f < 2; ++f)
+          for (int c = 0; c < 2 * (P + 1); ++c)
+            {
+              const int n    = L.N[d];
+              const int node = (c <= P) ? c : n - P + (c - P - 1);
+              for (int t = 0; t < W; ++t)
+                {
+                  const std::vector<double> &tab = f ? plan.hBe[d] : plan.hAe[d];
+                  const double               v   = (f == 0 || op.has_B) ? tab[(size_t)node * W + t] : 0.0;
+                  (d == 0 ? a.tbx : a.tby)[f][c][t] = v;
+                }
+            }
       a.zt       = plan.d_zt;
       a.jobs     = part.d_jobs;
       a.job_ptr  = part.d_ptr;
@@ -2103,6 +2122,75 @@ namespace gdm
     if (const char *env = std::getenv("GDM_PERS_SLOTS"))
       slots = std::max(slots, atoi(env));
     return slots;
+  }
+
+  // Plan search at operator creation (never inside an apply): the time of a launch is a jagged function of the plane
+  // costs the static partition assumes for edge tiles (132 ... 145 GDoF/s over nine nearby weight triples at 257^3,
+  // profiles/r2/session_z2_weights.txt), because the cost of a share depends on the CTA it shares an SM with.  So a few
+  // candidate triples are measured on two scratch vectors (median of 5 launches each after 2 warm-up launches) and the
+  // fastest is kept.  Only for windows large enough to be cut into shares; GDM_PERS_TUNE=0 or GDM_PERS_WEIGHTS disable it
+  // (the partition, and with it the last bits of the result, then no longer depend on a measurement).
+  void pers_tune(Operator &op, void *p)
+  {
+    PersPlan     &plan = *static_cast<PersPlan *>(p);
+    Context      &ctx  = *op.sys->ctx;
+    const Layout &L    = op.sys->L;
+    const char   *env  = std::getenv("GDM_PERS_TUNE");
+    if ((env && env[0] == '0') || std::getenv("GDM_PERS_WEIGHTS") || plan.tuned)
+      return;
+    plan.tuned           = true;
+    const int64_t tiles  = (int64_t)plan.tiles_x * plan.tiles_y;
+    const int64_t work   = tiles * std::max(0, plan.in_hi - plan.in_lo);
+    const int     slots  = pers_max_grid(op, p);
+    if (tiles < 8 || slots < tiles || work < (int64_t)24 * slots || plan.cz1 - plan.cz0 < 16 * L.p)
+      return;
+    static const int cand[][3] = {{1300, 1400, 1600}, {1250, 1250, 1400}, {1450, 1450, 1650}, {1400, 1400, 1550},
+                                  {1250, 1350, 1450}, {1550, 1550, 1750}, {1300, 1300, 1450}, {1150, 1150, 1250}};
+    auto clear_parts = [&]() {
+      GDM_CUDA_CHECK(cudaDeviceSynchronize());
+      for (auto &kv : plan.parts)
+        PersPlan::free_part(kv.second);
+      plan.parts.clear();
+    };
+    double *src = ctx.acquire((size_t)L.size), *dst = ctx.acquire((size_t)L.size);
+    GDM_CUDA_CHECK(cudaMemsetAsync(src, 0, (size_t)L.size * sizeof(double), ctx.stream));
+    cudaEvent_t e0, e1;
+    GDM_CUDA_CHECK(cudaEventCreate(&e0));
+    GDM_CUDA_CHECK(cudaEventCreate(&e1));
+    int    best = 0;
+    double best_ms = 1e30;
+    const bool verbose = std::getenv("GDM_FUSED_VERBOSE") != nullptr;
+    for (int c = 0; c < (int)(sizeof(cand) / sizeof(cand[0])); ++c)
+      {
+        plan.wx = cand[c][0], plan.wy = cand[c][1], plan.wxy = cand[c][2];
+        clear_parts();
+        float ms[5];
+        for (int i = -2; i < 5; ++i)
+          {
+            GDM_CUDA_CHECK(cudaEventRecord(e0, ctx.stream));
+            pers_launch(op, p, dst, src, false, plan.cz0, plan.cz1, ctx.stream, nullptr, nullptr, 0);
+            GDM_CUDA_CHECK(cudaEventRecord(e1, ctx.stream));
+            GDM_CUDA_CHECK(cudaEventSynchronize(e1));
+            if (i >= 0)
+              GDM_CUDA_CHECK(cudaEventElapsedTime(&ms[i], e0, e1));
+          }
+        std::sort(ms, ms + 5);
+        if (verbose)
+          fprintf(stderr, "[gdm] plan search: edge-tile plane costs %d,%d,%d -> %.4f ms (median of 5)\n", cand[c][0], cand[c][1],
+                  cand[c][2], ms[2]);
+        if (ms[2] < best_ms)
+          {
+            best_ms = ms[2];
+            best    = c;
+          }
+      }
+    plan.wx = cand[best][0], plan.wy = cand[best][1], plan.wxy = cand[best][2];
+    clear_parts();
+    ctx.launches -= 7 * (int)(sizeof(cand) / sizeof(cand[0])); // (the search is not part of any apply)
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx.release(src);
+    ctx.release(dst);
   }
 
   // upper bound of the number of shares (= fused-dot partial sums) of one launch
