@@ -454,6 +454,11 @@ class SparseMatrix:
         """dst = A^T src (`SparseMatrix::Tvmult`): vmult for mass/stiffness, the transposed operator for advection."""
         capi.check(self.lib.gdm_operator_tvmult(self.h, dst.h, src.h))
 
+    def mass_inverse(self, dst, src):
+        """dst = M^-1 src for a mass operator on a Cartesian grid: Kronecker-direct banded line solves
+        instead of the CG / ILU / AMG mass solve of the reference's Runge-Kutta stages.  One rank."""
+        capi.check(self.lib.gdm_operator_mass_inverse(self.h, dst.h, src.h))
+
     def vmult_host(self, dst, src):
         """vmult on HOST numpy buffers (H2D, apply, D2H)."""
         src = np.ascontiguousarray(src, dtype=np.float64)

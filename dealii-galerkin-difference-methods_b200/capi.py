@@ -128,6 +128,7 @@ SIGNATURES = {
     "gdm_operator_vmult": (C.c_int, [_H, _H, _H]),
     "gdm_operator_vmult_add": (C.c_int, [_H, _H, _H]),
     "gdm_operator_tvmult": (C.c_int, [_H, _H, _H]),
+    "gdm_operator_mass_inverse": (C.c_int, [_H, _H, _H]),
     "gdm_operator_vmult_dot": (C.c_int, [_H, _H, _H, C.POINTER(C.c_double)]),
     "gdm_operator_vmult_host": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "gdm_operator_diagonal": (C.c_int, [_H, _H]),

@@ -140,6 +140,8 @@ namespace gdm
     cudaFree(stage_dst);
     if (fused)
       fused_plan_destroy(*this);
+    if (massinv)
+      massinv_destroy(*this);
   }
 
   // ------------------------------------------------------------------ layout
@@ -1406,6 +1408,18 @@ int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *s
       vector_transfer(vd, dst_host, false);
       GDM_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
     }
+  GDM_CATCH
+}
+
+int gdm_operator_mass_inverse(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src)
+{
+  GDM_TRY
+  GDM_ARG(op);
+  GDM_ARG(dst);
+  GDM_ARG(src);
+  GDM_REQUIRE(dst->impl.sys == op->impl.sys && src->impl.sys == op->impl.sys, GDM_ERR_INVALID, "vector/operator system mismatch");
+  GDM_CUDA_CHECK(cudaSetDevice(op->impl.sys->ctx->device));
+  massinv_apply(op->impl, dst->impl.d, src->impl.d);
   GDM_CATCH
 }
 

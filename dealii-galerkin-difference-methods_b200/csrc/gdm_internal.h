@@ -192,6 +192,7 @@ namespace gdm
     int     kernel_used = GDM_KERNEL_GENERIC;
     std::unique_ptr<CsrOverlay> csr;
     void   *fused = nullptr;          // FusedPlan* (kron3d.cu)
+    void   *massinv = nullptr;        // MassInvPlan* (massinv.cu), created on first use
     void   *unconstrained = nullptr;  // gdm_operator_s* of the same operator without constraints (lifting of inhomogeneous
                                       // Dirichlet values into the right-hand side), created on first use
     void   *transposed = nullptr;     // gdm_operator_s* of the transposed advection operator (Tvmult), created on first use
@@ -252,6 +253,10 @@ namespace gdm
   void  pers_plan_destroy(void *plan);
   int   pers_max_grid(const Operator &op, const void *plan);
   int   pers_max_partials(const Operator &op, const void *plan);
+  // massinv.cu: Kronecker-direct inverse of a MASS operator (banded line solves per direction)
+  bool  massinv_supported(const Operator &op);
+  void  massinv_apply(Operator &op, double *dst, const double *src);
+  void  massinv_destroy(Operator &op);
   void  pers_tune(Operator &op, void *plan); // plan search at operator creation (measured; kron3d_pers.cu)
   void  pers_window(const void *plan, int &cz0, int &cz1); // output planes of the whole slab (local indices)
   // output planes [oz0, oz1) (local indices); dot_partials != nullptr: CTA w leaves its share of <dot_src, A src> in

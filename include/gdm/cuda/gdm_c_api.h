@@ -223,6 +223,12 @@ int gdm_operator_vmult_add(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src
 /* SparseMatrix::Tvmult: dst = A^T src.  Equal to vmult for mass and stiffness; for the advection kinds the transposed
  * operator is created on first use (same velocity, scale, constraints). */
 int gdm_operator_tvmult(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src);
+/* Kronecker-direct inverse of a GDM_OP_MASS operator: dst = M^-1 src by banded line solves per direction (Cholesky of
+ * the 1D mass matrices; periodic directions through a p-node border), constrained rows: src_i / M_ii.  Replaces the
+ * CG / ILU / AMG mass solves of every Runge-Kutta stage (applications/advection/include/gdm/advection/problem.h:236-267,
+ * applications/wave/include/gdm/wave/problem.h:471-502, prototypes/advection_01_gdm.cc:208-216) where the grid is
+ * Cartesian.  One rank, no irregular rows (GDM_ERR_NOT_IMPLEMENTED otherwise); dst may alias src. */
+int gdm_operator_mass_inverse(gdm_operator_t op, gdm_vector_t dst, gdm_vector_t src);
 /* Host-buffer form of vmult (the call a deal.II user makes with host vectors):
  * copies src to the device, applies, copies dst back; synchronises. */
 /* dst = A src and *src_dot_dst = <src, dst> over all ranks (the q = A p, p.q pair of SolverCG): on the fused path the

@@ -448,6 +448,12 @@ namespace dealii
     {
       internal::check(gdm_operator_tvmult(h, dst.handle(), src.handle()));
     }
+    // dst = M^-1 src for a mass matrix on a Cartesian grid (Kronecker-direct banded line solves; replaces the
+    // preconditioned CG of applications/advection/include/gdm/advection/problem.h:236-267)
+    void mass_inverse_vmult(Vector<double> &dst, const Vector<double> &src) const
+    {
+      internal::check(gdm_operator_mass_inverse(h, dst.handle(), src.handle()));
+    }
     unsigned long long m() const { return gdm_operator_m(h); }
     unsigned long long n() const { return gdm_operator_m(h); }
     gdm_operator_t     handle() const { return h; }

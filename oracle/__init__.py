@@ -27,5 +27,6 @@ from .solvers import (ReductionControl, SolverControlNoConvergence, solver_cg,
                       ExplicitRungeKutta4, DiscreteTime)
 from .kron_apply import KronApply, kron_apply, constraint_matrices_1d
 from .vector_tools import interpolate, integrate_difference, compute_global_error
+from .mass_inverse import kron_mass_solve, bordered_solve_1d, free_matrix_1d
 
 __all__ = [n for n in dir() if not n.startswith("_")]

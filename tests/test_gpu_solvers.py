@@ -323,3 +323,75 @@ def test_wave_rk4_block_system(lib, dim, reps):
     E0 = 0.5 * float(uh @ (Ko @ uh))
     E1 = 0.5 * float(yo[n:] @ (Mo @ yo[n:]) + yo[:n] @ (Ko @ yo[:n]))
     assert abs(E1 - E0) <= 1e-3 * E0
+
+
+@pytest.mark.parametrize("dim,p,reps,bc,nc", [(3, 3, [14, 13, 15], "dirichlet", 1), (3, 5, [13, 12, 14], "periodic", 1),
+                                              (3, 3, [12, 13, 11], "mixed", 1), (3, 1, [9, 8, 7], "left", 1),
+                                              (2, 3, [15, 14], "none", 2), (2, 5, [17, 16], "periodic", 1), (1, 3, [20], "dirichlet", 1),
+                                              (3, 3, [24, 22, 20], "dirichlet", 1)])
+def test_kronecker_direct_mass_inverse(lib, dim, p, reps, bc, nc):
+    """gdm_operator_mass_inverse: banded line solves per direction against a sparse direct solve of the
+    oracle's assembled mass matrix; replaces the CG mass solve of the RK stages
+    (applications/advection/include/gdm/advection/problem.h:236-267)."""
+    import gdm_b200 as g
+    import scipy.sparse.linalg as spla
+    gs, gc, os_, oc = make_pair(dim, p, nc, reps, bc)
+    scale = 0.75
+    M = make_operator(gs, gc, "mass", scale=scale)
+    Mo = oracle_operator(os_, oc, "mass", scale=scale)
+    bh = np.random.default_rng(5).uniform(-1, 1, gs.n_dofs())
+    ref = spla.spsolve(Mo.tocsc(), bh)
+    b, x = g.Vector(gs, bh), g.Vector(gs)
+    M.mass_inverse(x, b)
+    assert rel_err(x.numpy(), ref) <= 1e-11
+    assert np.array_equal(b.numpy(), bh)
+    y = g.Vector(gs)
+    M.vmult(y, x)
+    assert rel_err(y.numpy(), bh) <= 1e-11
+    M.mass_inverse(b, b)  # in place
+    assert rel_err(b.numpy(), ref) <= 1e-11
+
+
+def test_wave_rk4_with_direct_mass_inverse(lib):
+    """The wave block system of test_wave_rk4_block_system with the CG mass solve replaced by the direct inverse: same
+    trajectory as the oracle's RK4 with exact (sparse direct) mass solves."""
+    import gdm_b200 as g
+    import scipy.sparse.linalg as spla
+    n, p = 12, 3
+    gs, gc, os_, oc = make_pair(3, p, 1, [n, n, n], "dirichlet", hi=[1.0, 1.0, 1.0])
+    M, K = make_operator(gs, gc, "mass"), make_operator(gs, gc, "stiffness")
+    Mo, Ko = oracle_operator(os_, oc, "mass"), oracle_operator(os_, oc, "stiffness")
+    lu = spla.splu(Mo.tocsc())
+    con = oc.constrained_mask(os_.n_dofs())
+    u0 = lambda pts, c: np.sin(np.pi * pts[:, 0]) * np.sin(np.pi * pts[:, 1]) * np.sin(np.pi * pts[:, 2])
+    uh = O.interpolate(os_, u0)
+    uh[con] = 0.0
+    u, v = g.Vector(gs, uh), g.Vector(gs)
+    tmp = g.Vector(gs)
+
+    def f(t, y, out):
+        out[0].equ(y[1])
+        K.vmult(tmp, y[0])
+        tmp.scale(-1.0)
+        gc.set_zero(tmp)
+        M.mass_inverse(out[1], tmp)
+
+    def fo(t, y):
+        r = -(Ko @ y[0])
+        r[con] = 0.0
+        return [y[1].copy(), lu.solve(r)]
+
+    rk = g.TimeStepping.ExplicitRungeKutta(g.TimeStepping.RK_CLASSIC_FOURTH_ORDER)
+    dt, t = 0.3 / n, 0.0
+    yo = [uh.copy(), np.zeros_like(uh)]
+    b = [1 / 6, 1 / 3, 1 / 3, 1 / 6]
+    for step in range(4):
+        t = rk.evolve_one_time_step(f, t, dt, [u, v])
+        # classical RK4 on the oracle side
+        k1 = fo(0, yo)
+        k2 = fo(0, [yo[i] + 0.5 * dt * k1[i] for i in range(2)])
+        k3 = fo(0, [yo[i] + 0.5 * dt * k2[i] for i in range(2)])
+        k4 = fo(0, [yo[i] + dt * k3[i] for i in range(2)])
+        yo = [yo[i] + dt * (b[0] * k1[i] + b[1] * k2[i] + b[2] * k3[i] + b[3] * k4[i]) for i in range(2)]
+    assert rel_err(u.numpy(), yo[0]) <= 1e-10
+    assert np.abs(v.numpy() - yo[1]).max() <= 1e-10 * max(np.abs(yo[1]).max(), 1.0)
