@@ -216,6 +216,21 @@ class System:
         capi.check(self.lib.gdm_system_sparsity_row(self.h, int(flux), int(row), cols, n.value, C.byref(n)))
         return list(cols[: n.value])
 
+    def write_matrix_to_file(self, constraints, kind, file_name, write_binary_file=False, scale=1.0, b=(0.0, 0.0, 0.0),
+                             constrained_diagonal=capi.DIAG_ASSEMBLED):
+        """`write_matrix_to_file` of the reference's eigenvalue tool (applications/wave/wave-ev.cc:93-127): the assembled
+        operator of `kind` (capi.OP_MASS, OP_STIFFNESS, ...) as "row column value" triplets in the iteration order of a
+        deal.II SparseMatrix (text, or binary uint32/uint32/double records).  Host only.  Returns the number of entries."""
+        d = capi.OperatorDesc()
+        d.kind, d.scale, d.constrained_diagonal, d.kernel = kind, float(scale), constrained_diagonal, capi.KERNEL_GENERIC
+        for i in range(3):
+            d.b[i] = float(b[i]) if i < len(b) else 0.0
+        ch = constraints._handle_for(self) if constraints is not None else None
+        n = C.c_uint64()
+        capi.check(self.lib.gdm_system_write_matrix(self.h, ch, C.byref(d), str(file_name).encode(), int(write_binary_file),
+                                                    C.byref(n)))
+        return n.value
+
     def matrix_1d(self, d, kind):
         p, n = self.fe_degree, self.n_subdivisions[d]
         band = np.zeros((n + 1, 2 * p + 1))

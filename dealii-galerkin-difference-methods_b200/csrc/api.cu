@@ -213,7 +213,7 @@ namespace gdm
   }
 
   // --------------------------------------------------------- operator tables
-  static void build_tables(Operator &op)
+  static void build_tables(Operator &op, const bool upload_to_device = true)
   {
     const Layout &L = op.sys->L;
     const int     p = L.p, W = 2 * p + 1;
@@ -319,7 +319,7 @@ namespace gdm
             op.hdiagB[d].assign(diagB.begin() + r0, diagB.begin() + r0 + nr);
           }
         auto upload = [&](const std::vector<double> &h, double *&dptr) {
-          if (h.empty())
+          if (h.empty() || !upload_to_device)
             return;
           GDM_CUDA_CHECK(cudaMalloc(&dptr, h.size() * sizeof(double)));
           GDM_CUDA_CHECK(cudaMemcpy(dptr, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -1149,6 +1149,137 @@ int gdm_operator_create(gdm_system_t sys, gdm_constraints_t c, const gdm_operato
               GDM_ERR_NOT_IMPLEMENTED,
               "periodicity along the partitioned direction with more than one rank needs the fused kernel (dim 3, scalar)");
   *out = o.release();
+  GDM_CATCH
+}
+
+// The assembled operator in the triplet format of the reference's eigenvalue tool (write_matrix_to_file,
+// applications/wave/wave-ev.cc:93-127): the entries of the SparseMatrix in its iteration order -- row by row, the
+// diagonal entry first (deal.II stores it first in the rows of a square pattern), then ascending columns -- as text
+// "row column value" lines or as binary (uint32, uint32, double) records.  The pattern is the reference's
+// create_sparsity_pattern (system.h:586-599) with constrained rows and columns kept; values come from the 1D tables.
+// Host only (works on a description-only context); one rank; no periodic directions.
+int gdm_system_write_matrix(gdm_system_t sys, gdm_constraints_t c, const gdm_operator_desc *desc, const char *file_name,
+                            int write_binary_file, uint64_t *n_entries)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(desc);
+  GDM_ARG(file_name);
+  GDM_REQUIRE(c == nullptr || (c->impl.sys == &sys->impl && c->impl.closed), GDM_ERR_INVALID, "constraints: other system or not closed");
+  const Layout &L = sys->impl.L;
+  GDM_REQUIRE(L.n_ranks == 1, GDM_ERR_NOT_IMPLEMENTED, "matrix dump: one rank");
+  Operator op;
+  op.sys  = &sys->impl;
+  op.desc = *desc;
+  for (int d = 0; d < 3; ++d)
+    {
+      op.periodic[d]     = c ? c->impl.periodic[d] : false;
+      op.dirichlet[d][0] = c ? c->impl.dirichlet[d][0] : false;
+      op.dirichlet[d][1] = c ? c->impl.dirichlet[d][1] : false;
+      GDM_REQUIRE(!op.periodic[d], GDM_ERR_NOT_IMPLEMENTED, "matrix dump: periodic directions");
+    }
+  op.has_B = desc->kind != GDM_OP_MASS;
+  build_tables(op, false);
+  const int p = L.p, W = 2 * p + 1;
+  FILE     *f = fopen(file_name, write_binary_file ? "wb" : "w");
+  GDM_REQUIRE(f != nullptr, GDM_ERR_INVALID, std::string("cannot open ") + file_name);
+  auto tap = [&](const std::vector<double> &t, int d, int i, int j) -> double {
+    const int k = j - i + p;
+    return (k < 0 || k >= W) ? 0.0 : t[(size_t)i * W + k];
+  };
+  auto split = [&](uint64_t dof, int (&idx)[3], int &comp) {
+    const uint64_t node = dof / L.nc;
+    comp                = (int)(dof % L.nc);
+    idx[0]              = (int)(node % L.nn[0]);
+    idx[1]              = (int)((node / L.nn[0]) % L.nn[1]);
+    idx[2]              = (int)(node / ((uint64_t)L.nn[0] * L.nn[1]));
+  };
+  std::vector<uint64_t> cols(4096);
+  uint64_t              total = 0;
+  for (uint64_t row = 0; row < (uint64_t)L.n_dofs_global; ++row)
+    {
+      uint64_t n = 0;
+      int      rc = gdm_system_sparsity_row(sys, 0, row, nullptr, 0, &n);
+      if (n > cols.size())
+        cols.resize(n);
+      rc = gdm_system_sparsity_row(sys, 0, row, cols.data(), cols.size(), &n);
+      if (rc != GDM_OK)
+        {
+          fclose(f);
+          return rc;
+        }
+      int ri[3], rcomp;
+      split(row, ri, rcomp);
+      bool constrained = false;
+      for (int d = 0; d < L.dim; ++d)
+        constrained |= (op.dirichlet[d][0] && ri[d] == 0) || (op.dirichlet[d][1] && ri[d] == L.N[d]);
+      auto value = [&](uint64_t col) -> double {
+        int ci[3], ccomp;
+        split(col, ci, ccomp);
+        if (constrained)
+          {
+            if (col != row || desc->constrained_diagonal != GDM_DIAG_ASSEMBLED)
+              return 0.0;
+            // sum over cells of |cell_matrix(i, i)| = |scale * diagonal of the unconstrained operator|
+            double v = 0.0;
+            if (!op.has_B)
+              {
+                v = 1.0;
+                for (int d = 0; d < L.dim; ++d)
+                  v *= op.hdiagA[d][ri[d]];
+              }
+            else
+              for (int d = 0; d < L.dim; ++d)
+                {
+                  double t = op.hdiagB[d][ri[d]];
+                  for (int e = 0; e < L.dim; ++e)
+                    if (e != d)
+                      t *= op.hdiagA[e][ri[e]];
+                  v += t;
+                }
+            return std::fabs(desc->scale * v);
+          }
+        if (ccomp != rcomp)
+          return 0.0;
+        double v = 0.0;
+        if (!op.has_B)
+          {
+            v = 1.0;
+            for (int d = 0; d < L.dim; ++d)
+              v *= tap(op.hA[d], d, ri[d], ci[d]);
+          }
+        else
+          for (int d = 0; d < L.dim; ++d)
+            {
+              double t = tap(op.hB[d], d, ri[d], ci[d]);
+              for (int e = 0; e < L.dim; ++e)
+                if (e != d)
+                  t *= tap(op.hA[e], e, ri[e], ci[e]);
+              v += t;
+            }
+        return desc->scale * v;
+      };
+      auto emit = [&](uint64_t col) {
+        const double v = value(col);
+        if (write_binary_file)
+          {
+            const unsigned int r32 = (unsigned int)row, c32 = (unsigned int)col;
+            fwrite(&r32, sizeof(unsigned int), 1, f);
+            fwrite(&c32, sizeof(unsigned int), 1, f);
+            fwrite(&v, sizeof(double), 1, f);
+          }
+        else
+          fprintf(f, "%llu %llu %g\n", (unsigned long long)row, (unsigned long long)col, v);
+        ++total;
+      };
+      emit(row); // the diagonal entry is stored first
+      for (uint64_t k = 0; k < n; ++k)
+        if (cols[k] != row)
+          emit(cols[k]);
+    }
+  fclose(f);
+  if (n_entries)
+    *n_entries = total;
   GDM_CATCH
 }
 

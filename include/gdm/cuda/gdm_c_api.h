@@ -212,6 +212,14 @@ typedef struct gdm_operator_desc {
 
 int gdm_operator_create(gdm_system_t sys, gdm_constraints_t c /* may be NULL */,
                         const gdm_operator_desc *desc, gdm_operator_t *op);
+/* write_matrix_to_file of the reference's eigenvalue tool (applications/wave/wave-ev.cc:93-127): the assembled operator
+ * (kind / scale / constrained_diagonal of desc, constraints c or NULL) as "row column value" text lines or binary
+ * (uint32, uint32, double) records, in the iteration order of a deal.II SparseMatrix (per row: diagonal first, then
+ * ascending columns; pattern of create_sparsity_pattern with constrained rows and columns kept).  Host only (also on a
+ * description-only context), one rank, no periodic directions.  n_entries may be NULL. */
+int gdm_system_write_matrix(gdm_system_t sys, gdm_constraints_t c, const gdm_operator_desc *desc, const char *file_name,
+                            int write_binary_file, uint64_t *n_entries);
+
 int gdm_operator_destroy(gdm_operator_t op);
 /* Irregular rows (cut cells, ghost penalty, Nitsche): CSR rows that REPLACE the
  * tensor-product result in those rows.  row_ids/col are global DoF indices;

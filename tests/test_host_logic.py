@@ -159,3 +159,54 @@ def test_sparsity_pattern_rows(lib, dim, p, reps, nc, flux):
         assert gs.sparsity_row(row, flux) == ref[row], row
     if dim == 3 and p == 3 and not flux:  # interior rows couple (2p+1)^3 = 343 nodes
         assert max(len(r) for r in ref) == 343
+
+
+@pytest.mark.parametrize("dim,p,reps,nc,kind,bc", [(1, 3, [9], 1, "mass", "dirichlet"), (2, 3, [7, 6], 1, "stiffness", "dirichlet"),
+                                                   (2, 1, [4, 5], 2, "mass", "none"), (3, 3, [7, 6, 8], 1, "stiffness", "dirichlet"),
+                                                   (2, 5, [11, 12], 1, "advection", "left")])
+@pytest.mark.parametrize("binary", [False, True])
+def test_write_matrix_to_file(lib, tmp_path, dim, p, reps, nc, kind, bc, binary):
+    """The triplet dump of the reference's eigenvalue tool (applications/wave/wave-ev.cc:93-127) produced on the host from
+    the 1D tables: pattern = create_sparsity_pattern, per row the diagonal first and then ascending columns (iteration
+    order of a deal.II SparseMatrix), values = the oracle's assembled operator."""
+    import gdm_b200 as g
+    import oracle as O
+    from gdm_b200 import capi
+    from helpers_cpu import make_oracle_pair
+    ctx = g.Context(device=-1)
+    gs = g.System(dim, p, nc, context=ctx)
+    hi = [1.0 + 0.25 * d for d in range(dim)]
+    gs.subdivided_hyper_rectangle(reps, [0.0] * dim, hi)
+    gc = g.AffineConstraints()
+    if bc == "dirichlet":
+        gs.make_zero_boundary_constraints(gc)
+    elif bc == "left":
+        gs.make_zero_boundary_constraints(0, gc)
+    gc.close()
+    so, co = make_oracle_pair(dim, p, nc, reps, bc)
+    bvec = [1.0, 0.15, -0.05][:dim]
+    if kind == "advection":
+        Ao = O.kron_operator(so, co, "advection", b=bvec, constrained_diagonal="zero").tocsr()
+        code, diag = capi.OP_ADVECTION, capi.DIAG_ZERO
+    else:
+        Ao = O.kron_operator(so, co, kind).tocsr()
+        code, diag = (capi.OP_MASS if kind == "mass" else capi.OP_STIFFNESS), capi.DIAG_ASSEMBLED
+    path = tmp_path / "matrix.txt"
+    n = gs.write_matrix_to_file(gc, code, path, binary, b=bvec, constrained_diagonal=diag)
+    if binary:
+        rec = np.fromfile(path, dtype=np.dtype([("r", "<u4"), ("c", "<u4"), ("v", "<f8")]))
+        rows, cols, vals = rec["r"].astype(np.int64), rec["c"].astype(np.int64), rec["v"]
+    else:
+        t = np.loadtxt(path, ndmin=2)
+        rows, cols, vals = t[:, 0].astype(np.int64), t[:, 1].astype(np.int64), t[:, 2]
+    assert len(rows) == n
+    pattern = so.create_sparsity_pattern()
+    k = 0
+    for r in range(so.n_dofs()):
+        expect = [r] + [c for c in pattern[r] if c != r]
+        assert list(cols[k:k + len(expect)]) == expect and np.all(rows[k:k + len(expect)] == r)
+        k += len(expect)
+    assert k == n
+    ref = np.asarray(Ao[rows, cols]).reshape(-1)
+    tol = 1e-14 if binary else 6e-6  # text: operator<< of a double prints 6 significant digits
+    assert np.abs(vals - ref).max() <= tol * np.abs(ref).max()
