@@ -142,10 +142,22 @@ def assemble_cell_loop(system, constraints, kind, b=None, literal=False):
     for cell in range(system.n_cells()):
         cat = system.active_fe_index(cell)
         if cat not in mats:
-            ms = cell_matrix_scalar(system, cell, kind, get, jxw, b)
             full = np.zeros((npc * nc, npc * nc))
-            for c in range(nc):
-                full[c * npc:(c + 1) * npc, c * npc:(c + 1) * npc] = ms
+            if kind == "elasticity":
+                # 2 eps(u) : eps(v) = grad u : grad v + grad u : grad v^T  (`tests/elasticity_01_gdm.cc:143-160`):
+                # block (c, d) = delta_cd sum_a (d_a phi_i, d_a phi_j) + (d_d phi_i, d_c phi_j)
+                assert nc == system.dim
+                idx = system.cell_indices(cell)
+                _, grads = get([system.variant(idx[d], d) for d in range(system.dim)])
+                lap = sum(np.einsum("q,qi,qj->ij", jxw, g, g) for g in grads)
+                for c in range(nc):
+                    for d in range(nc):
+                        blk = np.einsum("q,qi,qj->ij", jxw, grads[d], grads[c])
+                        full[c * npc:(c + 1) * npc, d * npc:(d + 1) * npc] = blk + (lap if c == d else 0.0)
+            else:
+                ms = cell_matrix_scalar(system, cell, kind, get, jxw, b)
+                for c in range(nc):
+                    full[c * npc:(c + 1) * npc, c * npc:(c + 1) * npc] = ms
             mats[cat] = full
         cm = mats[cat]
         dofs = system.get_dof_indices(cell)

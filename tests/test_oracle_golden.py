@@ -243,3 +243,38 @@ def test_kronecker_direct_mass_inverse(dim, p, reps, bc, nc):
     dirichlet, periodic = _bc_flags(dim, bc)
     x = O.kron_mass_solve(s, dirichlet, periodic, Mo.diagonal(), b)
     assert np.abs(x - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_elasticity_01_gdm_golden(golden_dir):
+    """tests/elasticity_01_gdm.cc (2D, p=3, two components coupled through 2 eps(u):eps(v), zero Dirichlet, Jacobi-CG
+    (100, 1e-10, 1e-8)): the oracle's cell loop with the vector-valued cell matrix reproduces the committed L2 error.
+    The operator is outside the hot path (no CUDA kernel for coupled components); the golden pins the oracle's
+    multi-component machinery (DoF numbering, right-hand side, integrate_difference)."""
+    import os
+    gold = open(os.path.join(golden_dir, "elasticity_01_gdm.output")).read().split()[-1]
+    n, p, a = 40, 3, np.pi
+    s = O.System(2, p, 2)
+    s.subdivided_hyper_cube(n)
+    c = O.Constraints()
+    s.make_zero_boundary_constraints(c)
+    c.close()
+    A = O.assemble_cell_loop(s, c, "elasticity")
+    assert abs(A - A.T).max() <= 1e-12 * abs(A).max()
+
+    def exact(pts, comp):
+        x, y = pts[:, 0], pts[:, 1]
+        return np.sin(a * x) ** 2 * np.cos(a * y) * np.sin(a * y) if comp == 0 else -np.cos(a * x) * np.sin(a * x) * np.sin(a * y) ** 2
+
+    def f(pts, comp):
+        x, y = pts[:, 0], pts[:, 1]
+        if comp == 0:
+            return (6 * a * a * np.sin(a * x) ** 2 * np.sin(a * y) * np.cos(a * y)
+                    - 2 * a * a * np.sin(a * y) * np.cos(a * x) ** 2 * np.cos(a * y))
+        return (-6 * a * a * np.sin(a * x) * np.sin(a * y) ** 2 * np.cos(a * x)
+                + 2 * a * a * np.sin(a * x) * np.cos(a * x) * np.cos(a * y) ** 2)
+
+    rhs = O.rhs_cell_loop(s, c, f)
+    ctl = O.ReductionControl(100, 1e-10, 1e-8)
+    u = O.solver_cg(A, np.zeros(s.n_dofs()), rhs, O.PreconditionJacobi(A), ctl)
+    err = O.compute_global_error(O.integrate_difference(s, u, exact))
+    assert "%g" % err == gold
