@@ -1478,7 +1478,9 @@ int gdm_operator_vmult_host(gdm_operator_t op, double *dst_host, const double *s
       const bool   nb_lo = own_lo > 0, nb_hi = own_hi < nz; // neighbouring slabs (ghost planes below / above)
       // chunks of about 8p planes (4p planes measured no faster: 4.46 vs 4.58 GDoF/s; the PCIe rate of the box with both
       // directions busy bounds the path at 6.2 GDoF/s, tools/pcie_probe.py); event slots 28 and 29: slab-face windows
-      const int    n_chunks = std::min(28, std::max(2, n_own / (8 * P)));
+      int          n_chunks = std::min(28, std::max(2, n_own / (8 * P)));
+      if (const char *env = std::getenv("GDM_HOST_CHUNKS")) // diagnostic
+        n_chunks = std::min(28, std::max(2, atoi(env)));
       const int    cz = (n_own + n_chunks - 1) / n_chunks;
       const size_t plane_host = (size_t)L.ln[0] * L.nc * L.ln[1];
       if (!o.stage_src)
