@@ -216,6 +216,13 @@ class System:
         capi.check(self.lib.gdm_system_sparsity_row(self.h, int(flux), int(row), cols, n.value, C.byref(n)))
         return list(cols[: n.value])
 
+    def write_vtu(self, values, label, file_name):
+        """Nodal field -> ASCII VTU (stand-in for `GDM::DataOut`, include/gdm/data_out.h): `values` = all DoFs (numpy)."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.size == self.n_dofs()
+        capi.check(self.lib.gdm_system_write_vtu(self.h, v.ctypes.data_as(C.POINTER(C.c_double)), str(label).encode(),
+                                                 str(file_name).encode()))
+
     def write_matrix_to_file(self, constraints, kind, file_name, write_binary_file=False, scale=1.0, b=(0.0, 0.0, 0.0),
                              constrained_diagonal=capi.DIAG_ASSEMBLED):
         """`write_matrix_to_file` of the reference's eigenvalue tool (applications/wave/wave-ev.cc:93-127): the assembled

@@ -123,6 +123,7 @@ SIGNATURES = {
     "gdm_vector_linfty_norm": (C.c_int, [_H, _PD]),
     "gdm_vector_update_ghost_values": (C.c_int, [_H]),
     "gdm_operator_create": (C.c_int, [_H, _H, C.POINTER(OperatorDesc), _PH]),
+    "gdm_system_write_vtu": (C.c_int, [_H, C.POINTER(C.c_double), C.c_char_p, C.c_char_p]),
     "gdm_system_write_matrix": (C.c_int, [_H, _H, C.POINTER(OperatorDesc), C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]),
     "gdm_operator_destroy": (C.c_int, [_H]),
     "gdm_operator_attach_csr": (C.c_int, [_H, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1283,6 +1283,70 @@ int gdm_system_write_matrix(gdm_system_t sys, gdm_constraints_t c, const gdm_ope
   GDM_CATCH
 }
 
+// VTU file (ASCII UnstructuredGrid) of a nodal field for visual checks: the stand-in for GDM::DataOut (include/gdm/data_out.h,
+// used at prototypes/advection_01_gdm.cc:248-255).  GDM DoFs are nodal values, so the grid cells (lines, quadrilaterals,
+// hexahedra between neighbouring nodes) carry the DoFs as point data, one array per component.  Host only: `values` holds
+// all DoFs of the system in the global numbering (gdm_vector_download on one rank).
+int gdm_system_write_vtu(gdm_system_t sys, const double *values, const char *label, const char *file_name)
+{
+  GDM_TRY
+  GDM_ARG(sys);
+  GDM_ARG(values);
+  GDM_ARG(label);
+  GDM_ARG(file_name);
+  const Layout &L = sys->impl.L;
+  FILE         *f = fopen(file_name, "w");
+  GDM_REQUIRE(f != nullptr, GDM_ERR_INVALID, std::string("cannot open ") + file_name);
+  const int64_t n_nodes = (int64_t)L.nn[0] * L.nn[1] * L.nn[2];
+  int64_t       n_cells = 1;
+  for (int d = 0; d < L.dim; ++d)
+    n_cells *= L.N[d];
+  const int npc = 1 << L.dim; // points per cell
+  fprintf(f, "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n");
+  fprintf(f, "<Piece NumberOfPoints=\"%lld\" NumberOfCells=\"%lld\">\n", (long long)n_nodes, (long long)n_cells);
+  fprintf(f, "<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n");
+  for (int k = 0; k < L.nn[2]; ++k)
+    for (int j = 0; j < L.nn[1]; ++j)
+      for (int i = 0; i < L.nn[0]; ++i)
+        fprintf(f, "%.17g %.17g %.17g\n", L.lo[0] + i * L.h[0], L.dim > 1 ? L.lo[1] + j * L.h[1] : 0.0,
+                L.dim > 2 ? L.lo[2] + k * L.h[2] : 0.0);
+  fprintf(f, "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"ascii\">\n");
+  auto node = [&](int i, int j, int k) { return (long long)i + (long long)L.nn[0] * ((long long)j + (long long)L.nn[1] * k); };
+  for (int k = 0; k < std::max(1, L.N[2]); ++k)
+    for (int j = 0; j < std::max(1, L.N[1]); ++j)
+      for (int i = 0; i < L.N[0]; ++i)
+        {
+          if (L.dim == 1)
+            fprintf(f, "%lld %lld\n", node(i, 0, 0), node(i + 1, 0, 0));
+          else if (L.dim == 2) // VTK_QUAD: counter-clockwise
+            fprintf(f, "%lld %lld %lld %lld\n", node(i, j, 0), node(i + 1, j, 0), node(i + 1, j + 1, 0), node(i, j + 1, 0));
+          else // VTK_HEXAHEDRON
+            fprintf(f, "%lld %lld %lld %lld %lld %lld %lld %lld\n", node(i, j, k), node(i + 1, j, k), node(i + 1, j + 1, k),
+                    node(i, j + 1, k), node(i, j, k + 1), node(i + 1, j, k + 1), node(i + 1, j + 1, k + 1), node(i, j + 1, k + 1));
+        }
+  fprintf(f, "</DataArray>\n<DataArray type=\"Int64\" Name=\"offsets\" format=\"ascii\">\n");
+  for (int64_t c = 1; c <= n_cells; ++c)
+    fprintf(f, "%lld\n", (long long)(c * npc));
+  fprintf(f, "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n");
+  const int vtk_type = (L.dim == 1) ? 3 : (L.dim == 2 ? 9 : 12);
+  for (int64_t c = 0; c < n_cells; ++c)
+    fprintf(f, "%d\n", vtk_type);
+  fprintf(f, "</DataArray>\n</Cells>\n<PointData>\n");
+  for (int c = 0; c < L.nc; ++c)
+    {
+      if (L.nc == 1)
+        fprintf(f, "<DataArray type=\"Float64\" Name=\"%s\" format=\"ascii\">\n", label);
+      else
+        fprintf(f, "<DataArray type=\"Float64\" Name=\"%s_%d\" format=\"ascii\">\n", label, c);
+      for (int64_t nd = 0; nd < n_nodes; ++nd)
+        fprintf(f, "%.17g\n", values[nd * L.nc + c]);
+      fprintf(f, "</DataArray>\n");
+    }
+  fprintf(f, "</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+  fclose(f);
+  GDM_CATCH
+}
+
 int gdm_operator_destroy(gdm_operator_t op)
 {
   if (op && op->impl.transposed)

@@ -288,6 +288,11 @@ int gdm_interpolate(gdm_system_t sys, gdm_function_fn f, void *user, gdm_vector_
 int gdm_integrate_difference(gdm_system_t sys, gdm_vector_t v, gdm_function_fn exact, void *user,
                              double *cellwise /* may be NULL */, double *global_l2);
 
+/* VTU file (ASCII UnstructuredGrid; point data on the grid cells, one array per component) of a nodal field: the stand-in
+ * for GDM::DataOut (include/gdm/data_out.h; prototypes/advection_01_gdm.cc:248-255) for visual checks.  Host only;
+ * values = all DoFs in the global numbering (one rank). */
+int gdm_system_write_vtu(gdm_system_t sys, const double *values, const char *label, const char *file_name);
+
 #ifdef __cplusplus
 }
 #endif

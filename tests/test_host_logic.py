@@ -210,3 +210,33 @@ def test_write_matrix_to_file(lib, tmp_path, dim, p, reps, nc, kind, bc, binary)
     ref = np.asarray(Ao[rows, cols]).reshape(-1)
     tol = 1e-14 if binary else 6e-6  # text: operator<< of a double prints 6 significant digits
     assert np.abs(vals - ref).max() <= tol * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("dim,reps,nc", [(1, [7], 1), (2, [5, 4], 2), (3, [3, 4, 2], 1)])
+def test_write_vtu(lib, tmp_path, dim, reps, nc):
+    """Stand-in for GDM::DataOut (include/gdm/data_out.h): points = nodes, cells = grid cells, DoFs as point data."""
+    import xml.etree.ElementTree as ET
+    import gdm_b200 as g
+    ctx = g.Context(device=-1)
+    gs = g.System(dim, 3, nc, context=ctx)
+    hi = [1.0 + 0.5 * d for d in range(dim)]
+    gs.subdivided_hyper_rectangle([max(r, 3) for r in reps], [0.0] * dim, hi)
+    reps = [max(r, 3) for r in reps]
+    vals = np.arange(gs.n_dofs(), dtype=float) * 0.5
+    path = tmp_path / "field.vtu"
+    gs.write_vtu(vals, "solution", path)
+    root = ET.parse(path).getroot()
+    piece = root.find("UnstructuredGrid/Piece")
+    n_nodes, n_cells = int(np.prod([r + 1 for r in reps])), int(np.prod(reps))
+    assert int(piece.get("NumberOfPoints")) == n_nodes and int(piece.get("NumberOfCells")) == n_cells
+    pts = np.array(piece.find("Points/DataArray").text.split(), dtype=float).reshape(-1, 3)
+    assert pts.shape[0] == n_nodes and abs(pts[:, 0].max() - hi[0]) < 1e-14 and (dim < 2 or abs(pts[:, 1].max() - hi[1]) < 1e-14)
+    arrays = {a.get("Name"): a for a in piece.find("Cells").findall("DataArray")}
+    conn = np.array(arrays["connectivity"].text.split(), dtype=int).reshape(n_cells, 2 ** dim)
+    assert conn.min() == 0 and conn.max() == n_nodes - 1 and all(len(set(c)) == 2 ** dim for c in conn)
+    assert set(arrays["types"].text.split()) == {str({1: 3, 2: 9, 3: 12}[dim])}
+    pd = piece.find("PointData").findall("DataArray")
+    assert len(pd) == nc
+    for c, a in enumerate(pd):
+        assert a.get("Name") == ("solution" if nc == 1 else f"solution_{c}")
+        assert np.array_equal(np.array(a.text.split(), dtype=float), vals[c::nc])
