@@ -29,7 +29,7 @@ __all__ = [
     "Context", "default_context", "System", "AffineConstraints", "Vector", "SparseMatrix", "MatrixCreator",
     "VectorTools", "SolverCG", "ReductionControl", "PreconditionIdentity", "PreconditionJacobi",
     "DiagonalMatrix", "TimeStepping", "DiscreteTime", "MappingQ1", "QGauss", "generate_polynomials_1D",
-    "ExcNotImplemented", "NoConvergence", "GdmError", "init_distributed", "capi",
+    "ExcNotImplemented", "NoConvergence", "GdmError", "init_distributed", "capi", "CutPoisson",
 ]
 
 
@@ -758,3 +758,104 @@ class VectorTools:
     def compute_global_error(triangulation, cellwise_error, norm="L2_norm"):
         """dealii::VectorTools::compute_global_error for the L2 norm (serial form)."""
         return float(np.sqrt(np.sum(np.asarray(cellwise_error) ** 2)))
+
+
+# ------------------------------------------------------------ cut-cell set-up
+class CutPoisson:
+    """Cut-cell set-up of the CutFEM Poisson problem of `prototypes/cut_poisson_01_gdm.cc` (host side).
+
+    Classifies the cells of a Cartesian grid against a Q1 level set (`:105-121`), generates the cut quadratures
+    (`:176-190`) and assembles the rows that differ from the plain stiffness operator (`:196-329`): `rows()` are the
+    arguments of `SparseMatrix.attach_csr`, `rhs()` the load vector, `l2_error_inside` the error of `:349-398`.
+
+        cut = CutPoisson(2, 3, [64, 64], [-1.21] * 2, [1.21] * 2, level_set_nodal, ghost_penalty=True)
+        A = SparseMatrix(); MatrixCreator.create_laplace_matrix(mapping, system, quadrature, A, AffineConstraints())
+        A.attach_csr(*cut.rows())
+        SolverCG(ReductionControl(n, 1e-10, 1e-6)).solve(A, u, Vector(system, cut.rhs()), PreconditionIdentity())
+    """
+    INSIDE, OUTSIDE, INTERSECTED = 0, 1, 2
+
+    def __init__(self, dim, fe_degree, n_subdivisions, lo, hi, level_set, ghost_penalty=True, ghost_parameter=0.5,
+                 nitsche_parameter=None, rhs_value=4.0, boundary_value=1.0, gp_h_power=1):
+        self.lib = capi.load()
+        d = capi.CutDesc()
+        d.dim, d.fe_degree = dim, fe_degree
+        for e in range(dim):
+            d.n_subdivisions[e] = int(n_subdivisions[e])
+            d.lo[e], d.hi[e] = float(lo[e]), float(hi[e])
+        d.ghost_penalty, d.gp_h_power = int(bool(ghost_penalty)), int(gp_h_power)
+        d.ghost_parameter = float(ghost_parameter)
+        d.nitsche_parameter = float(5.0 * (fe_degree + 1) * fe_degree if nitsche_parameter is None else nitsche_parameter)
+        d.rhs_value, d.boundary_value = float(rhs_value), float(boundary_value)
+        self.n_dofs = int(np.prod([int(n) + 1 for n in n_subdivisions[:dim]]))
+        self.n_cells = int(np.prod([int(n) for n in n_subdivisions[:dim]]))
+        level_set = np.ascontiguousarray(level_set, dtype=np.float64)
+        if level_set.size != self.n_dofs:
+            raise GdmError(capi.ERR_INVALID, f"level set has {level_set.size} values, the grid {self.n_dofs} nodes")
+        self.h = C.c_void_p()
+        capi.check(self.lib.gdm_cut_poisson_create(C.byref(d), level_set.ctypes.data_as(C.c_void_p), C.byref(self.h)))
+
+    def sizes(self):
+        """n_rows, nnz, n_identity_rows, (inside, outside, intersected) cell counts."""
+        n_rows, nnz, n_id = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        cells = (C.c_uint64 * 3)()
+        capi.check(self.lib.gdm_cut_sizes(self.h, C.byref(n_rows), C.byref(nnz), C.byref(n_id), cells))
+        return n_rows.value, nnz.value, n_id.value, tuple(int(c) for c in cells)
+
+    def rows(self):
+        n_rows, nnz, _, _ = self.sizes()
+        row_ids, rowptr = np.zeros(n_rows, dtype=np.uint64), np.zeros(n_rows + 1, dtype=np.uint64)
+        col, val = np.zeros(nnz, dtype=np.uint64), np.zeros(nnz)
+        capi.check(self.lib.gdm_cut_rows(self.h, row_ids.ctypes.data_as(C.c_void_p), rowptr.ctypes.data_as(C.c_void_p),
+                                         col.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p)))
+        return row_ids, rowptr, col, val
+
+    def rhs(self):
+        out = np.zeros(self.n_dofs)
+        capi.check(self.lib.gdm_cut_rhs(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def locations(self):
+        out = np.zeros(self.n_cells, dtype=np.uint8)
+        capi.check(self.lib.gdm_cut_locations(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def l2_error_inside(self, u, exact):
+        """exact(point[3], component) -> float."""
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        assert u.size == self.n_dofs
+        cb = VectorTools._wrap(exact)
+        err = C.c_double()
+        capi.check(self.lib.gdm_cut_l2_error_inside(self.h, u.ctypes.data_as(C.c_void_p), cb, None, C.byref(err)))
+        return err.value
+
+    @staticmethod
+    def quadrature(vertex_values, n_gauss):
+        """The generator on one unit cell: vertex_values of shape (2,)*dim indexed [x][y][z].
+        Returns (points, weights), (points, weights, normals)."""
+        lib = capi.load()
+        v = np.asarray(vertex_values, dtype=np.float64)
+        dim = v.ndim
+        flat = np.ascontiguousarray(v.transpose(*range(dim - 1, -1, -1)).ravel())  # x fastest: bit e = direction e
+        n_in, n_sf = C.c_uint64(), C.c_uint64()
+        capi.check(lib.gdm_cut_quadrature(dim, flat.ctypes.data_as(C.c_void_p), n_gauss, 0, C.byref(n_in), None, None,
+                                          C.byref(n_sf), None, None, None))
+        cap = max(n_in.value, n_sf.value, 1)
+        ip, iw = np.zeros((cap, dim)), np.zeros(cap)
+        sp, sw, sn = np.zeros((cap, dim)), np.zeros(cap), np.zeros((cap, dim))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        capi.check(lib.gdm_cut_quadrature(dim, p(flat), n_gauss, cap, C.byref(n_in), p(ip), p(iw), C.byref(n_sf),
+                                          p(sp), p(sw), p(sn)))
+        a, b = n_in.value, n_sf.value
+        return (ip[:a], iw[:a]), (sp[:b], sw[:b], sn[:b])
+
+    def _free(self):
+        if getattr(self, "h", None):
+            self.lib.gdm_cut_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass

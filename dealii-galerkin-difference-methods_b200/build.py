@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgdm_b200.so")
-SOURCES = ["api.cu", "basis.cpp", "generic.cu", "blas1.cu", "cg.cu", "rk.cu", "comm.cu", "kron3d.cu", "kron3d_pers.cu", "massinv.cu"]
+SOURCES = ["api.cu", "basis.cpp", "generic.cu", "blas1.cu", "cg.cu", "rk.cu", "comm.cu", "kron3d.cu", "kron3d_pers.cu", "massinv.cu", "cut.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -61,6 +61,13 @@ class ReductionControlC(C.Structure):
                 ("last_step", C.c_uint32), ("last_value", C.c_double), ("initial_value", C.c_double)]
 
 
+class CutDesc(C.Structure):
+    _fields_ = [("dim", C.c_int), ("fe_degree", C.c_int), ("n_subdivisions", C.c_uint32 * 3),
+                ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("ghost_penalty", C.c_int), ("gp_h_power", C.c_int),
+                ("ghost_parameter", C.c_double), ("nitsche_parameter", C.c_double), ("rhs_value", C.c_double),
+                ("boundary_value", C.c_double)]
+
+
 FUNCTION_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_int, C.c_void_p)
 RK_RHS_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p)
 
@@ -124,6 +131,15 @@ SIGNATURES = {
     "gdm_vector_update_ghost_values": (C.c_int, [_H]),
     "gdm_operator_create": (C.c_int, [_H, _H, C.POINTER(OperatorDesc), _PH]),
     "gdm_system_write_vtu": (C.c_int, [_H, C.POINTER(C.c_double), C.c_char_p, C.c_char_p]),
+    "gdm_cut_poisson_create": (C.c_int, [C.POINTER(CutDesc), C.c_void_p, _PH]),
+    "gdm_cut_destroy": (C.c_int, [_H]),
+    "gdm_cut_sizes": (C.c_int, [_H, _PU64, _PU64, _PU64, _PU64]),
+    "gdm_cut_rows": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gdm_cut_rhs": (C.c_int, [_H, C.c_void_p]),
+    "gdm_cut_locations": (C.c_int, [_H, C.c_void_p]),
+    "gdm_cut_l2_error_inside": (C.c_int, [_H, C.c_void_p, FUNCTION_FN, C.c_void_p, _PD]),
+    "gdm_cut_quadrature": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_uint64, _PU64, C.c_void_p, C.c_void_p, _PU64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "gdm_system_write_matrix": (C.c_int, [_H, _H, C.POINTER(OperatorDesc), C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]),
     "gdm_operator_destroy": (C.c_int, [_H]),
     "gdm_operator_attach_csr": (C.c_int, [_H, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -293,6 +293,46 @@ int gdm_integrate_difference(gdm_system_t sys, gdm_vector_t v, gdm_function_fn e
  * values = all DoFs in the global numbering (one rank). */
 int gdm_system_write_vtu(gdm_system_t sys, const double *values, const char *label, const char *file_name);
 
+/* ------------------------------------------------------- cut-cell set-up (host) */
+/* The step before the hot path in a CutFEM run: level-set classification, cut quadrature and the
+ * assembly of the rows that differ from the plain stiffness operator, ready for gdm_operator_attach_csr.  Host only,
+ * no context needed, scalar field, no constraints, one rank (all rows).
+ *   classification   NonMatching::MeshClassifier for a Q1 level set (prototypes/cut_poisson_01_gdm.cc:105-121)
+ *   quadrature       NonMatching::FEValues with QGauss<1>(p+1) (prototypes/cut_poisson_01_gdm.cc:176-190)
+ *   assembly         prototypes/cut_poisson_01_gdm.cc:196-329 (volume + Nitsche + ghost penalty, zero diagonal -> 1)
+ *   error            prototypes/cut_poisson_01_gdm.cc:349-398 */
+typedef struct gdm_cut_desc {
+  int      dim;               /* 1, 2, 3 */
+  int      fe_degree;         /* odd */
+  uint32_t n_subdivisions[3];
+  double   lo[3], hi[3];
+  int      ghost_penalty;     /* face_has_ghost_penalty terms on / off (cut_poisson_01_gdm.cc:123-146) */
+  int      gp_h_power;        /* 1: the prototype's scaling; 3: the wave application's matrix (wave/stiffness.h:760-765) */
+  double   ghost_parameter;   /* 0.5 */
+  double   nitsche_parameter; /* 5 (p+1) p */
+  double   rhs_value;         /* constant right-hand side f (4) */
+  double   boundary_value;    /* constant Dirichlet value g on the surface (1) */
+} gdm_cut_desc;
+typedef struct gdm_cut_s *gdm_cut_t;
+/* level_set: nodal values of the Q1 level set at the grid nodes, DoF order (x fastest); negative = inside */
+int gdm_cut_poisson_create(const gdm_cut_desc *desc, const double *level_set, gdm_cut_t *cut);
+int gdm_cut_destroy(gdm_cut_t cut);
+/* n_rows = rows to attach (band rows around the surface + identity rows of DoFs no active cell touches);
+ * n_cells_by_location[3] = inside, outside, intersected.  Any pointer may be NULL. */
+int gdm_cut_sizes(gdm_cut_t cut, uint64_t *n_rows, uint64_t *nnz, uint64_t *n_identity_rows,
+                  uint64_t *n_cells_by_location);
+/* the arguments of gdm_operator_attach_csr: row_ids[n_rows] ascending, rowptr[n_rows+1], col/val[nnz] (columns ascending) */
+int gdm_cut_rows(gdm_cut_t cut, uint64_t *row_ids, uint64_t *rowptr, uint64_t *col, double *val);
+int gdm_cut_rhs(gdm_cut_t cut, double *rhs /* n_dofs */);
+int gdm_cut_locations(gdm_cut_t cut, uint8_t *location /* n_cells: 0 inside, 1 outside, 2 intersected */);
+/* sqrt( sum over non-outside cells of the integral over the inside part of (u_h - exact)^2 ); u = all DoFs */
+int gdm_cut_l2_error_inside(gdm_cut_t cut, const double *u, gdm_function_fn exact, void *user, double *error);
+/* The quadrature generator on its own: unit cell, vertex_values[2^dim] (bit e of the index = upper end in direction e).
+ * Fills at most `capacity` points per rule (points [q*dim + e]) and returns the full counts; arrays may be NULL. */
+int gdm_cut_quadrature(int dim, const double *vertex_values, int n_gauss, uint64_t capacity, uint64_t *n_inside,
+                       double *inside_points, double *inside_weights, uint64_t *n_surface, double *surface_points,
+                       double *surface_weights, double *surface_normals);
+
 #ifdef __cplusplus
 }
 #endif

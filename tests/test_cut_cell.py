@@ -1,0 +1,172 @@
+"""Cut-cell set-up, CPU: the oracle against the reference's golden output, the product's host-side
+generator (`csrc/cut.cpp` through the C ABI) against the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle as O
+from oracle import cut
+
+
+def golden_errors(golden_dir):
+    """The two L2 errors of prototypes/cut_poisson_01_gdm.output: without and with ghost penalty."""
+    txt = open(os.path.join(golden_dir, "prototypes_cut_poisson_01_gdm.output")).read()
+    rows = re.findall(r"^\s*([0-9.]+)\s+([0-9.e+-]+)\s*$", txt, flags=re.M)
+    assert len(rows) == 2 and all(abs(float(h) - 0.0378) < 1e-4 for h, _ in rows)
+    return [float(e) for _, e in rows]
+
+
+def exact_solution(dim):
+    return lambda pts: 1.0 - 2.0 / dim * ((pts ** 2).sum(axis=1) - 1.0)  # cut_poisson_01_gdm.cc:52-64
+
+
+def sphere_problem(dim, p, n, L=1.21, R=1.0):
+    s = O.System(dim, p, 1)
+    s.subdivided_hyper_cube(n, -L, L)
+    return s, cut.interpolate_level_set(s, cut.sphere_level_set([0.0] * dim, R))
+
+
+# ----------------------------------------------------------------------------------------------- quadrature generator
+def _generators(lib):
+    import gdm_b200 as g
+    return [("oracle", cut.cut_quadrature), ("product", g.CutPoisson.quadrature)]
+
+
+def test_cut_quadrature_known_integrals(lib):
+    """Multilinear level sets with closed-form measures: a hyperbola in 2D (spectral convergence in the number of
+    Gauss points), a plane in 3D (exact), and agreement of the two implementations point by point."""
+    from scipy.integrate import quad
+    hyper = np.array([[-0.25, -0.25], [-0.25, 0.75]])  # x y - 1/4
+    area = 0.25 + 0.25 * np.log(4.0)
+    arc = quad(lambda x: np.sqrt(1 + (0.25 / x ** 2) ** 2), 0.25, 1)[0]
+    plane = np.zeros((2, 2, 2))
+    for i in np.ndindex(2, 2, 2):
+        plane[i] = sum(i) - 1.3
+    t = 1.3
+    vol = t ** 3 / 6 - 3 * (t - 1) ** 3 / 6
+    tri_area = np.sqrt(3) * (t ** 2 / 2 - 3 * (t - 1) ** 2 / 2)
+    for name, gen in _generators(lib):
+        errs = []
+        for n in (2, 4, 8):
+            (ip, iw), (sp_, sw, sn) = gen(hyper, n)
+            errs.append((abs(iw.sum() - area), abs(sw.sum() - arc)))
+        assert errs[0][0] < 1e-3 and errs[1][0] < 1e-6 and errs[2][0] < 1e-12, (name, errs)
+        assert errs[2][1] < 1e-10, (name, errs)
+        (ip, iw), (sp_, sw, sn) = gen(plane, 4)
+        assert abs(iw.sum() - vol) < 1e-14 and abs(sw.sum() - tri_area) < 1e-14, name
+        assert np.allclose(sn, 1 / np.sqrt(3), atol=1e-14)
+        assert np.all(ip.sum(axis=1) < 1.3) and np.allclose(sp_.sum(axis=1), 1.3, atol=1e-14)
+        # polynomial moments over the half space x < 0.3 (1D cut): Gauss(p+1) on the inside sub-interval
+        (ip, iw), (sp_, sw, sn) = gen(np.array([-0.3, 0.7]), 4)
+        assert abs(np.sum(iw * ip[:, 0] ** 7) - 0.3 ** 8 / 8) < 1e-16 and abs(sp_[0, 0] - 0.3) < 1e-15 and sn[0, 0] == 1.0
+    rng = np.random.default_rng(0)
+    for dim in (1, 2, 3):
+        for _ in range(20):
+            v = rng.uniform(-1, 1, (2,) * dim)
+            (a, aw), (b, bw, bn) = cut.cut_quadrature(v, 3)
+            (c, cw), (d, dw, dn) = _generators(lib)[1][1](v, 3)
+            assert len(aw) == len(cw) and len(bw) == len(dw)
+            assert abs(aw.sum() - cw.sum()) < 1e-14 and abs(bw.sum() - dw.sum()) < 1e-13
+            ka, kc = np.lexsort(a.T[::-1]), np.lexsort(c.T[::-1])
+            assert np.allclose(a[ka], c[kc], atol=1e-13) and np.allclose(aw[ka], cw[kc], atol=1e-14)
+
+
+def test_cut_quadrature_sphere_measures_converge():
+    """Volume and area of the Q1-interpolated unit ball converge with h^2 (the geometry error of the level set)."""
+    for dim, exact_v, exact_a, sizes in ((2, np.pi, 2 * np.pi, (8, 16, 32)), (3, 4 / 3 * np.pi, 4 * np.pi, (6, 12))):
+        errs = []
+        for n in sizes:
+            s, ls = sphere_problem(dim, 3, n)
+            loc = cut.classify(s, ls)
+            hv = float(np.prod(s.h))
+            v = a = 0.0
+            for c in range(s.n_cells()):
+                if loc[c] == cut.INSIDE:
+                    v += hv
+                elif loc[c] == cut.INTERSECTED:
+                    (ip, iw), (sp_, sw, sn) = cut.cut_quadrature(cut.cell_vertex_values(s, ls, c), 4)
+                    v += iw.sum() * hv
+                    a += sw.sum() * hv / s.h[0]
+            errs.append((abs(v - exact_v), abs(a - exact_a)))
+        for e0, e1 in zip(errs[:-1], errs[1:]):
+            assert 3.5 < e0[0] / e1[0] < 4.5 and 3.5 < e0[1] / e1[1] < 4.5, errs
+
+
+# --------------------------------------------------------------------------------------------- golden of the reference
+@pytest.mark.parametrize("ghost_penalty", [False, True])
+def test_oracle_reproduces_cut_poisson_golden(golden_dir, ghost_penalty):
+    """prototypes/cut_poisson_01_gdm.cc end to end (2D, 64^2 cells on [-1.21, 1.21]^2, p = 3, unit circle, CG to 1e-6):
+    L2 error 4.2303e-04 / 4.3420e-04.  The cut quadrature point sets differ from deal.II's (same rule, other
+    partition), the error printed with 5 digits agrees to one unit in the last digit."""
+    gold = golden_errors(golden_dir)[1 if ghost_penalty else 0]
+    s, ls = sphere_problem(2, 3, 64)
+    A, rhs, loc = cut.assemble_cut_poisson(s, ls, ghost_penalty=ghost_penalty)
+    assert abs(A - A.T).max() < 1e-12
+    n = s.n_dofs()
+    ctl = O.ReductionControl(n, 1e-10, 1e-6)
+    u = O.solver_cg(A, np.zeros(n), rhs, O.PreconditionIdentity(), ctl)
+    err = cut.l2_error_inside(s, ls, u, exact_solution(2), loc)
+    assert abs(err - gold) <= 1.5e-8, (err, gold, ctl.last_step())
+
+
+# ------------------------------------------------------------------------------------------- product against the oracle
+def overlay_matrix(s, rows, rowptr, col, val):
+    """The operator the GPU applies: tensor-product stiffness rows, replaced by the attached CSR rows."""
+    n = s.n_dofs()
+    rows = rows.astype(np.int64)
+    K = O.kron_unconstrained(s, "stiffness")
+    M = sp.csr_matrix((val, col.astype(np.int64), rowptr.astype(np.int64)), shape=(len(rows), n))
+    keep = np.ones(n)
+    keep[rows] = 0.0
+    P = sp.csr_matrix((np.ones(len(rows)), (rows, np.arange(len(rows)))), shape=(n, len(rows)))
+    return (sp.diags(keep) @ K + P @ M).tocsr()
+
+
+@pytest.mark.parametrize("dim,p,n,gp,power", [(1, 3, 16, True, 1), (2, 3, 16, False, 1), (2, 3, 20, True, 1),
+                                              (2, 5, 24, True, 3), (2, 1, 12, True, 1), (3, 3, 8, True, 1),
+                                              (3, 1, 10, True, 3)])
+def test_product_rows_match_oracle_assembly(lib, dim, p, n, gp, power):
+    """gdm_cut_poisson_create: cell locations, right-hand side and (tensor rows + attached rows) == the oracle's matrix."""
+    import gdm_b200 as g
+    s, ls = sphere_problem(dim, p, n)
+    A, rhs, loc = cut.assemble_cut_poisson(s, ls, ghost_penalty=gp, gp_h_power=power)
+    c = g.CutPoisson(dim, p, [n] * dim, [-1.21] * dim, [1.21] * dim, ls, ghost_penalty=gp, gp_h_power=power)
+    n_rows, nnz, n_id, cells = c.sizes()
+    assert np.array_equal(c.locations(), loc)
+    assert cells == tuple(int((loc == k).sum()) for k in (cut.INSIDE, cut.OUTSIDE, cut.INTERSECTED))
+    rows, rowptr, col, val = c.rows()
+    assert len(rows) == n_rows and rowptr[-1] == nnz == len(col) and np.all(np.diff(rows.astype(np.int64)) > 0)
+    full = overlay_matrix(s, rows, rowptr, col, val)
+    assert abs(full - A).max() <= 1e-13 * abs(A).max()
+    assert np.abs(c.rhs() - rhs).max() <= 1e-14 * np.abs(rhs).max()
+    # identity rows: exactly the DoFs no active cell touches
+    d = A.diagonal()
+    lone = np.array([A.indptr[i + 1] - A.indptr[i] == 1 and d[i] == 1.0 for i in range(s.n_dofs())])
+    assert n_id == int(lone.sum())
+
+
+def test_product_setup_reproduces_golden_on_host(lib, golden_dir):
+    """The product's rows, right-hand side and error norm with the oracle's CG in between (no GPU here): the golden error."""
+    import gdm_b200 as g
+    s, ls = sphere_problem(2, 3, 64)
+    c = g.CutPoisson(2, 3, [64, 64], [-1.21] * 2, [1.21] * 2, ls, ghost_penalty=True)
+    A = overlay_matrix(s, *c.rows())
+    n = s.n_dofs()
+    ctl = O.ReductionControl(n, 1e-10, 1e-6)
+    u = O.solver_cg(A, np.zeros(n), c.rhs(), O.PreconditionIdentity(), ctl)
+    err = c.l2_error_inside(u, lambda pt, comp: 1.0 - (pt[0] ** 2 + pt[1] ** 2 - 1.0))
+    assert abs(err - golden_errors(golden_dir)[1]) <= 1.5e-8
+    assert abs(err - cut.l2_error_inside(s, ls, u, exact_solution(2))) <= 1e-15
+
+
+def test_cut_argument_checks(lib):
+    import gdm_b200 as g
+    with pytest.raises(g.GdmError):
+        g.CutPoisson(2, 3, [8, 8], [0, 0], [1, 1], np.zeros(10))
+    with pytest.raises(g.GdmError):
+        g.CutPoisson(2, 4, [8, 8], [0, 0], [1, 1], np.zeros(81))
+    with pytest.raises(g.GdmError):
+        g.CutPoisson(2, 3, [2, 8], [0, 0], [1, 1], np.zeros(27))
