@@ -301,12 +301,19 @@ def face_has_ghost_penalty(system, location, cell, d, side):
 
 # -------------------------------------------------------------------------------------------------- the assembly
 def assemble_cut_poisson(system, ls, ghost_penalty=True, ghost_parameter=0.5, nitsche_parameter=None,
-                         rhs_value=4.0, boundary_value=1.0, gp_h_power=1):
+                         rhs_value=4.0, boundary_value=1.0, gp_h_power=1, kind="stiffness", outside_diagonal=1.0):
     """Global matrix (CSR), right-hand side and cell locations of the CutFEM Poisson problem.
 
     Follows `prototypes/cut_poisson_01_gdm.cc:196-329` term by term (scalar field, no constraints).
+    `rhs_value` / `boundary_value` may be callables of the physical points [q, dim].
+    `kind="mass"`: the cut mass matrix of `applications/wave/include/gdm/wave/mass.h:47-249` instead (inside mass, no
+    surface terms, ghost penalty with `ghost_parameter` = gamma_M and `gp_h_power=3`); the right-hand side is then
+    (v, rhs_value) on the inside part.  `outside_diagonal=0` leaves the rows no active cell touches empty, which is
+    what the matrix-free residual `wave/stiffness.h:42-407` amounts to.
     """
-    assert system.n_components == 1
+    assert system.n_components == 1 and kind in ("stiffness", "mass")
+    fval = rhs_value if callable(rhs_value) else (lambda pts: np.full(len(pts), float(rhs_value)))
+    gval = boundary_value if callable(boundary_value) else (lambda pts: np.full(len(pts), float(boundary_value)))
     p, dim = system.fe_degree, system.dim
     n = system.n_dofs()
     if nitsche_parameter is None:
@@ -336,11 +343,12 @@ def assemble_cut_poisson(system, ls, ghost_penalty=True, ghost_parameter=0.5, ni
             if cat not in inside_cache:
                 idx = system.cell_indices(cell)
                 value, _ = get([system.variant(idx[e], e) for e in range(dim)])
-                inside_cache[cat] = (cell_matrix_scalar(system, cell, "stiffness", get, jxw_full),
-                                     rhs_value * np.einsum("q,qi->i", jxw_full, value))
-            km, fv = inside_cache[cat]
+                inside_cache[cat] = (cell_matrix_scalar(system, cell, kind, get, jxw_full), value)
+            km, value = inside_cache[cat]
             add(dofs, km)
-            rhs[dofs] += fv
+            grids = np.meshgrid(*([xq] * dim)[::-1], indexing="ij")
+            ref = np.stack([g.ravel() for g in grids[::-1]], axis=1)  # the point order of _cell_tables (x fastest)
+            rhs[dofs] += np.einsum("q,q,qi->i", jxw_full, fval(physical_points(system, cell, ref)), value)
         else:
             (ip, iw), (sp_, sw, sn) = cut_quadrature(cell_vertex_values(system, ls, cell), p + 1)
             local = np.zeros((len(dofs), len(dofs)))
@@ -348,10 +356,13 @@ def assemble_cut_poisson(system, ls, ghost_penalty=True, ghost_parameter=0.5, ni
             if len(iw):
                 value, grads = shape_at_points(system, cell, ip)
                 jxw = iw * float(np.prod(h))
-                for g in grads:
-                    local += np.einsum("q,qi,qj->ij", jxw, g, g)
-                lrhs += rhs_value * np.einsum("q,qi->i", jxw, value)
-            if len(sw):
+                if kind == "mass":
+                    local += np.einsum("q,qi,qj->ij", jxw, value, value)
+                else:
+                    for g in grads:
+                        local += np.einsum("q,qi,qj->ij", jxw, g, g)
+                lrhs += np.einsum("q,q,qi->i", jxw, fval(physical_points(system, cell, ip)), value)
+            if len(sw) and kind == "stiffness":
                 value, grads = shape_at_points(system, cell, sp_)
                 nphys = sn / h
                 scale = np.linalg.norm(nphys, axis=1)
@@ -360,8 +371,9 @@ def assemble_cut_poisson(system, ls, ghost_penalty=True, ghost_parameter=0.5, ni
                 ng = sum(nphys[:, e][:, None] * grads[e] for e in range(dim))  # normal . grad phi_i
                 local += -np.einsum("q,qi,qj->ij", jxw, ng, value) - np.einsum("q,qi,qj->ij", jxw, value, ng) \
                     + nitsche_parameter / hmin * np.einsum("q,qi,qj->ij", jxw, value, value)
-                lrhs += boundary_value * (nitsche_parameter / hmin * np.einsum("q,qi->i", jxw, value)
-                                          - np.einsum("q,qi->i", jxw, ng))
+                gq = gval(physical_points(system, cell, sp_))
+                lrhs += nitsche_parameter / hmin * np.einsum("q,q,qi->i", jxw, gq, value) \
+                    - np.einsum("q,q,qi->i", jxw, gq, ng)
             add(dofs, local)
             rhs[dofs] += lrhs
         if ghost_penalty:
@@ -382,11 +394,21 @@ def assemble_cut_poisson(system, ls, ghost_penalty=True, ghost_parameter=0.5, ni
     A.sum_duplicates()
     diag = A.diagonal()
     fix = np.where(diag == 0.0)[0]  # `:324-329`: rows no active cell touches become identity rows
-    A = (A + sp.coo_matrix((np.ones(len(fix)), (fix, fix)), shape=(n, n))).tocsr()
+    A = (A + sp.coo_matrix((np.full(len(fix), float(outside_diagonal)), (fix, fix)), shape=(n, n))).tocsr()
     return A, rhs, location
 
 
+def error_norms_inside(system, ls, u, exact, location=None):
+    """(L2, L1, Linf) of u_h - u over the inside part, Linf as the maximum over the quadrature points: the three columns
+    `applications/wave/include/gdm/wave/problem.h:609-615` prints (`postprocess`, `:531-607`)."""
+    return _errors_inside(system, ls, u, exact, location)
+
+
 def l2_error_inside(system, ls, u, exact, location=None):
+    return _errors_inside(system, ls, u, exact, location)[0]
+
+
+def _errors_inside(system, ls, u, exact, location=None):
     """sqrt(sum over non-outside cells of int_{inside part} (u_h - u)^2) (`prototypes/cut_poisson_01_gdm.cc:349-398`)."""
     p, dim = system.fe_degree, system.dim
     if location is None:
@@ -394,7 +416,7 @@ def l2_error_inside(system, ls, u, exact, location=None):
     get, jxw_full, xq = _cell_tables(system)
     full_ref, _ = _tensor_gauss(np.zeros(dim), np.ones(dim), xq, xq)
     vol = float(np.prod(system.h))
-    acc = 0.0
+    acc = l1 = linf = 0.0
     u = np.asarray(u, dtype=float)
     for cell in range(system.n_cells()):
         if location[cell] == OUTSIDE:
@@ -414,5 +436,8 @@ def l2_error_inside(system, ls, u, exact, location=None):
             value, _ = shape_at_points(system, cell, ref)
             jxw = w * vol
         pts = physical_points(system, cell, ref)
-        acc += float(np.sum((value @ u[dofs] - exact(pts)) ** 2 * jxw))
-    return float(np.sqrt(acc))
+        diff = value @ u[dofs] - exact(pts)
+        acc += float(np.sum(diff ** 2 * jxw))
+        l1 += float(np.sum(np.abs(diff) * jxw))
+        linf = max(linf, float(np.abs(diff).max()))
+    return float(np.sqrt(acc)), l1, linf
