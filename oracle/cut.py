@@ -441,3 +441,50 @@ def _errors_inside(system, ls, u, exact, location=None):
         l1 += float(np.sum(np.abs(diff) * jxw))
         linf = max(linf, float(np.abs(diff).max()))
     return float(np.sqrt(acc)), l1, linf
+
+
+def load_functionals(system, ls, nitsche_parameter=None, location=None):
+    """The data-dependent part of the residual `wave/stiffness.h:186-260` as two lists of (dofs, points, W[q, i]):
+    volume  b_i += sum_q f(x_q) phi_i JxW  over the inside part, and
+    surface b_i += sum_q g(x_q) (gamma_D / h phi_i - d_n phi_i) JxW  on the cut surface,
+    so that a time-dependent f or g costs one evaluation per quadrature point and stage (`apply_load`)."""
+    p, dim = system.fe_degree, system.dim
+    if nitsche_parameter is None:
+        nitsche_parameter = 5.0 * (p + 1) * p
+    if location is None:
+        location = classify(system, ls)
+    get, jxw_full, xq = _cell_tables(system)
+    h = np.array(system.h)
+    hmin, vol = float(h.min()), float(np.prod(h))
+    grids = np.meshgrid(*([xq] * dim)[::-1], indexing="ij")
+    full_ref = np.stack([g.ravel() for g in grids[::-1]], axis=1)
+    volume, surface = [], []
+    for cell in range(system.n_cells()):
+        if location[cell] == OUTSIDE:
+            continue
+        dofs = np.asarray(system.get_dof_indices(cell))
+        if location[cell] == INSIDE:
+            idx = system.cell_indices(cell)
+            value, _ = get([system.variant(idx[e], e) for e in range(dim)])
+            volume.append((dofs, physical_points(system, cell, full_ref), value * jxw_full[:, None]))
+            continue
+        (ip, iw), (sp_, sw, sn) = cut_quadrature(cell_vertex_values(system, ls, cell), p + 1)
+        if len(iw):
+            value, _ = shape_at_points(system, cell, ip)
+            volume.append((dofs, physical_points(system, cell, ip), value * (iw * vol)[:, None]))
+        if len(sw):
+            value, grads = shape_at_points(system, cell, sp_)
+            nphys = sn / h
+            scale = np.linalg.norm(nphys, axis=1)
+            nphys = nphys / scale[:, None]
+            jxw = sw * vol * scale
+            ng = sum(nphys[:, e][:, None] * grads[e] for e in range(dim))
+            surface.append((dofs, physical_points(system, cell, sp_), (nitsche_parameter / hmin * value - ng) * jxw[:, None]))
+    return volume, surface
+
+
+def apply_load(n, terms, fn):
+    b = np.zeros(n)
+    for dofs, pts, W in terms:
+        np.add.at(b, dofs, np.asarray(fn(pts), dtype=float) @ W)
+    return b

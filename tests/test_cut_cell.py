@@ -184,3 +184,24 @@ def test_cut_argument_checks(lib):
         g.CutPoisson(2, 4, [8, 8], [0, 0], [1, 1], np.zeros(81))
     with pytest.raises(g.GdmError):
         g.CutPoisson(2, 3, [2, 8], [0, 0], [1, 1], np.zeros(27))
+
+
+# ------------------------------------------------------------------------------- the wave application's goldens (1D)
+def _app_golden(golden_dir, name):
+    rows = [l.split() for l in open(os.path.join(golden_dir, name)) if not l.startswith(" [L]")]
+    return [(int(a), float(b), float(c), float(d), float(e)) for a, b, c, d, e in rows]
+
+
+@pytest.mark.parametrize("name", ["wave_0", "heat_1"])
+def test_oracle_reproduces_wave_app_goldens(golden_dir, name):
+    """applications/wave/tests/{wave_0,heat_1}.output (1D cut domain, ghost penalty in mass and stiffness, Nitsche with a
+    time-dependent boundary value, RK4 with the shortened last step): every printed step, all three error columns
+    (L2, L1, Linf) to the 9 digits printed.  The `[L] solved in k` lines (AMG / ILU counts) are not reproducible."""
+    from oracle import wave_app
+    rows = wave_app.wave_rk_run() if name == "wave_0" else wave_app.heat_rk_run()
+    gold = _app_golden(golden_dir, f"app_wave_{name}.output")
+    assert len(rows) == len(gold) == (112 if name == "wave_0" else 821)
+    for r, g in zip(rows, gold):
+        assert r[0] == g[0] and abs(r[1] - g[1]) <= 5.1e-6  # time is printed with 5 decimals
+        for i in (2, 3, 4):
+            assert abs(r[i] - g[i]) <= 6e-9 * g[i], (name, r, g)
