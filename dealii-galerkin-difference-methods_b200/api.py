@@ -776,7 +776,8 @@ class CutPoisson:
     INSIDE, OUTSIDE, INTERSECTED = 0, 1, 2
 
     def __init__(self, dim, fe_degree, n_subdivisions, lo, hi, level_set, ghost_penalty=True, ghost_parameter=0.5,
-                 nitsche_parameter=None, rhs_value=4.0, boundary_value=1.0, gp_h_power=1):
+                 nitsche_parameter=None, rhs_value=4.0, boundary_value=1.0, gp_h_power=1, kind="stiffness",
+                 outside_diagonal=1.0):
         self.lib = capi.load()
         d = capi.CutDesc()
         d.dim, d.fe_degree = dim, fe_degree
@@ -787,6 +788,7 @@ class CutPoisson:
         d.ghost_parameter = float(ghost_parameter)
         d.nitsche_parameter = float(5.0 * (fe_degree + 1) * fe_degree if nitsche_parameter is None else nitsche_parameter)
         d.rhs_value, d.boundary_value = float(rhs_value), float(boundary_value)
+        d.kind, d.outside_diagonal = {"stiffness": 0, "mass": 1}[kind], float(outside_diagonal)
         self.n_dofs = int(np.prod([int(n) + 1 for n in n_subdivisions[:dim]]))
         self.n_cells = int(np.prod([int(n) for n in n_subdivisions[:dim]]))
         level_set = np.ascontiguousarray(level_set, dtype=np.float64)
@@ -813,6 +815,16 @@ class CutPoisson:
     def rhs(self):
         out = np.zeros(self.n_dofs)
         capi.check(self.lib.gdm_cut_rhs(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def load_vector(self, f=None, g=None):
+        """(v, f) over the inside part + <gamma_D / h v - dv/dn, g> on the surface (`wave/stiffness.h:186-260`);
+        f, g: functions (point[3], component) -> float or None."""
+        out = np.zeros(self.n_dofs)
+        fcb = VectorTools._wrap(f) if f is not None else None
+        gcb = VectorTools._wrap(g) if g is not None else None
+        cast = lambda cb: C.cast(cb, C.c_void_p) if cb is not None else None
+        capi.check(self.lib.gdm_cut_load_vector(self.h, cast(fcb), None, cast(gcb), None, out.ctypes.data_as(C.c_void_p)))
         return out
 
     def locations(self):

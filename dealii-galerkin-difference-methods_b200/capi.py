@@ -65,7 +65,7 @@ class CutDesc(C.Structure):
     _fields_ = [("dim", C.c_int), ("fe_degree", C.c_int), ("n_subdivisions", C.c_uint32 * 3),
                 ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("ghost_penalty", C.c_int), ("gp_h_power", C.c_int),
                 ("ghost_parameter", C.c_double), ("nitsche_parameter", C.c_double), ("rhs_value", C.c_double),
-                ("boundary_value", C.c_double)]
+                ("boundary_value", C.c_double), ("kind", C.c_int), ("outside_diagonal", C.c_double)]
 
 
 FUNCTION_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_int, C.c_void_p)
@@ -137,6 +137,7 @@ SIGNATURES = {
     "gdm_cut_rows": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gdm_cut_rhs": (C.c_int, [_H, C.c_void_p]),
     "gdm_cut_locations": (C.c_int, [_H, C.c_void_p]),
+    "gdm_cut_load_vector": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gdm_cut_l2_error_inside": (C.c_int, [_H, C.c_void_p, FUNCTION_FN, C.c_void_p, _PD]),
     "gdm_cut_quadrature": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_uint64, _PU64, C.c_void_p, C.c_void_p, _PU64,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -568,6 +568,16 @@ namespace gdm
       }
 
       void build();
+      void load_vector(gdm_function_fn f, void *f_user, gdm_function_fn g, void *g_user, double *out);
+
+      // data-independent part of the load functionals on the intersected cells (built on first use)
+      struct CutCellLoad
+      {
+        uint64_t            cell;
+        std::vector<double> vpts, vW, spts, sW; // points [q*dim + e], weights [q*npc + i]
+      };
+      std::vector<CutCellLoad> cut_loads;
+      bool                     cut_loads_built = false;
     };
 
     void Assembly::build()
@@ -661,6 +671,7 @@ namespace gdm
       };
 
       // full-cell tables per category
+      const bool   mass = desc.kind == 1;
       const double vol = cell_volume(), hm = h_min();
       const double nitsche = desc.nitsche_parameter / hm;
       std::vector<Pt> full;
@@ -686,8 +697,11 @@ namespace gdm
                 for (int j = 0; j < npc; ++j)
                   {
                     double s = 0;
-                    for (int e = 0; e < dim; ++e)
-                      s += grads[e][q * npc + i] * grads[e][q * npc + j];
+                    if (mass)
+                      s = value[q * npc + i] * value[q * npc + j];
+                    else
+                      for (int e = 0; e < dim; ++e)
+                        s += grads[e][q * npc + i] * grads[e][q * npc + j];
                     K[(size_t)i * npc + j] += s * jxw;
                   }
               }
@@ -782,14 +796,17 @@ namespace gdm
                           for (int j = 0; j < npc; ++j)
                             {
                               double s = 0;
-                              for (int e = 0; e < dim; ++e)
-                                s += grads[e][q * npc + i] * grads[e][q * npc + j];
+                              if (mass)
+                                s = value[q * npc + i] * value[q * npc + j];
+                              else
+                                for (int e = 0; e < dim; ++e)
+                                  s += grads[e][q * npc + i] * grads[e][q * npc + j];
                               local[(size_t)i * npc + j] += s * jxw;
                             }
                         }
                     }
                 }
-              if (!spts.empty())
+              if (!spts.empty() && !mass)
                 {
                   shape_at_points(idx, spts, value, grads);
                   std::vector<double> ng(npc);
@@ -860,7 +877,7 @@ namespace gdm
             {
               row_ids.push_back(i);
               col.push_back(i);
-              val.push_back(1.0);
+              val.push_back(desc.outside_diagonal);
               rowptr.push_back(col.size());
               ++n_identity_rows;
               continue;
@@ -900,6 +917,125 @@ namespace gdm
                 }
             }
           rowptr.push_back(col.size());
+        }
+    }
+    // out_i = sum_q f(x_q) phi_i JxW over the inside part + sum_q g(x_q) (gamma_D / h phi_i - d_n phi_i) JxW on the surface:
+    // the data-dependent part of the residual applications/wave/include/gdm/wave/stiffness.h:186-260
+    void Assembly::load_vector(gdm_function_fn f, void *f_user, gdm_function_fn g, void *g_user, double *out)
+    {
+      std::fill(out, out + n_dofs, 0.0);
+      const double          vol = cell_volume(), nitsche = desc.nitsche_parameter / h_min();
+      std::vector<double>   value, grads[3];
+      std::vector<uint64_t> dofs;
+      int                   idx[3], off[3];
+      if (!cut_loads_built)
+        {
+          std::vector<Pt> ipts, spts;
+          for (uint64_t cell = 0; cell < n_cells; ++cell)
+            if (location[cell] == INTERSECTED)
+              {
+                cell_index(cell, idx);
+                double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                vertex_values(idx, v);
+                ipts.clear();
+                spts.clear();
+                cut_quadrature(dim, v, gauss, ipts, spts);
+                CutCellLoad L;
+                L.cell = cell;
+                auto physical = [&](const std::vector<Pt> &pts, std::vector<double> &x) {
+                  x.resize(pts.size() * dim);
+                  for (size_t q = 0; q < pts.size(); ++q)
+                    for (int e = 0; e < dim; ++e)
+                      x[q * dim + e] = lo[e] + (idx[e] + pts[q].x[e]) * h[e];
+                };
+                if (!ipts.empty())
+                  {
+                    shape_at_points(idx, ipts, value, grads);
+                    physical(ipts, L.vpts);
+                    L.vW.resize(ipts.size() * npc);
+                    for (size_t q = 0; q < ipts.size(); ++q)
+                      for (int i = 0; i < npc; ++i)
+                        L.vW[q * npc + i] = value[q * npc + i] * (ipts[q].w * vol);
+                  }
+                if (!spts.empty())
+                  {
+                    shape_at_points(idx, spts, value, grads);
+                    physical(spts, L.spts);
+                    L.sW.resize(spts.size() * npc);
+                    for (size_t q = 0; q < spts.size(); ++q)
+                      {
+                        double nph[3] = {0, 0, 0}, scale = 0;
+                        for (int e = 0; e < dim; ++e)
+                          {
+                            nph[e] = spts[q].n[e] / h[e];
+                            scale += nph[e] * nph[e];
+                          }
+                        scale = std::sqrt(scale);
+                        const double jxw = spts[q].w * vol * scale;
+                        for (int i = 0; i < npc; ++i)
+                          {
+                            double ng = 0;
+                            for (int e = 0; e < dim; ++e)
+                              ng += nph[e] / scale * grads[e][q * npc + i];
+                            L.sW[q * npc + i] = (nitsche * value[q * npc + i] - ng) * jxw;
+                          }
+                      }
+                  }
+                cut_loads.push_back(std::move(L));
+              }
+          cut_loads_built = true;
+        }
+      if (f)
+        {
+          std::vector<Pt> full;
+          const double    l0[3] = {0, 0, 0}, h1[3] = {1, 1, 1};
+          tensor_gauss(l0, h1, dim, gauss, full);
+          std::map<int, std::vector<double>> tables; // category -> phi_i(x_q)
+          for (uint64_t cell = 0; cell < n_cells; ++cell)
+            if (location[cell] == INSIDE)
+              {
+                cell_index(cell, idx);
+                cell_dofs(idx, off, dofs);
+                const int cat = category(idx);
+                auto      it  = tables.find(cat);
+                if (it == tables.end())
+                  {
+                    shape_at_points(idx, full, value, grads);
+                    it = tables.emplace(cat, value).first;
+                  }
+                const std::vector<double> &phi = it->second;
+                for (size_t q = 0; q < full.size(); ++q)
+                  {
+                    double x[3] = {0, 0, 0};
+                    for (int e = 0; e < dim; ++e)
+                      x[e] = lo[e] + (idx[e] + full[q].x[e]) * h[e];
+                    const double fq = f(x, 0, f_user) * full[q].w * vol;
+                    for (int i = 0; i < npc; ++i)
+                      out[dofs[i]] += fq * phi[q * npc + i];
+                  }
+              }
+        }
+      for (const CutCellLoad &L : cut_loads)
+        {
+          cell_index(L.cell, idx);
+          cell_dofs(idx, off, dofs);
+          for (int pass = 0; pass < 2; ++pass)
+            {
+              gdm_function_fn            fn   = pass == 0 ? f : g;
+              void                      *user = pass == 0 ? f_user : g_user;
+              const std::vector<double> &pts = pass == 0 ? L.vpts : L.spts, &W = pass == 0 ? L.vW : L.sW;
+              if (!fn)
+                continue;
+              for (size_t q = 0; q < pts.size() / dim; ++q)
+                {
+                  double x[3] = {0, 0, 0};
+                  for (int e = 0; e < dim; ++e)
+                    x[e] = pts[q * dim + e];
+                  const double fq = fn(x, 0, user);
+                  for (int i = 0; i < npc; ++i)
+                    out[dofs[i]] += fq * W[q * npc + i];
+                }
+            }
         }
     }
   } // namespace cut
@@ -977,6 +1113,7 @@ int gdm_cut_poisson_create(const gdm_cut_desc *desc, const double *level_set, gd
   GDM_REQUIRE(desc->dim >= 1 && desc->dim <= 3, GDM_ERR_INVALID, "dim must be 1, 2 or 3");
   GDM_REQUIRE(desc->fe_degree >= 1 && desc->fe_degree <= MAX_DEGREE && desc->fe_degree % 2 == 1, GDM_ERR_INVALID,
               "fe_degree must be odd and <= 9");
+  GDM_REQUIRE(desc->kind == 0 || desc->kind == 1, GDM_ERR_INVALID, "kind must be 0 (stiffness + Nitsche) or 1 (mass)");
   auto           h = std::make_unique<gdm_cut_s>();
   cut::Assembly &a = h->a;
   a.desc           = *desc;
@@ -1050,6 +1187,15 @@ int gdm_cut_rhs(gdm_cut_t c, double *rhs)
   GDM_ARG(c);
   GDM_ARG(rhs);
   std::copy(c->a.rhs.begin(), c->a.rhs.end(), rhs);
+  GDM_CATCH
+}
+
+int gdm_cut_load_vector(gdm_cut_t c, gdm_function_fn f, void *f_user, gdm_function_fn g, void *g_user, double *out)
+{
+  GDM_TRY
+  GDM_ARG(c);
+  GDM_ARG(out);
+  c->a.load_vector(f, f_user, g, g_user, out);
   GDM_CATCH
 }
 

@@ -312,6 +312,11 @@ typedef struct gdm_cut_desc {
   double   nitsche_parameter; /* 5 (p+1) p */
   double   rhs_value;         /* constant right-hand side f (4) */
   double   boundary_value;    /* constant Dirichlet value g on the surface (1) */
+  int      kind;              /* 0: stiffness + Nitsche (the Poisson matrix / the linear part of the residual
+                                 wave/stiffness.h:42-407); 1: the cut mass matrix wave/mass.h:47-249 (no surface terms;
+                                 use ghost_parameter = gamma_M, gp_h_power = 3) */
+  double   outside_diagonal;  /* diagonal of the rows no active cell touches: 1 for a matrix that is solved with
+                                 (cut_poisson_01_gdm.cc:324-329, wave/mass.h:246-248), 0 for the matrix-free residual */
 } gdm_cut_desc;
 typedef struct gdm_cut_s *gdm_cut_t;
 /* level_set: nodal values of the Q1 level set at the grid nodes, DoF order (x fastest); negative = inside */
@@ -324,6 +329,9 @@ int gdm_cut_sizes(gdm_cut_t cut, uint64_t *n_rows, uint64_t *nnz, uint64_t *n_id
 /* the arguments of gdm_operator_attach_csr: row_ids[n_rows] ascending, rowptr[n_rows+1], col/val[nnz] (columns ascending) */
 int gdm_cut_rows(gdm_cut_t cut, uint64_t *row_ids, uint64_t *rowptr, uint64_t *col, double *val);
 int gdm_cut_rhs(gdm_cut_t cut, double *rhs /* n_dofs */);
+/* out[n_dofs] = (v, f) over the inside part + <gamma_D / h v - dv/dn, g> on the surface, for functions of the point: the
+ * data-dependent part of the residual (wave/stiffness.h:186-260; time enters through `user`).  f or g may be NULL. */
+int gdm_cut_load_vector(gdm_cut_t cut, gdm_function_fn f, void *f_user, gdm_function_fn g, void *g_user, double *out);
 int gdm_cut_locations(gdm_cut_t cut, uint8_t *location /* n_cells: 0 inside, 1 outside, 2 intersected */);
 /* sqrt( sum over non-outside cells of the integral over the inside part of (u_h - exact)^2 ); u = all DoFs */
 int gdm_cut_l2_error_inside(gdm_cut_t cut, const double *u, gdm_function_fn exact, void *user, double *error);

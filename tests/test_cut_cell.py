@@ -205,3 +205,73 @@ def test_oracle_reproduces_wave_app_goldens(golden_dir, name):
         assert r[0] == g[0] and abs(r[1] - g[1]) <= 5.1e-6  # time is printed with 5 decimals
         for i in (2, 3, 4):
             assert abs(r[i] - g[i]) <= 6e-9 * g[i], (name, r, g)
+
+
+def overlay_matrix_kind(s, kind, rows, rowptr, col, val):
+    n = s.n_dofs()
+    rows = rows.astype(np.int64)
+    K = O.kron_unconstrained(s, kind)
+    M = sp.csr_matrix((val, col.astype(np.int64), rowptr.astype(np.int64)), shape=(len(rows), n))
+    keep = np.ones(n)
+    keep[rows] = 0.0
+    P = sp.csr_matrix((np.ones(len(rows)), (rows, np.arange(len(rows)))), shape=(n, len(rows)))
+    return (sp.diags(keep) @ K + P @ M).tocsr()
+
+
+def product_wave_operators(params):
+    """The operators of the wave application from the product's generator: (mass + attached rows), (stiffness + attached
+    rows with empty outside rows), the two CutPoisson handles."""
+    import gdm_b200 as g
+    dim, p, n1 = params["dim"], params["fe_degree"], params["n_subdivisions"]
+    s = O.System(dim, p, 1)
+    s.subdivided_hyper_cube(n1, params["left"], params["right"])
+    ls = cut.interpolate_level_set(s, cut.sphere_level_set([0.0] * dim, 1.0))
+    box = ([n1] * dim, [params["left"]] * dim, [params["right"]] * dim)
+    cm = g.CutPoisson(dim, p, *box, ls, ghost_penalty=True, ghost_parameter=params["ghost_parameter_M"], gp_h_power=3,
+                      kind="mass", rhs_value=0.0)
+    ca = g.CutPoisson(dim, p, *box, ls, ghost_penalty=True, ghost_parameter=params["ghost_parameter_A"], gp_h_power=1,
+                      nitsche_parameter=params["nitsche_parameter"], rhs_value=0.0, boundary_value=0.0, outside_diagonal=0.0)
+    return s, ls, cm, ca, overlay_matrix_kind(s, "mass", *cm.rows()), overlay_matrix_kind(s, "stiffness", *ca.rows())
+
+
+@pytest.mark.parametrize("dim,n1", [(1, 40), (2, 20), (3, 8)])
+def test_product_wave_operators_match_oracle(lib, dim, n1):
+    """Cut mass matrix (wave/mass.h:47-249), the residual's matrix with empty outside rows and the load functionals
+    (wave/stiffness.h:186-260) from gdm_cut_* against the oracle's."""
+    from oracle import wave_app
+    params = dict(wave_app.heat_preset(1), dim=dim, n_subdivisions=n1)
+    s, ls, cm, ca, M, A = product_wave_operators(params)
+    _, _, loc, Mo, Ao, volume, surface = wave_app.wave_operators(params)
+    assert abs(M - Mo).max() <= 1e-13 * abs(Mo).max() and abs(A - Ao).max() <= 1e-13 * abs(Ao).max()
+    f = lambda pts: np.sin(pts.sum(axis=1)) + 2.0
+    gq = lambda pts: np.cos(pts[:, 0]) - 0.5
+    ref = cut.apply_load(s.n_dofs(), volume, f) + cut.apply_load(s.n_dofs(), surface, gq)
+    got = ca.load_vector(lambda pt, c: np.sin(sum(pt[:dim])) + 2.0, lambda pt, c: np.cos(pt[0]) - 0.5)
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.abs(ca.load_vector(None, lambda pt, c: np.cos(pt[0]) - 0.5) - cut.apply_load(s.n_dofs(), surface, gq)).max() \
+        <= 1e-13 * np.abs(ref).max()
+
+
+def test_product_setup_reproduces_wave_0_golden_on_host(lib, golden_dir):
+    """applications/wave/tests/wave_0.output from the product's operators and load vector, with the oracle's RK4 and an
+    exact mass solve in between (no GPU here): first 12 printed steps."""
+    from oracle import wave_app
+    import scipy.sparse.linalg as sla
+    params = wave_app.wave_preset(1)
+    s, ls, cm, ca, M, A = product_wave_operators(params)
+    k = 1.5 * np.pi
+    n = s.n_dofs()
+    solve = sla.factorized(M.tocsc())
+    exact = params["exact"]
+    y = np.concatenate([O.interpolate(s, lambda pts, c: exact(pts, 0.0)), np.zeros(n)])
+
+    def f(t, yy):
+        b = ca.load_vector(None, lambda pt, c: np.cos(k * abs(pt[0])) * np.cos(k * t))
+        return np.concatenate([yy[n:], solve(-(A @ yy[:n]) + b)])
+
+    gold = _app_golden(golden_dir, "app_wave_wave_0.output")
+    rk, t, dt = O.ExplicitRungeKutta4(), 0.0, 0.3 * 2.42 / 40
+    for step in range(12):
+        e = cm.l2_error_inside(y[:n], lambda pt, c: np.cos(k * abs(pt[0])) * np.cos(k * t))
+        assert abs(e - gold[step][2]) <= 6e-9 * gold[step][2], (step, e, gold[step])
+        t, y = rk.evolve_one_time_step(f, t, dt, y)
