@@ -75,3 +75,95 @@ def test_cut_poisson_3d_fused(lib):
     err = c.l2_error_inside(u.numpy(), lambda pt, comp: 1.0 - 2.0 / 3.0 * (pt[0] ** 2 + pt[1] ** 2 + pt[2] ** 2 - 1.0))
     erro = c.l2_error_inside(uo, lambda pt, comp: 1.0 - 2.0 / 3.0 * (pt[0] ** 2 + pt[1] ** 2 + pt[2] ** 2 - 1.0))
     assert abs(err - erro) <= 1e-4 * erro and err < 1e-2
+
+
+def _gpu_wave_operators(g, params):
+    """Mass and stiffness operators with the cut rows of the wave application attached (wave/mass.h:47-249,
+    wave/stiffness.h:42-407), the host-side generators and the oracle system."""
+    from test_cut_cell import product_wave_operators
+    dim, n1 = params["dim"], params["n_subdivisions"]
+    gs, gc, os_, oc = make_pair(dim, params["fe_degree"], 1, [n1] * dim, "none",
+                                lo=[params["left"]] * dim, hi=[params["right"]] * dim)
+    s, ls, cm, ca, Mo, Ao = product_wave_operators(params)
+    M, A = make_operator(gs, gc, "mass"), make_operator(gs, gc, "stiffness")
+    M.attach_csr(*cm.rows())
+    A.attach_csr(*ca.rows())
+    return gs, os_, cm, ca, M, A, Mo, Ao
+
+
+def test_wave_app_wave_0(lib, golden_dir):
+    """applications/wave, simulation "wave" in 1D (problem.h:280-345) on the GPU: RK4 over [u; v], Jacobi-CG mass
+    solves with the reference's control (1000, 1e-20, 1e-14), cut rows attached to both operators; the L2 column of
+    applications/wave/tests/wave_0.output for the first 25 printed steps."""
+    import gdm_b200 as g
+    from oracle import wave_app
+    from test_cut_cell import _app_golden
+    params = wave_app.wave_preset(1)
+    gs, os_, cm, ca, M, A, Mo, Ao = _gpu_wave_operators(g, params)
+    k = 1.5 * np.pi
+    exact = lambda t: (lambda pt, c: np.cos(k * abs(pt[0])) * np.cos(k * t))
+    n = gs.n_dofs()
+    u, v = g.Vector(gs, O.interpolate(os_, lambda pts, c: params["exact"](pts, 0.0))), g.Vector(gs)
+    pre = g.PreconditionJacobi()
+    pre.initialize(M)
+    rhs, load = g.Vector(gs), g.Vector(gs)
+    iters = []
+
+    def f(t, y, out):
+        out[0].equ(y[1])                                  # du/dt = v
+        A.vmult(rhs, y[0])
+        rhs.scale(-1.0)
+        load.upload(ca.load_vector(None, exact(t)))       # <gamma_D/h v - dv/dn, g(t)> (zero here: g(+-1, t) = 0)
+        rhs.add(1.0, load)
+        out[1].set(0.0)
+        ctl = g.ReductionControl(1000, 1e-20, 1e-14)
+        g.SolverCG(ctl).solve(M, out[1], rhs, pre)        # dv/dt = M^-1 rhs(u, t)
+        iters.append(ctl.last_step())
+
+    gold = _app_golden(golden_dir, "app_wave_wave_0.output")
+    rk = g.TimeStepping.ExplicitRungeKutta(g.TimeStepping.RK_CLASSIC_FOURTH_ORDER)
+    t, dt = 0.0, 0.3 * 2.42 / 40
+    for step in range(25):
+        e = cm.l2_error_inside(u.numpy(), exact(t))
+        assert abs(e - gold[step][2]) <= 2e-8 * gold[step][2], (step, e, gold[step], iters[-4:])
+        t = rk.evolve_one_time_step(f, t, dt, [u, v])
+    print(f"wave_0 on the GPU: 25 steps, mass CG iterations {min(iters)}..{max(iters)}")
+
+
+def test_cut_heat_2d_rk4(lib):
+    """The 2D form of the heat-rk run (problem.h:72-127; x^9 y^8 exp(-t), wave-app.cc:95-121) with a Q1 level set: three
+    RK4 steps on the GPU (Jacobi-CG mass solves to 1e-12, time-dependent volume and surface loads from gdm_cut_load_vector)
+    against the oracle's run with an exact mass solve."""
+    import gdm_b200 as g
+    import scipy.sparse.linalg as sla
+    from oracle import wave_app
+    params = dict(wave_app.heat_preset(1), dim=2, n_subdivisions=24)
+    gs, os_, cm, ca, M, A, Mo, Ao = _gpu_wave_operators(g, params)
+    ex = lambda t: (lambda pt, c: pt[0] ** 9 * pt[1] ** 8 * np.exp(-t))
+    src = lambda t: (lambda pt, c: -pt[0] ** 7 * pt[1] ** 6 * np.exp(-t) * (pt[0] ** 2 * pt[1] ** 2 + 72 * pt[1] ** 2 + 56 * pt[0] ** 2))
+    n = gs.n_dofs()
+    u0 = O.interpolate(os_, lambda pts, c: pts[:, 0] ** 9 * pts[:, 1] ** 8)
+    u = g.Vector(gs, u0)
+    pre = g.PreconditionJacobi()
+    pre.initialize(M)
+    rhs, load = g.Vector(gs), g.Vector(gs)
+
+    def f(t, y, out):
+        A.vmult(rhs, y)
+        rhs.scale(-1.0)
+        load.upload(ca.load_vector(src(t), ex(t)))
+        rhs.add(1.0, load)
+        out.set(0.0)
+        g.SolverCG(g.ReductionControl(2000, 1e-30, 1e-12)).solve(M, out, rhs, pre)
+
+    solve = sla.factorized(Mo.tocsc())
+    fo = lambda t, y: solve(-(Ao @ y) + ca.load_vector(src(t), ex(t)))
+    rk, rko = g.TimeStepping.ExplicitRungeKutta(g.TimeStepping.RK_CLASSIC_FOURTH_ORDER), O.ExplicitRungeKutta4()
+    dx = 2.42 / 24
+    t, dt, yo = 0.0, params["cfl"] * dx ** 2, u0.copy()
+    for step in range(3):
+        rk.evolve_one_time_step(f, t, dt, u)
+        t, yo = rko.evolve_one_time_step(fo, t, dt, yo)
+    print(f"cut heat 2D: difference to the oracle run {rel_err(u.numpy(), yo):.2e}")
+    assert rel_err(u.numpy(), yo) <= 1e-9
+    assert abs(cm.l2_error_inside(u.numpy(), ex(t)) - cm.l2_error_inside(yo, ex(t))) <= 1e-10
