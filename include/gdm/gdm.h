@@ -454,6 +454,13 @@ namespace dealii
     {
       internal::check(gdm_operator_mass_inverse(h, dst.handle(), src.handle()));
     }
+    // irregular rows (cut cells, ghost penalty, Nitsche) that replace the tensor-product rows: the part of the
+    // assembled matrices of prototypes/cut_poisson_01_gdm.cc:196-329 / wave/{mass,stiffness}.h that is not Kronecker
+    void attach_irregular_rows(const std::vector<uint64_t> &row_ids, const std::vector<uint64_t> &rowptr,
+                               const std::vector<uint64_t> &col, const std::vector<double> &val)
+    {
+      internal::check(gdm_operator_attach_csr(h, row_ids.size(), row_ids.data(), rowptr.data(), col.data(), val.data()));
+    }
     unsigned long long m() const { return gdm_operator_m(h); }
     unsigned long long n() const { return gdm_operator_m(h); }
     gdm_operator_t     handle() const { return h; }
@@ -881,4 +888,107 @@ namespace GDM
       return std::sqrt(s);
     }
   } // namespace VectorTools
+
+  // ----------------------------------------------------------------------- cut-cell set-up
+  // What prototypes/cut_poisson_01_gdm.cc does with NonMatching::{MeshClassifier, FEValues} and FEInterfaceValues
+  // before the solve (:105-121 classification of a Q1 level set, :176-190 cut quadrature, :196-329 assembly,
+  // :349-398 error), as one host-side object over gdm_cut_* whose rows go to SparseMatrix::attach_irregular_rows.
+  // kind_mass = true gives the cut mass matrix of applications/wave/include/gdm/wave/mass.h:47-249.
+  template <int dim>
+  class CutCellSetup
+  {
+  public:
+    struct Parameters
+    {
+      bool   ghost_penalty     = true;
+      int    gp_h_power        = 1;    // 1: the prototype; 3: the wave application's matrices
+      double ghost_parameter   = 0.5;
+      double nitsche_parameter = -1.0; // default 5 (p+1) p
+      double rhs_value         = 4.0;
+      double boundary_value    = 1.0;
+      bool   kind_mass         = false;
+      double outside_diagonal  = 1.0;
+    };
+    CutCellSetup(const unsigned int fe_degree, const unsigned int n_subdivisions, const double left, const double right,
+                 const Function<dim> &level_set_function, const Parameters &prm = Parameters())
+    {
+      gdm_cut_desc d{};
+      d.dim       = dim;
+      d.fe_degree = (int)fe_degree;
+      std::size_t n_nodes = 1;
+      for (int e = 0; e < dim; ++e)
+        {
+          d.n_subdivisions[e] = n_subdivisions;
+          d.lo[e]             = left;
+          d.hi[e]             = right;
+          n_nodes *= n_subdivisions + 1;
+        }
+      d.ghost_penalty     = prm.ghost_penalty;
+      d.gp_h_power        = prm.gp_h_power;
+      d.ghost_parameter   = prm.ghost_parameter;
+      d.nitsche_parameter = prm.nitsche_parameter >= 0 ? prm.nitsche_parameter : 5.0 * (fe_degree + 1) * fe_degree;
+      d.rhs_value         = prm.rhs_value;
+      d.boundary_value    = prm.boundary_value;
+      d.kind              = prm.kind_mass ? 1 : 0;
+      d.outside_diagonal  = prm.outside_diagonal;
+      // VectorTools::interpolate of the level set into FE_Q(1): nodal values, x fastest
+      std::vector<double> level_set(n_nodes);
+      const double        h = (right - left) / n_subdivisions;
+      for (std::size_t i = 0; i < n_nodes; ++i)
+        {
+          Point<dim>  x;
+          std::size_t r = i;
+          for (int e = 0; e < dim; ++e)
+            {
+              x[e] = left + (r % (n_subdivisions + 1)) * h;
+              r /= n_subdivisions + 1;
+            }
+          level_set[i] = level_set_function.value(x, 0);
+        }
+      n_dofs = n_nodes;
+      dealii::internal::check(gdm_cut_poisson_create(&d, level_set.data(), &cut));
+    }
+    CutCellSetup(const CutCellSetup &) = delete;
+    ~CutCellSetup()
+    {
+      if (cut)
+        gdm_cut_destroy(cut);
+    }
+    void attach_to(SparseMatrix<double> &matrix) const
+    {
+      uint64_t n_rows = 0, nnz = 0;
+      dealii::internal::check(gdm_cut_sizes(cut, &n_rows, &nnz, nullptr, nullptr));
+      std::vector<uint64_t> row_ids(n_rows), rowptr(n_rows + 1), col(nnz);
+      std::vector<double>   val(nnz);
+      dealii::internal::check(gdm_cut_rows(cut, row_ids.data(), rowptr.data(), col.data(), val.data()));
+      matrix.attach_irregular_rows(row_ids, rowptr, col, val);
+    }
+    std::vector<double> rhs() const
+    {
+      std::vector<double> b(n_dofs);
+      dealii::internal::check(gdm_cut_rhs(cut, b.data()));
+      return b;
+    }
+    // (v, f) over the inside part + <gamma_D / h v - dv/dn, g> on the surface (wave/stiffness.h:186-260); either may be null
+    std::vector<double> load_vector(const Function<dim> *f, const Function<dim> *g) const
+    {
+      std::vector<double>      b(n_dofs);
+      VectorTools::FnCtx<dim>  cf{f}, cg{g};
+      dealii::internal::check(gdm_cut_load_vector(cut, f ? &VectorTools::fn_trampoline<dim> : nullptr, &cf,
+                                                  g ? &VectorTools::fn_trampoline<dim> : nullptr, &cg, b.data()));
+      return b;
+    }
+    double l2_error_inside(const std::vector<double> &solution, const Function<dim> &exact) const
+    {
+      VectorTools::FnCtx<dim> c{&exact};
+      double                  e = 0;
+      dealii::internal::check(gdm_cut_l2_error_inside(cut, solution.data(), &VectorTools::fn_trampoline<dim>, &c, &e));
+      return e;
+    }
+    gdm_cut_t handle() const { return cut; }
+
+  private:
+    gdm_cut_t   cut    = nullptr;
+    std::size_t n_dofs = 0;
+  };
 } // namespace GDM

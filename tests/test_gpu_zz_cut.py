@@ -167,3 +167,16 @@ def test_cut_heat_2d_rk4(lib):
     print(f"cut heat 2D: difference to the oracle run {rel_err(u.numpy(), yo):.2e}")
     assert rel_err(u.numpy(), yo) <= 1e-9
     assert abs(cm.l2_error_inside(u.numpy(), ex(t)) - cm.l2_error_inside(yo, ex(t))) <= 1e-10
+
+
+def test_cut_poisson_01_gdm_cpp_driver(lib, golden_dir):
+    """examples/cut_poisson_01_gdm.cc (the reference's prototype against include/gdm): same table as
+    prototypes/cut_poisson_01_gdm.output; the errors are printed with 5 digits and may differ by one unit in the last."""
+    import re
+    from test_gpu_examples import _run
+    out = _run("cut_poisson_01_gdm")
+    got = [(float(h), float(e)) for h, e in re.findall(r"^\s*([0-9.]+)\s+([0-9.e+-]+)\s*$", out, flags=re.M)]
+    gold = golden_errors(golden_dir)
+    assert len(got) == 2 and out.count("Mesh size  L2-Error") == 2, out
+    for (h, e), ge in zip(got, gold):
+        assert abs(h - 0.0378) < 1e-4 and abs(e - ge) <= 1.5e-8, (out, gold)
