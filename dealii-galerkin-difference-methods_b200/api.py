@@ -777,7 +777,7 @@ class CutPoisson:
 
     def __init__(self, dim, fe_degree, n_subdivisions, lo, hi, level_set, ghost_penalty=True, ghost_parameter=0.5,
                  nitsche_parameter=None, rhs_value=4.0, boundary_value=1.0, gp_h_power=1, kind="stiffness",
-                 outside_diagonal=1.0):
+                 outside_diagonal=1.0, row_range=None):
         self.lib = capi.load()
         d = capi.CutDesc()
         d.dim, d.fe_degree = dim, fe_degree
@@ -789,6 +789,8 @@ class CutPoisson:
         d.nitsche_parameter = float(5.0 * (fe_degree + 1) * fe_degree if nitsche_parameter is None else nitsche_parameter)
         d.rhs_value, d.boundary_value = float(rhs_value), float(boundary_value)
         d.kind, d.outside_diagonal = {"stiffness": 0, "mass": 1}[kind], float(outside_diagonal)
+        if row_range is not None:  # the locally owned DoF range of a rank (System.locally_owned_range())
+            d.row_begin, d.row_end = int(row_range[0]), int(row_range[1])
         self.n_dofs = int(np.prod([int(n) + 1 for n in n_subdivisions[:dim]]))
         self.n_cells = int(np.prod([int(n) for n in n_subdivisions[:dim]]))
         level_set = np.ascontiguousarray(level_set, dtype=np.float64)

@@ -65,7 +65,8 @@ class CutDesc(C.Structure):
     _fields_ = [("dim", C.c_int), ("fe_degree", C.c_int), ("n_subdivisions", C.c_uint32 * 3),
                 ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("ghost_penalty", C.c_int), ("gp_h_power", C.c_int),
                 ("ghost_parameter", C.c_double), ("nitsche_parameter", C.c_double), ("rhs_value", C.c_double),
-                ("boundary_value", C.c_double), ("kind", C.c_int), ("outside_diagonal", C.c_double)]
+                ("boundary_value", C.c_double), ("kind", C.c_int), ("outside_diagonal", C.c_double),
+                ("row_begin", C.c_uint64), ("row_end", C.c_uint64)]
 
 
 FUNCTION_FN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_int, C.c_void_p)

@@ -21,7 +21,10 @@
 #include <cmath>
 #include <array>
 #include <cstring>
+#include <chrono>
+#include <cstdlib>
 #include <map>
+#include <thread>
 
 #include "gdm_internal.h"
 
@@ -567,6 +570,12 @@ namespace gdm
         return -1;
       }
 
+      struct CutScratch
+      {
+        std::vector<Pt>     ipts, spts;
+        std::vector<double> value, grads[3];
+      };
+      void cut_cell_matrix(const int *idx, CutScratch &sc, double *local, double *lrhs) const;
       void build();
       void load_vector(gdm_function_fn f, void *f_user, gdm_function_fn g, void *g_user, double *out);
 
@@ -579,6 +588,80 @@ namespace gdm
       std::vector<CutCellLoad> cut_loads;
       bool                     cut_loads_built = false;
     };
+
+
+    // dense cell matrix and load vector of an intersected cell (prototypes/cut_poisson_01_gdm.cc:212-283); a pure
+    // function of the cell, evaluated by several threads
+    void Assembly::cut_cell_matrix(const int *idx, CutScratch &sc, double *local, double *lrhs) const
+    {
+      const bool   mass = desc.kind == 1;
+      const double vol = cell_volume(), nitsche = desc.nitsche_parameter / h_min();
+        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        vertex_values(idx, v);
+        sc.ipts.clear();
+        sc.spts.clear();
+        cut_quadrature(dim, v, gauss, sc.ipts, sc.spts);
+        std::fill(local, local + (size_t)npc * npc, 0.0);
+        std::fill(lrhs, lrhs + npc, 0.0);
+        if (!sc.ipts.empty())
+          {
+            shape_at_points(idx, sc.ipts, sc.value, sc.grads);
+            for (size_t q = 0; q < sc.ipts.size(); ++q)
+              {
+                const double jxw = sc.ipts[q].w * vol;
+                for (int i = 0; i < npc; ++i)
+                  {
+                    lrhs[i] += desc.rhs_value * sc.value[q * npc + i] * jxw;
+                    for (int j = 0; j < npc; ++j)
+                      {
+                        double s = 0;
+                        if (mass)
+                          s = sc.value[q * npc + i] * sc.value[q * npc + j];
+                        else
+                          for (int e = 0; e < dim; ++e)
+                            s += sc.grads[e][q * npc + i] * sc.grads[e][q * npc + j];
+                        local[(size_t)i * npc + j] += s * jxw;
+                      }
+                  }
+              }
+          }
+        if (!sc.spts.empty() && !mass)
+          {
+            shape_at_points(idx, sc.spts, sc.value, sc.grads);
+            std::vector<double> ng(npc);
+            for (size_t q = 0; q < sc.spts.size(); ++q)
+              {
+                // unit-cell normal and measure -> physical (anisotropic spacing allowed)
+                double nph[3] = {0, 0, 0}, scale = 0;
+                for (int e = 0; e < dim; ++e)
+                  {
+                    nph[e] = sc.spts[q].n[e] / h[e];
+                    scale += nph[e] * nph[e];
+                  }
+                scale = std::sqrt(scale);
+                for (int e = 0; e < dim; ++e)
+                  nph[e] /= scale;
+                const double jxw = sc.spts[q].w * vol * scale;
+                for (int i = 0; i < npc; ++i)
+                  {
+                    double s = 0;
+                    for (int e = 0; e < dim; ++e)
+                      s += nph[e] * sc.grads[e][q * npc + i];
+                    ng[i] = s;
+                  }
+                for (int i = 0; i < npc; ++i)
+                  {
+                    const double vi = sc.value[q * npc + i];
+                    lrhs[i] += desc.boundary_value * (nitsche * vi - ng[i]) * jxw;
+                    for (int j = 0; j < npc; ++j)
+                      {
+                        const double vj = sc.value[q * npc + j];
+                        local[(size_t)i * npc + j] += (-ng[i] * vj - ng[j] * vi + nitsche * vi * vj) * jxw;
+                      }
+                  }
+              }
+          }
+    }
 
     void Assembly::build()
     {
@@ -623,22 +706,15 @@ namespace gdm
         }
       std::vector<int64_t> slot(n_dofs, -1);
       n_band_rows = 0;
-      for (uint64_t i = 0; i < n_dofs; ++i)
+      // rows of this rank only (slab partition of the DoFs, system.h:720-757): every rank runs the generator on its range
+      const uint64_t row_b = desc.row_end > desc.row_begin ? desc.row_begin : 0;
+      const uint64_t row_e = desc.row_end > desc.row_begin ? std::min<uint64_t>(desc.row_end, n_dofs) : n_dofs;
+      for (uint64_t i = row_b; i < row_e; ++i)
         if (touched[i] && irregular[i])
           slot[i] = (int64_t)n_band_rows++;
       std::vector<double> acc(n_band_rows * box, 0.0);
       rhs.assign(n_dofs, 0.0);
 
-      auto box_index = [&](const int *drow, const int *dcol) {
-        uint64_t o = 0, s = 1;
-        for (int e = 0; e < dim; ++e)
-          {
-            const int delta = dcol[e] - drow[e] + Bc;
-            o += (uint64_t)delta * s;
-            s *= B;
-          }
-        return o;
-      };
       // local index -> node offsets inside the window
       std::vector<int> lidx(3 * npc, 0);
       {
@@ -652,21 +728,36 @@ namespace gdm
                 lidx[3 * m + 2] = k;
               }
       }
+      // box offset of (row i, column j) = base(window offsets) - lpart[i] + lpart[j]
+      std::vector<int64_t> lpart(npc);
+      for (int m = 0; m < npc; ++m)
+        {
+          int64_t o = 0, st = 1;
+          for (int e = 0; e < dim; ++e)
+            {
+              o += (int64_t)lidx[3 * m + e] * st;
+              st *= B;
+            }
+          lpart[m] = o;
+        }
       auto scatter = [&](const std::vector<uint64_t> &rdofs, const int *roff, const std::vector<uint64_t> &cdofs,
                          const int *coff, const double *mat, int ld, int r0, int c0) {
         (void)cdofs;
+        int64_t base = 0, st = 1;
+        for (int e = 0; e < dim; ++e)
+          {
+            base += (int64_t)(coff[e] - roff[e] + Bc) * st;
+            st *= B;
+          }
         for (int i = 0; i < npc; ++i)
           {
-            const int64_t s = slot[rdofs[i]];
-            if (s < 0)
+            const int64_t sl = slot[rdofs[i]];
+            if (sl < 0)
               continue;
-            const int rn[3] = {roff[0] + lidx[3 * i], roff[1] + lidx[3 * i + 1], roff[2] + lidx[3 * i + 2]};
-            double   *row   = &acc[(uint64_t)s * box];
+            double       *row = &acc[(uint64_t)sl * box] + (base - lpart[i]);
+            const double *m   = mat + (size_t)(r0 + i) * ld + c0;
             for (int j = 0; j < npc; ++j)
-              {
-                const int cn[3] = {coff[0] + lidx[3 * j], coff[1] + lidx[3 * j + 1], coff[2] + lidx[3 * j + 2]};
-                row[box_index(rn, cn)] += mat[(size_t)(r0 + i) * ld + (c0 + j)];
-              }
+              row[lpart[j]] += m[j];
           }
       };
 
@@ -757,8 +848,69 @@ namespace gdm
         return gp_cache.emplace(key, std::move(S)).first->second;
       };
 
-      std::vector<Pt> ipts, spts;
-      for (uint64_t cell = 0; cell < n_cells; ++cell)
+      // Blocks of consecutive cells: the intersected cells of a block are evaluated by all threads, then the block is
+      // scattered in cell order (the sums do not depend on the number of threads).
+      double     t_cut = 0, t_scatter = 0;
+      const auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+      unsigned n_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      if (const char *env = std::getenv("GDM_CUT_THREADS"))
+        n_threads = (unsigned)std::max(1, std::atoi(env));
+      const size_t          block_cut_cells = 64 * (size_t)n_threads;
+      std::vector<double>   block_local(block_cut_cells * npc * npc), block_rhs(block_cut_cells * npc);
+      std::vector<uint64_t> block_cells;
+      std::vector<int32_t>  block_slot;
+      std::vector<CutScratch> scratch(n_threads);
+      auto cell_in_range = [&](const int *cidx) {
+        if (row_b == 0 && row_e == n_dofs)
+          return true;
+        int                   o[3];
+        std::vector<uint64_t> d;
+        cell_dofs(cidx, o, d);
+        for (uint64_t i : d)
+          if (i >= row_b && i < row_e)
+            return true;
+        return false;
+      };
+      for (uint64_t b0 = 0; b0 < n_cells;)
+        {
+          uint64_t b1 = b0;
+          block_cells.clear();
+          block_slot.clear();
+          for (; b1 < n_cells && block_cells.size() < block_cut_cells; ++b1)
+            {
+              block_slot.push_back(-1);
+              if (location[b1] != INTERSECTED)
+                continue;
+              block_slot.back() = (int32_t)block_cells.size();
+              block_cells.push_back(b1);
+            }
+          const double t0 = now();
+          auto worker = [&](unsigned tid) {
+            int cidx[3];
+            for (size_t k = tid; k < block_cells.size(); k += n_threads)
+              {
+                cell_index(block_cells[k], cidx);
+                if (!cell_in_range(cidx))
+                  {
+                    std::fill(&block_rhs[k * npc], &block_rhs[(k + 1) * npc], 0.0);
+                    continue;
+                  }
+                cut_cell_matrix(cidx, scratch[tid], &block_local[k * npc * npc], &block_rhs[k * npc]);
+              }
+          };
+          if (n_threads > 1 && block_cells.size() > 1)
+            {
+              std::vector<std::thread> pool;
+              for (unsigned tid = 0; tid < n_threads; ++tid)
+                pool.emplace_back(worker, tid);
+              for (auto &th : pool)
+                th.join();
+            }
+          else
+            worker(0);
+          const double t1 = now();
+          t_cut += t1 - t0;
+      for (uint64_t cell = b0; cell < b1; ++cell)
         {
           if (location[cell] == OUTSIDE)
             continue;
@@ -777,74 +929,12 @@ namespace gdm
             }
           else
             {
-              double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-              vertex_values(idx, v);
-              ipts.clear();
-              spts.clear();
-              cut_quadrature(dim, v, gauss, ipts, spts);
-              std::fill(local.begin(), local.end(), 0.0);
-              std::fill(lrhs.begin(), lrhs.end(), 0.0);
-              if (!ipts.empty())
-                {
-                  shape_at_points(idx, ipts, value, grads);
-                  for (size_t q = 0; q < ipts.size(); ++q)
-                    {
-                      const double jxw = ipts[q].w * vol;
-                      for (int i = 0; i < npc; ++i)
-                        {
-                          lrhs[i] += desc.rhs_value * value[q * npc + i] * jxw;
-                          for (int j = 0; j < npc; ++j)
-                            {
-                              double s = 0;
-                              if (mass)
-                                s = value[q * npc + i] * value[q * npc + j];
-                              else
-                                for (int e = 0; e < dim; ++e)
-                                  s += grads[e][q * npc + i] * grads[e][q * npc + j];
-                              local[(size_t)i * npc + j] += s * jxw;
-                            }
-                        }
-                    }
-                }
-              if (!spts.empty() && !mass)
-                {
-                  shape_at_points(idx, spts, value, grads);
-                  std::vector<double> ng(npc);
-                  for (size_t q = 0; q < spts.size(); ++q)
-                    {
-                      // unit-cell normal and measure -> physical (anisotropic spacing allowed)
-                      double nph[3] = {0, 0, 0}, scale = 0;
-                      for (int e = 0; e < dim; ++e)
-                        {
-                          nph[e] = spts[q].n[e] / h[e];
-                          scale += nph[e] * nph[e];
-                        }
-                      scale = std::sqrt(scale);
-                      for (int e = 0; e < dim; ++e)
-                        nph[e] /= scale;
-                      const double jxw = spts[q].w * vol * scale;
-                      for (int i = 0; i < npc; ++i)
-                        {
-                          double s = 0;
-                          for (int e = 0; e < dim; ++e)
-                            s += nph[e] * grads[e][q * npc + i];
-                          ng[i] = s;
-                        }
-                      for (int i = 0; i < npc; ++i)
-                        {
-                          const double vi = value[q * npc + i];
-                          lrhs[i] += desc.boundary_value * (nitsche * vi - ng[i]) * jxw;
-                          for (int j = 0; j < npc; ++j)
-                            {
-                              const double vj = value[q * npc + j];
-                              local[(size_t)i * npc + j] += (-ng[i] * vj - ng[j] * vi + nitsche * vi * vj) * jxw;
-                            }
-                        }
-                    }
-                }
+              const double *local = &block_local[(size_t)block_slot[cell - b0] * npc * npc];
+              const double *lrhs  = &block_rhs[(size_t)block_slot[cell - b0] * npc];
               for (int i = 0; i < npc; ++i)
                 rhs[dofs[i]] += lrhs[i];
-              scatter(dofs, off, dofs, off, local.data(), npc, 0, 0);
+              if (cell_in_range(idx))
+                scatter(dofs, off, dofs, off, local, npc, 0, 0);
             }
           if (desc.ghost_penalty)
             for (int d = 0; d < dim; ++d)
@@ -864,6 +954,11 @@ namespace gdm
                   scatter(ndofs, noff, ndofs, noff, S.data(), n2, npc, npc);
                 }
         }
+          b0 = b1;
+          t_scatter += now() - t1;
+        }
+      if (std::getenv("GDM_CUT_VERBOSE"))
+        std::fprintf(stderr, "gdm_cut: %u threads, cut cells %.3f s, scatter %.3f s\n", n_threads, t_cut, t_scatter);
 
       // rows in ascending DoF order; columns ascending inside a row
       row_ids.clear();
@@ -871,7 +966,7 @@ namespace gdm
       col.clear();
       val.clear();
       n_identity_rows = 0;
-      for (uint64_t i = 0; i < n_dofs; ++i)
+      for (uint64_t i = row_b; i < row_e; ++i)
         {
           if (!touched[i])
             {

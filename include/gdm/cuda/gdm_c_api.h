@@ -296,7 +296,7 @@ int gdm_system_write_vtu(gdm_system_t sys, const double *values, const char *lab
 /* ------------------------------------------------------- cut-cell set-up (host) */
 /* The step before the hot path in a CutFEM run: level-set classification, cut quadrature and the
  * assembly of the rows that differ from the plain stiffness operator, ready for gdm_operator_attach_csr.  Host only,
- * no context needed, scalar field, no constraints, one rank (all rows).
+ * no context needed, scalar field, no constraints; every rank assembles its own row range (row_begin, row_end).
  *   classification   NonMatching::MeshClassifier for a Q1 level set (prototypes/cut_poisson_01_gdm.cc:105-121)
  *   quadrature       NonMatching::FEValues with QGauss<1>(p+1) (prototypes/cut_poisson_01_gdm.cc:176-190)
  *   assembly         prototypes/cut_poisson_01_gdm.cc:196-329 (volume + Nitsche + ghost penalty, zero diagonal -> 1)
@@ -317,6 +317,9 @@ typedef struct gdm_cut_desc {
                                  use ghost_parameter = gamma_M, gp_h_power = 3) */
   double   outside_diagonal;  /* diagonal of the rows no active cell touches: 1 for a matrix that is solved with
                                  (cut_poisson_01_gdm.cc:324-329, wave/mass.h:246-248), 0 for the matrix-free residual */
+  uint64_t row_begin, row_end; /* rows (global DoFs) to assemble: the locally owned range of a rank
+                                  (gdm_system_locally_owned_range); 0, 0 = all.  With a range the right-hand side is
+                                  complete in that range only. */
 } gdm_cut_desc;
 typedef struct gdm_cut_s *gdm_cut_t;
 /* level_set: nodal values of the Q1 level set at the grid nodes, DoF order (x fastest); negative = inside */

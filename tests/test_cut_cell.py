@@ -275,3 +275,31 @@ def test_product_setup_reproduces_wave_0_golden_on_host(lib, golden_dir):
         e = cm.l2_error_inside(y[:n], lambda pt, c: np.cos(k * abs(pt[0])) * np.cos(k * t))
         assert abs(e - gold[step][2]) <= 6e-9 * gold[step][2], (step, e, gold[step])
         t, y = rk.evolve_one_time_step(f, t, dt, y)
+
+
+@pytest.mark.parametrize("dim,n1,n_ranks", [(2, 20, 3), (3, 9, 2)])
+def test_product_rows_per_rank_range(lib, dim, n1, n_ranks):
+    """Every rank assembles the rows of its own slab (system.h:720-757) with no communication: the per-rank row sets
+    are disjoint, their union is the one-rank result entry by entry, the right-hand side agrees inside each range."""
+    import gdm_b200 as g
+    s, ls = sphere_problem(dim, 3, n1)
+    box = ([n1] * dim, [-1.21] * dim, [1.21] * dim)
+    full = g.CutPoisson(dim, 3, *box, ls, ghost_penalty=True)
+    rows, rowptr, col, val = full.rows()
+    rhs = full.rhs()
+    got_rows, got_col, got_val, got_ptr = [], [], [], [0]
+    for r in range(n_ranks):
+        os_r = O.System(dim, 3, 1, rank=r, n_ranks=n_ranks)
+        os_r.subdivided_hyper_cube(n1, -1.21, 1.21)
+        b, e = os_r.locally_owned_range()
+        part = g.CutPoisson(dim, 3, *box, ls, ghost_penalty=True, row_range=(b, e))
+        pr, pp, pc, pv = part.rows()
+        assert np.all((pr >= b) & (pr < e))
+        assert np.array_equal(part.rhs()[b:e], rhs[b:e])
+        got_rows.append(pr)
+        got_col.append(pc)
+        got_val.append(pv)
+        got_ptr += list(got_ptr[-1] + pp[1:].astype(np.int64))
+    assert np.array_equal(np.concatenate(got_rows), rows)
+    assert np.array_equal(np.array(got_ptr, dtype=np.uint64), rowptr)
+    assert np.array_equal(np.concatenate(got_col), col) and np.array_equal(np.concatenate(got_val), val)
