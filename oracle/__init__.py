@@ -13,7 +13,8 @@ Rules:
 Pinning: the restatement is checked against the reference's committed golden
 outputs (`tests/golden/*.output`, copied by `tests/golden/make_golden.py`):
 poly_01, fe_02_gdm, poisson_01_gdm, poisson_02_gdm (1 and 3 ranks), mass_01_gdm,
-mass_02_gdm.  3D has no reference golden (`tests/fe_01_gdm.output` is missing
+mass_02_gdm, elasticity_01_gdm, prototypes/cut_poisson_01_gdm (cut.py), applications/wave/tests/wave_0 and heat_1
+(wave_app.py, every printed step).  3D has no reference golden (`tests/fe_01_gdm.output` is missing
 upstream): 3D parity is pinned only through the dimension-generic cell-loop
 restatement validated in 1D/2D.
 """
@@ -28,5 +29,6 @@ from .solvers import (ReductionControl, SolverControlNoConvergence, solver_cg,
 from .kron_apply import KronApply, kron_apply, constraint_matrices_1d
 from .vector_tools import interpolate, integrate_difference, compute_global_error
 from .mass_inverse import kron_mass_solve, bordered_solve_1d, free_matrix_1d
+from . import cut, wave_app
 
 __all__ = [n for n in dir() if not n.startswith("_")]
