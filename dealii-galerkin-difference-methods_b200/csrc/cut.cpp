@@ -606,24 +606,35 @@ namespace gdm
         if (!sc.ipts.empty())
           {
             shape_at_points(idx, sc.ipts, sc.value, sc.grads);
+            // upper triangle only (the products commute, so the mirrored entries carry the same bits), direction sums
+            // written out so that the j loop vectorises
             for (size_t q = 0; q < sc.ipts.size(); ++q)
               {
-                const double jxw = sc.ipts[q].w * vol;
+                const double  jxw = sc.ipts[q].w * vol;
+                const double *vq = sc.value.data() + q * npc, *a0 = sc.grads[0].data() + q * npc,
+                             *a1 = dim > 1 ? sc.grads[1].data() + q * npc : nullptr,
+                             *a2 = dim > 2 ? sc.grads[2].data() + q * npc : nullptr;
                 for (int i = 0; i < npc; ++i)
                   {
-                    lrhs[i] += desc.rhs_value * sc.value[q * npc + i] * jxw;
-                    for (int j = 0; j < npc; ++j)
-                      {
-                        double s = 0;
-                        if (mass)
-                          s = sc.value[q * npc + i] * sc.value[q * npc + j];
-                        else
-                          for (int e = 0; e < dim; ++e)
-                            s += sc.grads[e][q * npc + i] * sc.grads[e][q * npc + j];
-                        local[(size_t)i * npc + j] += s * jxw;
-                      }
+                    lrhs[i] += desc.rhs_value * vq[i] * jxw;
+                    double *row = local + (size_t)i * npc;
+                    if (mass)
+                      for (int j = i; j < npc; ++j)
+                        row[j] += (vq[i] * vq[j]) * jxw;
+                    else if (dim == 1)
+                      for (int j = i; j < npc; ++j)
+                        row[j] += (a0[i] * a0[j]) * jxw;
+                    else if (dim == 2)
+                      for (int j = i; j < npc; ++j)
+                        row[j] += (a0[i] * a0[j] + a1[i] * a1[j]) * jxw;
+                    else
+                      for (int j = i; j < npc; ++j)
+                        row[j] += ((a0[i] * a0[j] + a1[i] * a1[j]) + a2[i] * a2[j]) * jxw;
                   }
               }
+            for (int i = 1; i < npc; ++i)
+              for (int j = 0; j < i; ++j)
+                local[(size_t)i * npc + j] = local[(size_t)j * npc + i];
           }
         if (!sc.spts.empty() && !mass)
           {

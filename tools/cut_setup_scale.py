@@ -14,8 +14,13 @@ import gdm_b200 as g  # noqa: E402
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    n_ranks = int(sys.argv[sys.argv.index("--ranks") + 1]) if "--ranks" in sys.argv else 1
+    argv = sys.argv[1:]
+    n_ranks = 1
+    if "--ranks" in argv:
+        i = argv.index("--ranks")
+        n_ranks = int(argv[i + 1])
+        del argv[i:i + 2]
+    args = argv
     for n1 in [int(a) for a in args] or [48]:
         ax = -1.21 + np.arange(n1 + 1) * (2.42 / n1)
         z, y, x = np.meshgrid(ax, ax, ax, indexing="ij")
