@@ -843,6 +843,15 @@ class CutPoisson:
         capi.check(self.lib.gdm_cut_l2_error_inside(self.h, u.ctypes.data_as(C.c_void_p), cb, None, C.byref(err)))
         return err.value
 
+    def error_norms_inside(self, u, exact):
+        """(L2, L1, Linf) over the inside part: the columns of `applications/wave` (`wave/problem.h:531-615`)."""
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        assert u.size == self.n_dofs
+        cb = VectorTools._wrap(exact)
+        out = (C.c_double * 3)()
+        capi.check(self.lib.gdm_cut_error_norms_inside(self.h, u.ctypes.data_as(C.c_void_p), cb, None, out))
+        return tuple(out)
+
     @staticmethod
     def quadrature(vertex_values, n_gauss):
         """The generator on one unit cell: vertex_values of shape (2,)*dim indexed [x][y][z].

@@ -140,6 +140,7 @@ SIGNATURES = {
     "gdm_cut_locations": (C.c_int, [_H, C.c_void_p]),
     "gdm_cut_load_vector": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gdm_cut_l2_error_inside": (C.c_int, [_H, C.c_void_p, FUNCTION_FN, C.c_void_p, _PD]),
+    "gdm_cut_error_norms_inside": (C.c_int, [_H, C.c_void_p, FUNCTION_FN, C.c_void_p, _PD]),
     "gdm_cut_quadrature": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_uint64, _PU64, C.c_void_p, C.c_void_p, _PU64,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "gdm_system_write_matrix": (C.c_int, [_H, _H, C.POINTER(OperatorDesc), C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]),

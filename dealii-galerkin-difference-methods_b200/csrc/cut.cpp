@@ -1169,6 +1169,12 @@ struct gdm_cut_s
   }                                               \
   return GDM_OK;
 #define GDM_ARG(x) GDM_REQUIRE((x) != nullptr, GDM_ERR_INVALID, "null argument " #x)
+#define GDM_ARG_NOTHROW(x)                          \
+  if ((x) == nullptr)                              \
+    {                                              \
+      gdm::set_last_error("null argument " #x);    \
+      return GDM_ERR_INVALID;                      \
+    }
 
 extern "C" {
 
@@ -1314,13 +1320,13 @@ int gdm_cut_locations(gdm_cut_t c, uint8_t *location)
   GDM_CATCH
 }
 
-int gdm_cut_l2_error_inside(gdm_cut_t c, const double *u, gdm_function_fn exact, void *user, double *error)
+int gdm_cut_error_norms_inside(gdm_cut_t c, const double *u, gdm_function_fn exact, void *user, double *norms)
 {
   GDM_TRY
   GDM_ARG(c);
   GDM_ARG(u);
   GDM_ARG(exact);
-  GDM_ARG(error);
+  GDM_ARG(norms);
   const cut::Assembly  &a = c->a;
   std::vector<cut::Pt>  full, ipts, spts;
   const double          l0[3] = {0, 0, 0}, h1[3] = {1, 1, 1};
@@ -1329,7 +1335,7 @@ int gdm_cut_l2_error_inside(gdm_cut_t c, const double *u, gdm_function_fn exact,
   std::vector<uint64_t> dofs;
   int                   idx[3], off[3];
   const double          vol = a.cell_volume();
-  double                acc = 0;
+  double                acc = 0, l1 = 0, linf = 0;
   for (uint64_t cell = 0; cell < a.n_cells; ++cell)
     {
       if (a.location[cell] == cut::OUTSIDE)
@@ -1358,9 +1364,22 @@ int gdm_cut_l2_error_inside(gdm_cut_t c, const double *u, gdm_function_fn exact,
             x[e] = a.lo[e] + (idx[e] + (*pts)[q].x[e]) * a.h[e];
           const double diff = uh - exact(x, 0, user);
           acc += diff * diff * (*pts)[q].w * vol;
+          l1 += std::fabs(diff) * (*pts)[q].w * vol;
+          linf = std::max(linf, std::fabs(diff));
         }
     }
-  *error = std::sqrt(acc);
+  norms[0] = std::sqrt(acc);
+  norms[1] = l1;
+  norms[2] = linf;
   GDM_CATCH
+}
+
+int gdm_cut_l2_error_inside(gdm_cut_t c, const double *u, gdm_function_fn exact, void *user, double *error)
+{
+  GDM_ARG_NOTHROW(error);
+  double    norms[3] = {0, 0, 0};
+  const int rc = gdm_cut_error_norms_inside(c, u, exact, user, norms);
+  *error       = norms[0];
+  return rc;
 }
 }

@@ -338,6 +338,9 @@ int gdm_cut_load_vector(gdm_cut_t cut, gdm_function_fn f, void *f_user, gdm_func
 int gdm_cut_locations(gdm_cut_t cut, uint8_t *location /* n_cells: 0 inside, 1 outside, 2 intersected */);
 /* sqrt( sum over non-outside cells of the integral over the inside part of (u_h - exact)^2 ); u = all DoFs */
 int gdm_cut_l2_error_inside(gdm_cut_t cut, const double *u, gdm_function_fn exact, void *user, double *error);
+/* norms[3] = L2, L1, Linf (maximum over the quadrature points) of u_h - exact over the inside part: the three columns
+ * applications/wave prints after every step (wave/problem.h:531-615) */
+int gdm_cut_error_norms_inside(gdm_cut_t cut, const double *u, gdm_function_fn exact, void *user, double *norms);
 /* The quadrature generator on its own: unit cell, vertex_values[2^dim] (bit e of the index = upper end in direction e).
  * Fills at most `capacity` points per rule (points [q*dim + e]) and returns the full counts; arrays may be NULL. */
 int gdm_cut_quadrature(int dim, const double *vertex_values, int n_gauss, uint64_t capacity, uint64_t *n_inside,

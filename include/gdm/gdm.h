@@ -985,6 +985,14 @@ namespace GDM
       dealii::internal::check(gdm_cut_l2_error_inside(cut, solution.data(), &VectorTools::fn_trampoline<dim>, &c, &e));
       return e;
     }
+    // L2, L1, Linf over the inside part (wave/problem.h:531-615)
+    std::array<double, 3> error_norms_inside(const std::vector<double> &solution, const Function<dim> &exact) const
+    {
+      VectorTools::FnCtx<dim> c{&exact};
+      std::array<double, 3>   e{};
+      dealii::internal::check(gdm_cut_error_norms_inside(cut, solution.data(), &VectorTools::fn_trampoline<dim>, &c, e.data()));
+      return e;
+    }
     gdm_cut_t handle() const { return cut; }
 
   private:

@@ -174,6 +174,9 @@ def test_product_setup_reproduces_golden_on_host(lib, golden_dir):
     err = c.l2_error_inside(u, lambda pt, comp: 1.0 - (pt[0] ** 2 + pt[1] ** 2 - 1.0))
     assert abs(err - golden_errors(golden_dir)[1]) <= 1.5e-8
     assert abs(err - cut.l2_error_inside(s, ls, u, exact_solution(2))) <= 1e-15
+    norms = c.error_norms_inside(u, lambda pt, comp: 1.0 - (pt[0] ** 2 + pt[1] ** 2 - 1.0))
+    ref = cut.error_norms_inside(s, ls, u, exact_solution(2))
+    assert norms[0] == err and all(abs(a - b) <= 1e-10 * b for a, b in zip(norms, ref))
 
 
 def test_cut_argument_checks(lib):
