@@ -59,9 +59,9 @@ def test_compute_fails_loudly_without_gpu(lib):
 
 def test_cpp_drivers_compile_against_include_gdm(lib, tmp_path):
     """The C++ mirror of the reference interface (include/gdm/*.h) and the drivers written against it compile and link
-    (no run without a GPU): examples/{poisson_01_gdm, mass_01_gdm, advection_01_gdm, cut_poisson_01_gdm}.cc."""
+    (no run without a GPU): examples/{poisson_01_gdm, mass_01_gdm, advection_01_gdm, cut_poisson_01_gdm, wave_app}.cc."""
     pkg = os.path.join(ROOT, "dealii-galerkin-difference-methods_b200")
-    for name in ("poisson_01_gdm", "mass_01_gdm", "advection_01_gdm", "cut_poisson_01_gdm"):
+    for name in ("poisson_01_gdm", "mass_01_gdm", "advection_01_gdm", "cut_poisson_01_gdm", "wave_app"):
         exe = str(tmp_path / name)
         subprocess.check_call(["g++", "-O0", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
                                "-o", exe, os.path.join(ROOT, "examples", name + ".cc"), "-L" + pkg, "-lgdm_b200",

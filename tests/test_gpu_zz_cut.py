@@ -180,3 +180,21 @@ def test_cut_poisson_01_gdm_cpp_driver(lib, golden_dir):
     assert len(got) == 2 and out.count("Mesh size  L2-Error") == 2, out
     for (h, e), ge in zip(got, gold):
         assert abs(h - 0.0378) < 1e-4 and abs(e - ge) <= 1.5e-8, (out, gold)
+
+
+@pytest.mark.parametrize("simulation,golden", [("wave", "app_wave_wave_0.output"), ("heat-rk", "app_wave_heat_1.output")])
+def test_wave_app_cpp_driver(lib, golden_dir, simulation, golden):
+    """examples/wave_app.cc (the explicit runs of applications/wave/wave-app.cc against include/gdm) on the GPU: every
+    printed step of applications/wave/tests/{wave_0,heat_1}.output, all three error columns; the ` [L] solved in k`
+    lines carry this library's Jacobi-CG counts instead of the reference's AMG / ILU counts and are not compared."""
+    from test_gpu_examples import _run
+    from test_cut_cell import _app_golden
+    out = _run("wave_app", 1, simulation)
+    rows = [l.split() for l in out.splitlines() if l.strip() and not l.startswith(" [L]")]
+    gold = _app_golden(golden_dir, golden)
+    assert len(rows) == len(gold), out[-2000:]
+    assert out.count(" [L] solved in") == 4 * (len(gold) - 1)
+    for r, g_ in zip(rows, gold):
+        assert int(r[0]) == g_[0] and abs(float(r[1]) - g_[1]) <= 5.1e-6
+        for i in (2, 3, 4):
+            assert abs(float(r[i]) - g_[i]) <= 2e-8 * g_[i], (r, g_)
