@@ -301,7 +301,8 @@ def face_has_ghost_penalty(system, location, cell, d, side):
 
 # -------------------------------------------------------------------------------------------------- the assembly
 def assemble_cut_poisson(system, ls, ghost_penalty=True, ghost_parameter=0.5, nitsche_parameter=None,
-                         rhs_value=4.0, boundary_value=1.0, gp_h_power=1, kind="stiffness", outside_diagonal=1.0):
+                         rhs_value=4.0, boundary_value=1.0, gp_h_power=1, kind="stiffness", outside_diagonal=1.0,
+                         surface_terms=True):
     """Global matrix (CSR), right-hand side and cell locations of the CutFEM Poisson problem.
 
     Follows `prototypes/cut_poisson_01_gdm.cc:196-329` term by term (scalar field, no constraints).
@@ -309,7 +310,8 @@ def assemble_cut_poisson(system, ls, ghost_penalty=True, ghost_parameter=0.5, ni
     `kind="mass"`: the cut mass matrix of `applications/wave/include/gdm/wave/mass.h:47-249` instead (inside mass, no
     surface terms, ghost penalty with `ghost_parameter` = gamma_M and `gp_h_power=3`); the right-hand side is then
     (v, rhs_value) on the inside part.  `outside_diagonal=0` leaves the rows no active cell touches empty, which is
-    what the matrix-free residual `wave/stiffness.h:42-407` amounts to.
+    what the matrix-free residual `wave/stiffness.h:42-407` amounts to.  `surface_terms=False` drops the Nitsche terms
+    on the cut surface (`function_interface_dbc` unset: the two-domain runs couple there instead).
     """
     assert system.n_components == 1 and kind in ("stiffness", "mass")
     fval = rhs_value if callable(rhs_value) else (lambda pts: np.full(len(pts), float(rhs_value)))
@@ -362,7 +364,7 @@ def assemble_cut_poisson(system, ls, ghost_penalty=True, ghost_parameter=0.5, ni
                     for g in grads:
                         local += np.einsum("q,qi,qj->ij", jxw, g, g)
                 lrhs += np.einsum("q,q,qi->i", jxw, fval(physical_points(system, cell, ip)), value)
-            if len(sw) and kind == "stiffness":
+            if len(sw) and kind == "stiffness" and surface_terms:
                 value, grads = shape_at_points(system, cell, sp_)
                 nphys = sn / h
                 scale = np.linalg.norm(nphys, axis=1)
@@ -488,3 +490,86 @@ def apply_load(n, terms, fn):
     for dofs, pts, W in terms:
         np.add.at(b, dofs, np.asarray(fn(pts), dtype=float) @ W)
     return b
+
+
+# ---------------------------------------------------------------- two-domain (composite) runs of applications/wave
+def _boundary_face_rules(system, ls, cell, n_gauss):
+    """[(d, side, unit-cell points, weights)] for the faces of `cell` on the box boundary: the part of the face where
+    the level set is negative (`NonMatching::FEInterfaceValues::reinit(cell, f)`, `wave/stiffness.h:268-283`)."""
+    dim = system.dim
+    idx = system.cell_indices(cell)
+    xg, wg = gauss_legendre_01(n_gauss)
+    c = cell_vertex_values(system, ls, cell)
+    out = []
+    for d in range(dim):
+        for side in (0, 1):
+            if idx[d] != (0 if side == 0 else system.n_subdivisions[d] - 1):
+                continue
+            fc = _face(c, d, side)
+            if dim == 1:
+                pts, w = (np.zeros((1, 0)), np.ones(1)) if float(fc) < 0 else (np.zeros((0, 0)), np.zeros(0))
+            else:
+                pts, w = _volume([fc], [-1], np.zeros(dim - 1), np.ones(dim - 1), xg, wg)
+            if len(w):
+                out.append((d, side, np.insert(pts, d, float(side), axis=1), w))
+    return out
+
+
+def domain_boundary_terms(system, ls, nitsche_parameter):
+    """Nitsche terms on the box boundary for the domain {level set < 0} (`wave/stiffness.h:262-340`, term IV): the
+    matrix  -<d_n v, u> - <v, d_n u> + gamma_D / h <v, u>  and the load functional  <gamma_D / h v - d_n v, g>."""
+    dim, n = system.dim, system.n_dofs()
+    h = np.array(system.h)
+    hmin = float(h.min())
+    location = classify(system, ls)
+    rows, cols, vals, load = [], [], [], []
+    for cell in range(system.n_cells()):
+        if location[cell] == OUTSIDE:
+            continue
+        for d, side, pts, w in _boundary_face_rules(system, ls, cell, system.fe_degree + 1):
+            dofs = np.asarray(system.get_dof_indices(cell))
+            value, grads = shape_at_points(system, cell, pts)
+            jxw = w * float(np.prod(np.delete(h, d)))
+            ng = (1.0 if side else -1.0) * grads[d]
+            local = -np.einsum("q,qi,qj->ij", jxw, ng, value) - np.einsum("q,qi,qj->ij", jxw, value, ng) \
+                + nitsche_parameter / hmin * np.einsum("q,qi,qj->ij", jxw, value, value)
+            rows.append(np.repeat(dofs, len(dofs)))
+            cols.append(np.tile(dofs, len(dofs)))
+            vals.append(local.ravel())
+            load.append((dofs, physical_points(system, cell, pts), (nitsche_parameter / hmin * value - ng) * jxw[:, None]))
+    if not vals:
+        return sp.csr_matrix((n, n)), load
+    B = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
+    return B, load
+
+
+def coupling_matrices(system, ls):
+    """P = sum_q (n . grad phi_i) phi_j JxW and Q = sum_q phi_i phi_j JxW over the cut surface (n = normal of the level
+    set): the interface coupling of the two-domain residual (`wave/stiffness.h:441-574`) is
+        r0 -= -1/2 P [u] - 1/2 P^T (u0 + u1) + tau / h Q [u],   r1 -= -1/2 P [u] + 1/2 P^T (u0 + u1) - tau / h Q [u]
+    with [u] = u0 - u1 and tau = gamma_D / 2."""
+    dim, n, p = system.dim, system.n_dofs(), system.fe_degree
+    h = np.array(system.h)
+    vol = float(np.prod(h))
+    location = classify(system, ls)
+    rows, cols, pv, qv = [], [], [], []
+    for cell in range(system.n_cells()):
+        if location[cell] != INTERSECTED:
+            continue
+        _, (sp_, sw, sn) = cut_quadrature(cell_vertex_values(system, ls, cell), p + 1)
+        if not len(sw):
+            continue
+        dofs = np.asarray(system.get_dof_indices(cell))
+        value, grads = shape_at_points(system, cell, sp_)
+        nphys = sn / h
+        scale = np.linalg.norm(nphys, axis=1)
+        nphys = nphys / scale[:, None]
+        jxw = sw * vol * scale
+        ng = sum(nphys[:, e][:, None] * grads[e] for e in range(dim))
+        rows.append(np.repeat(dofs, len(dofs)))
+        cols.append(np.tile(dofs, len(dofs)))
+        pv.append(np.einsum("q,qi,qj->ij", jxw, ng, value).ravel())
+        qv.append(np.einsum("q,qi,qj->ij", jxw, value, value).ravel())
+    r, c = np.concatenate(rows), np.concatenate(cols)
+    return (sp.coo_matrix((np.concatenate(pv), (r, c)), shape=(n, n)).tocsr(),
+            sp.coo_matrix((np.concatenate(qv), (r, c)), shape=(n, n)).tocsr())

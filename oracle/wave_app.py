@@ -130,3 +130,65 @@ def heat_impl_run(params=None):
         postprocess(t1)
         time.advance_time()
     return rows
+
+
+def composite_run(params, second_order):
+    """The two-domain runs (`problem.h:129-209` heat, `:347-437` wave; presets `wave-app.cc:152-220,286-336`): one field
+    on {level set < 0}, one on {level set > 0}, each with its own cut mass matrix and ghost penalty, Nitsche on the box
+    boundary for the outer field (`wave/stiffness.h:262-340`), coupled on the surface (`:441-574`).  The outer domain's
+    operators are the inner domain's with the level set negated.  Rows alternate inside / outside like the output."""
+    dim, p = params["dim"], params["fe_degree"]
+    s = System(dim, p, 1, add_ghost_layer=True)
+    s.subdivided_hyper_cube(params["n_subdivisions"], params["left"], params["right"])
+    ls = cut.interpolate_level_set(s, cut.sphere_level_set([0.0] * dim, 1.0))
+    gd, hmin, n = params["nitsche_parameter"], min(s.h), s.n_dofs()
+    exact, source = params["exact"], params.get("rhs")
+    fields = []
+    for sign in (1.0, -1.0):
+        lsd = sign * ls
+        M, _, loc = cut.assemble_cut_poisson(s, lsd, True, params["ghost_parameter_M"], rhs_value=0.0, gp_h_power=3, kind="mass")
+        A, _, _ = cut.assemble_cut_poisson(s, lsd, True, params["ghost_parameter_A"], gd, rhs_value=0.0, boundary_value=0.0,
+                                           gp_h_power=1, outside_diagonal=0.0, surface_terms=False)
+        B, bload = cut.domain_boundary_terms(s, lsd, gd)
+        volume, _ = cut.load_functionals(s, lsd, gd, loc)
+        fields.append(dict(ls=lsd, loc=loc, solve=sla.factorized(M.tocsc()), A=(A + B).tocsr(), bload=bload, volume=volume))
+    P, Q = cut.coupling_matrices(s, ls)
+    tau = 0.5 * gd / hmin
+
+    def residuals(t, u0, u1):
+        jump, total = u0 - u1, u0 + u1
+        c_sym = -0.5 * (P @ jump)
+        c_avg = 0.5 * (P.T @ total)
+        c_pen = tau * (Q @ jump)
+        out = []
+        for k, (f, u) in enumerate(zip(fields, (u0, u1))):
+            r = -(f["A"] @ u) + cut.apply_load(n, f["bload"], lambda pts: exact(pts, t))
+            if source is not None:
+                r += cut.apply_load(n, f["volume"], lambda pts: source(pts, t))
+            r -= (c_sym - c_avg + c_pen) if k == 0 else (c_sym + c_avg - c_pen)
+            out.append(f["solve"](r))
+        return out
+
+    u_init = interpolate(s, lambda pts, c: exact(pts, params["start_t"]))
+    y = np.concatenate([u_init, u_init] + ([np.zeros(n), np.zeros(n)] if second_order else []))
+
+    def f(t, yy):
+        r0, r1 = residuals(t, yy[:n], yy[n:2 * n])
+        return np.concatenate([yy[2 * n:], r0, r1]) if second_order else np.concatenate([r0, r1])
+
+    rows, counter = [], [0, 0]
+
+    def postprocess(t):
+        for k, fl in enumerate(fields):
+            rows.append((counter[k], t) + cut.error_norms_inside(s, fl["ls"], y[k * n:(k + 1) * n], lambda pts: exact(pts, t), fl["loc"]))
+            counter[k] += 1
+
+    dx = (params["right"] - params["left"]) / params["n_subdivisions"]
+    time = DiscreteTime(params["start_t"], params["end_t"], params["cfl"] * dx ** params["cfl_pow"])
+    rk = ExplicitRungeKutta4()
+    postprocess(0.0)
+    while not time.is_at_end():
+        _, y = rk.evolve_one_time_step(f, time.get_current_time(), time.get_next_step_size(), y)
+        postprocess(time.get_current_time() + time.get_next_step_size())
+        time.advance_time()
+    return rows

@@ -36,6 +36,8 @@ OUTPUTS = [
     "applications/wave/tests/heat_0.output",
     "applications/wave/tests/heat_1.output",
     "applications/wave/tests/step85_0.output",
+    "applications/wave/tests/wave_composite_0.output",
+    "applications/wave/tests/heat_composite_0.output",
     "applications/advection/tests/test_01.output",
 ]
 

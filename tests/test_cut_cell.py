@@ -195,15 +195,19 @@ def _app_golden(golden_dir, name):
     return [(int(a), float(b), float(c), float(d), float(e)) for a, b, c, d, e in rows]
 
 
-@pytest.mark.parametrize("name", ["wave_0", "heat_1", "heat_0"])
+@pytest.mark.parametrize("name", ["wave_0", "heat_1", "heat_0", "wave_composite_0", "heat_composite_0"])
 def test_oracle_reproduces_wave_app_goldens(golden_dir, name):
-    """applications/wave/tests/{wave_0,heat_1,heat_0}.output (wave-rk, heat-rk, heat-impl; 1D cut domain, ghost penalty in mass and stiffness, Nitsche with a
+    """applications/wave/tests/{wave_0,heat_1,heat_0,wave_composite_0,heat_composite_0}.output (wave-rk, heat-rk,
+    heat-impl, and the two-domain runs with the coupling on the cut surface; 1D cut domain, ghost penalty in mass and stiffness, Nitsche with a
     time-dependent boundary value, RK4 with the shortened last step): every printed step, all three error columns
     (L2, L1, Linf) to the 9 digits printed.  The `[L] solved in k` lines (AMG / ILU counts) are not reproducible."""
     from oracle import wave_app
-    rows = {"wave_0": wave_app.wave_rk_run, "heat_1": wave_app.heat_rk_run, "heat_0": wave_app.heat_impl_run}[name]()
+    rows = {"wave_0": wave_app.wave_rk_run, "heat_1": wave_app.heat_rk_run, "heat_0": wave_app.heat_impl_run,
+            "wave_composite_0": lambda: wave_app.composite_run(wave_app.wave_preset(1), True),
+            "heat_composite_0": lambda: wave_app.composite_run(wave_app.heat_preset(1), False)}[name]()
     gold = _app_golden(golden_dir, f"app_wave_{name}.output")
-    assert len(rows) == len(gold) == {"wave_0": 112, "heat_1": 821, "heat_0": 7}[name]
+    assert len(rows) == len(gold) == {"wave_0": 112, "heat_1": 821, "heat_0": 7, "wave_composite_0": 224,
+                                      "heat_composite_0": 1642}[name]
     for r, g in zip(rows, gold):
         assert r[0] == g[0] and abs(r[1] - g[1]) <= 5.1e-6  # time is printed with 5 decimals
         for i in (2, 3, 4):
