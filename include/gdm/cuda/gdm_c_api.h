@@ -322,7 +322,9 @@ typedef struct gdm_cut_desc {
                                   complete in that range only. */
 } gdm_cut_desc;
 typedef struct gdm_cut_s *gdm_cut_t;
-/* level_set: nodal values of the Q1 level set at the grid nodes, DoF order (x fastest); negative = inside */
+/* level_set: nodal values of the Q1 level set at the grid nodes, DoF order (x fastest); negative = inside.  A level set
+ * that vanishes exactly on a whole grid plane is degenerate (the cells on its positive side classify as intersected with
+ * an empty inside part, as with deal.II's classifier, and the surface rule on that plane is empty): shift it. */
 int gdm_cut_poisson_create(const gdm_cut_desc *desc, const double *level_set, gdm_cut_t *cut);
 int gdm_cut_destroy(gdm_cut_t cut);
 /* n_rows = rows to attach (band rows around the surface + identity rows of DoFs no active cell touches);

@@ -310,3 +310,36 @@ def test_product_rows_per_rank_range(lib, dim, n1, n_ranks):
     assert np.array_equal(np.concatenate(got_rows), rows)
     assert np.array_equal(np.array(got_ptr, dtype=np.uint64), rowptr)
     assert np.array_equal(np.concatenate(got_col), col) and np.array_equal(np.concatenate(got_val), val)
+
+
+def test_cut_edge_cases(lib):
+    """No surface in the grid (everything inside: no rows to attach, the right-hand side is the plain load vector;
+    everything outside: identity rows only), and sliver cuts (a surface 1e-9 h away from a grid plane)."""
+    import gdm_b200 as g
+    s = O.System(2, 3, 1)
+    s.subdivided_hyper_cube(8, 0.0, 1.0)
+    n = s.n_dofs()
+    inside = g.CutPoisson(2, 3, [8, 8], [0, 0], [1, 1], -np.ones(n), rhs_value=1.0)
+    assert inside.sizes() == (0, 0, 0, (64, 0, 0))
+    M1 = O.matrices_1d(3, 8, 1.0 / 8)
+    assert np.abs(inside.rhs() - np.kron(M1[3], M1[3])).max() <= 1e-15
+    outside = g.CutPoisson(2, 3, [8, 8], [0, 0], [1, 1], np.ones(n))
+    rows, rowptr, col, val = outside.rows()
+    assert outside.sizes() == (n, n, n, (0, 64, 0)) and np.array_equal(rows, col) and np.all(val == 1.0)
+    assert np.all(outside.rhs() == 0.0)
+    # half plane x < x0 with x0 just right / just left of the grid plane x = 0.5
+    X = s.node_coordinates()
+    for eps in (1e-9, -1e-9):
+        x0 = 0.5 + eps / 8
+        ls = X[:, 0] - x0
+        c = g.CutPoisson(2, 3, [8, 8], [0, 0], [1, 1], ls, ghost_penalty=True)
+        A, rhs, loc = cut.assemble_cut_poisson(s, ls, ghost_penalty=True)
+        assert np.array_equal(c.locations(), loc) and (loc == cut.INTERSECTED).sum() == 8
+        full = overlay_matrix(s, *c.rows())
+        assert np.isfinite(full.data).all() and abs(full - A).max() <= 1e-12 * abs(A).max()
+        area = c.load_vector(lambda pt, comp: 1.0, None).sum()  # sum_i (phi_i, 1) = |inside|
+        assert abs(area - x0) <= 1e-13
+    for v in ([-1.0, 1e-12], [1e-12, -1.0], [-1e-12, 1.0]):
+        (ip, iw), (sp_, sw, sn) = g.CutPoisson.quadrature(np.array(v), 4)
+        frac = v[0] / (v[0] - v[1]) if v[0] < 0 else 1 - v[0] / (v[0] - v[1])
+        assert abs(iw.sum() - frac) <= 1e-15 and len(sw) == 1
