@@ -777,7 +777,7 @@ class CutPoisson:
 
     def __init__(self, dim, fe_degree, n_subdivisions, lo, hi, level_set, ghost_penalty=True, ghost_parameter=0.5,
                  nitsche_parameter=None, rhs_value=4.0, boundary_value=1.0, gp_h_power=1, kind="stiffness",
-                 outside_diagonal=1.0, row_range=None):
+                 outside_diagonal=1.0, row_range=None, surface_terms=True, domain_boundary_terms=False):
         self.lib = capi.load()
         d = capi.CutDesc()
         d.dim, d.fe_degree = dim, fe_degree
@@ -789,6 +789,7 @@ class CutPoisson:
         d.nitsche_parameter = float(5.0 * (fe_degree + 1) * fe_degree if nitsche_parameter is None else nitsche_parameter)
         d.rhs_value, d.boundary_value = float(rhs_value), float(boundary_value)
         d.kind, d.outside_diagonal = {"stiffness": 0, "mass": 1}[kind], float(outside_diagonal)
+        d.no_surface_terms, d.domain_boundary_terms = int(not surface_terms), int(bool(domain_boundary_terms))
         if row_range is not None:  # the locally owned DoF range of a rank (System.locally_owned_range())
             d.row_begin, d.row_end = int(row_range[0]), int(row_range[1])
         self.n_dofs = int(np.prod([int(n) + 1 for n in n_subdivisions[:dim]]))
@@ -828,6 +829,26 @@ class CutPoisson:
         cast = lambda cb: C.cast(cb, C.c_void_p) if cb is not None else None
         capi.check(self.lib.gdm_cut_load_vector(self.h, cast(fcb), None, cast(gcb), None, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def boundary_load_vector(self, g):
+        """<gamma_D / h v - dv/dn, g> on the box boundary (`wave/stiffness.h:262-340`)."""
+        out = np.zeros(self.n_dofs)
+        cb = VectorTools._wrap(g)
+        capi.check(self.lib.gdm_cut_boundary_load_vector(self.h, cb, None, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def coupling_rows(self, which):
+        """CSR rows (row_ids, rowptr, col, val) of the interface coupling matrices of the two-domain runs
+        (`wave/stiffness.h:441-574`): which = "P", "PT" or "Q"."""
+        w = {"P": 0, "PT": 1, "Q": 2}[which]
+        n_rows, nnz = C.c_uint64(), C.c_uint64()
+        capi.check(self.lib.gdm_cut_coupling_rows(self.h, w, 0, 0, C.byref(n_rows), C.byref(nnz), None, None, None, None))
+        row_ids, rowptr = np.zeros(n_rows.value, dtype=np.uint64), np.zeros(n_rows.value + 1, dtype=np.uint64)
+        col, val = np.zeros(nnz.value, dtype=np.uint64), np.zeros(nnz.value)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        capi.check(self.lib.gdm_cut_coupling_rows(self.h, w, n_rows.value, nnz.value, C.byref(n_rows), C.byref(nnz),
+                                                  p(row_ids), p(rowptr), p(col), p(val)))
+        return row_ids, rowptr, col, val
 
     def locations(self):
         out = np.zeros(self.n_cells, dtype=np.uint8)

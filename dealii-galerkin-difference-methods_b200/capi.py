@@ -66,6 +66,7 @@ class CutDesc(C.Structure):
                 ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("ghost_penalty", C.c_int), ("gp_h_power", C.c_int),
                 ("ghost_parameter", C.c_double), ("nitsche_parameter", C.c_double), ("rhs_value", C.c_double),
                 ("boundary_value", C.c_double), ("kind", C.c_int), ("outside_diagonal", C.c_double),
+                ("no_surface_terms", C.c_int), ("domain_boundary_terms", C.c_int),
                 ("row_begin", C.c_uint64), ("row_end", C.c_uint64)]
 
 
@@ -138,6 +139,9 @@ SIGNATURES = {
     "gdm_cut_rows": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gdm_cut_rhs": (C.c_int, [_H, C.c_void_p]),
     "gdm_cut_locations": (C.c_int, [_H, C.c_void_p]),
+    "gdm_cut_boundary_load_vector": (C.c_int, [_H, FUNCTION_FN, C.c_void_p, C.c_void_p]),
+    "gdm_cut_coupling_rows": (C.c_int, [_H, C.c_int, C.c_uint64, C.c_uint64, _PU64, _PU64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
     "gdm_cut_load_vector": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gdm_cut_l2_error_inside": (C.c_int, [_H, C.c_void_p, FUNCTION_FN, C.c_void_p, _PD]),
     "gdm_cut_error_norms_inside": (C.c_int, [_H, C.c_void_p, FUNCTION_FN, C.c_void_p, _PD]),

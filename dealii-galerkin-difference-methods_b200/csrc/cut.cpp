@@ -576,6 +576,21 @@ namespace gdm
         std::vector<double> value, grads[3];
       };
       void cut_cell_matrix(const int *idx, CutScratch &sc, double *local, double *lrhs) const;
+      // part of the face (d, side) of a cell on the box boundary where the level set is negative, as unit-cell points
+      // with face weights (NonMatching::FEInterfaceValues::reinit(cell, f), wave/stiffness.h:268-283)
+      void boundary_face_rule(const int *idx, int d, int side, std::vector<Pt> &pts) const;
+      bool at_box_boundary(const int *idx) const
+      {
+        for (int e = 0; e < dim; ++e)
+          if (idx[e] == 0 || idx[e] == N[e] - 1)
+            return true;
+        return false;
+      }
+      // Nitsche terms on the box boundary (wave/stiffness.h:262-340, term IV): adds the cell matrix to local
+      // (npc x npc, may be null) and, for a boundary function g, the load  <gamma_D / h v - d_n v, g>  to lrhs (may be null)
+      void boundary_terms(const int *idx, CutScratch &sc, double *local, gdm_function_fn g, void *user, double *lrhs) const;
+      void coupling(int which, std::vector<uint64_t> &rows, std::vector<uint64_t> &rp, std::vector<uint64_t> &cols,
+                    std::vector<double> &vals) const;
       void build();
       void load_vector(gdm_function_fn f, void *f_user, gdm_function_fn g, void *g_user, double *out);
 
@@ -636,7 +651,7 @@ namespace gdm
               for (int j = 0; j < i; ++j)
                 local[(size_t)i * npc + j] = local[(size_t)j * npc + i];
           }
-        if (!sc.spts.empty() && !mass)
+        if (!sc.spts.empty() && !mass && !desc.no_surface_terms)
           {
             shape_at_points(idx, sc.spts, sc.value, sc.grads);
             std::vector<double> ng(npc);
@@ -672,6 +687,162 @@ namespace gdm
                   }
               }
           }
+    }
+
+
+    void Assembly::boundary_face_rule(const int *idx, int d, int side, std::vector<Pt> &pts) const
+    {
+      pts.clear();
+      double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      vertex_values(idx, v);
+      MLF f;
+      f.d = dim;
+      for (int i = 0; i < (1 << dim); ++i)
+        f.c[i] = v[i];
+      const MLF        fc = face(f, d, side);
+      std::vector<Pt>  base;
+      const double     l0[3] = {0, 0, 0}, h1[3] = {1, 1, 1};
+      if (dim == 1)
+        {
+          if (fc.c[0] < 0)
+            {
+              Pt b{};
+              b.w = 1.0;
+              base.push_back(b);
+            }
+        }
+      else
+        volume({fc}, {-1}, l0, h1, dim - 1, gauss, 0, base);
+      for (const Pt &b : base)
+        {
+          Pt  p{};
+          int m = 0;
+          for (int e = 0; e < dim; ++e)
+            p.x[e] = (e == d) ? (double)side : b.x[m++];
+          p.w = b.w;
+          pts.push_back(p);
+        }
+    }
+
+    void Assembly::boundary_terms(const int *idx, CutScratch &sc, double *local, gdm_function_fn g, void *user, double *lrhs) const
+    {
+      const double nitsche = desc.nitsche_parameter / h_min();
+      for (int d = 0; d < dim; ++d)
+        for (int side = 0; side < 2; ++side)
+          {
+            if (idx[d] != (side == 0 ? 0 : N[d] - 1))
+              continue;
+            boundary_face_rule(idx, d, side, sc.spts);
+            if (sc.spts.empty())
+              continue;
+            shape_at_points(idx, sc.spts, sc.value, sc.grads);
+            double area = 1;
+            for (int e = 0; e < dim; ++e)
+              if (e != d)
+                area *= h[e];
+            const double sgn = side ? 1.0 : -1.0;
+            for (size_t q = 0; q < sc.spts.size(); ++q)
+              {
+                const double  jxw = sc.spts[q].w * area;
+                const double *vq = sc.value.data() + q * npc, *gq = sc.grads[d].data() + q * npc;
+                double        gval = 0;
+                if (lrhs && g)
+                  {
+                    double x[3] = {0, 0, 0};
+                    for (int e = 0; e < dim; ++e)
+                      x[e] = lo[e] + (idx[e] + sc.spts[q].x[e]) * h[e];
+                    gval = g(x, 0, user);
+                  }
+                for (int i = 0; i < npc; ++i)
+                  {
+                    const double ngi = sgn * gq[i];
+                    if (lrhs && g)
+                      lrhs[i] += gval * (nitsche * vq[i] - ngi) * jxw;
+                    if (local)
+                      for (int j = 0; j < npc; ++j)
+                        local[(size_t)i * npc + j] += (-ngi * vq[j] - sgn * gq[j] * vq[i] + nitsche * vq[i] * vq[j]) * jxw;
+                  }
+              }
+          }
+    }
+
+    // which = 0: P_ij = sum_q (n . grad phi_i) phi_j JxW, 1: P^T, 2: Q_ij = sum_q phi_i phi_j JxW over the cut surface
+    // (n = normal of the level set): the interface coupling of the two-domain residual, wave/stiffness.h:441-574
+    void Assembly::coupling(int which, std::vector<uint64_t> &rows, std::vector<uint64_t> &rp, std::vector<uint64_t> &cols,
+                            std::vector<double> &vals) const
+    {
+      struct Trip
+      {
+        uint64_t r, c;
+        double   v;
+      };
+      std::vector<Trip>     trips;
+      CutScratch            sc;
+      std::vector<uint64_t> dofs;
+      std::vector<double>   ng(npc);
+      int                   idx[3], off[3];
+      const double          vol = cell_volume();
+      for (uint64_t cell = 0; cell < n_cells; ++cell)
+        {
+          if (location[cell] != INTERSECTED)
+            continue;
+          cell_index(cell, idx);
+          double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          vertex_values(idx, v);
+          sc.ipts.clear();
+          sc.spts.clear();
+          cut_quadrature(dim, v, gauss, sc.ipts, sc.spts);
+          if (sc.spts.empty())
+            continue;
+          cell_dofs(idx, off, dofs);
+          shape_at_points(idx, sc.spts, sc.value, sc.grads);
+          std::vector<double> local((size_t)npc * npc, 0.0);
+          for (size_t q = 0; q < sc.spts.size(); ++q)
+            {
+              double nph[3] = {0, 0, 0}, scale = 0;
+              for (int e = 0; e < dim; ++e)
+                {
+                  nph[e] = sc.spts[q].n[e] / h[e];
+                  scale += nph[e] * nph[e];
+                }
+              scale            = std::sqrt(scale);
+              const double jxw = sc.spts[q].w * vol * scale;
+              for (int i = 0; i < npc; ++i)
+                {
+                  double t = 0;
+                  for (int e = 0; e < dim; ++e)
+                    t += nph[e] / scale * sc.grads[e][q * npc + i];
+                  ng[i] = t;
+                }
+              const double *vq = sc.value.data() + q * npc;
+              for (int i = 0; i < npc; ++i)
+                for (int j = 0; j < npc; ++j)
+                  local[(size_t)i * npc + j] += (which == 0 ? ng[i] * vq[j] : which == 1 ? vq[i] * ng[j] : vq[i] * vq[j]) * jxw;
+            }
+          for (int i = 0; i < npc; ++i)
+            for (int j = 0; j < npc; ++j)
+              trips.push_back({dofs[i], dofs[j], local[(size_t)i * npc + j]});
+        }
+      std::stable_sort(trips.begin(), trips.end(), [](const Trip &a, const Trip &b) { return a.r != b.r ? a.r < b.r : a.c < b.c; });
+      rows.clear();
+      cols.clear();
+      vals.clear();
+      rp.assign(1, 0);
+      for (size_t k = 0; k < trips.size();)
+        {
+          const uint64_t r = trips[k].r;
+          rows.push_back(r);
+          while (k < trips.size() && trips[k].r == r)
+            {
+              const uint64_t c   = trips[k].c;
+              double         sum = 0;
+              for (; k < trips.size() && trips[k].r == r && trips[k].c == c; ++k)
+                sum += trips[k].v;
+              cols.push_back(c);
+              vals.push_back(sum);
+            }
+          rp.push_back(cols.size());
+        }
     }
 
     void Assembly::build()
@@ -714,6 +885,9 @@ namespace gdm
                 if (ghost_penalty_neighbor(idx, d, side) >= 0)
                   for (uint64_t i : dofs) // the neighbour marks its own window when the loop gets to it
                     irregular[i] = 1;
+          if (desc.domain_boundary_terms && desc.kind == 0 && location[cell] != OUTSIDE && at_box_boundary(idx))
+            for (uint64_t i : dofs)
+              irregular[i] = 1;
         }
       std::vector<int64_t> slot(n_dofs, -1);
       n_band_rows = 0;
@@ -946,6 +1120,12 @@ namespace gdm
                 rhs[dofs[i]] += lrhs[i];
               if (cell_in_range(idx))
                 scatter(dofs, off, dofs, off, local, npc, 0, 0);
+            }
+          if (desc.domain_boundary_terms && !mass && at_box_boundary(idx) && cell_in_range(idx))
+            {
+              std::fill(local.begin(), local.end(), 0.0);
+              boundary_terms(idx, scratch[0], local.data(), nullptr, nullptr, nullptr);
+              scatter(dofs, off, dofs, off, local.data(), npc, 0, 0);
             }
           if (desc.ghost_penalty)
             for (int d = 0; d < dim; ++d)
@@ -1308,6 +1488,57 @@ int gdm_cut_load_vector(gdm_cut_t c, gdm_function_fn f, void *f_user, gdm_functi
   GDM_ARG(c);
   GDM_ARG(out);
   c->a.load_vector(f, f_user, g, g_user, out);
+  GDM_CATCH
+}
+
+int gdm_cut_boundary_load_vector(gdm_cut_t c, gdm_function_fn g, void *user, double *out)
+{
+  GDM_TRY
+  GDM_ARG(c);
+  GDM_ARG(g);
+  GDM_ARG(out);
+  const cut::Assembly &a = c->a;
+  std::fill(out, out + a.n_dofs, 0.0);
+  cut::Assembly::CutScratch sc;
+  std::vector<uint64_t>     dofs;
+  std::vector<double>       lrhs(a.npc);
+  int                       idx[3], off[3];
+  for (uint64_t cell = 0; cell < a.n_cells; ++cell)
+    {
+      if (a.location[cell] == cut::OUTSIDE)
+        continue;
+      a.cell_index(cell, idx);
+      if (!a.at_box_boundary(idx))
+        continue;
+      std::fill(lrhs.begin(), lrhs.end(), 0.0);
+      a.boundary_terms(idx, sc, nullptr, g, user, lrhs.data());
+      a.cell_dofs(idx, off, dofs);
+      for (int i = 0; i < a.npc; ++i)
+        out[dofs[i]] += lrhs[i];
+    }
+  GDM_CATCH
+}
+
+int gdm_cut_coupling_rows(gdm_cut_t c, int which, uint64_t capacity_rows, uint64_t capacity_nnz, uint64_t *n_rows,
+                          uint64_t *nnz, uint64_t *row_ids, uint64_t *rowptr, uint64_t *col, double *val)
+{
+  GDM_TRY
+  GDM_ARG(c);
+  GDM_ARG(n_rows);
+  GDM_ARG(nnz);
+  GDM_REQUIRE(which >= 0 && which <= 2, GDM_ERR_INVALID, "which must be 0 (P), 1 (P^T) or 2 (Q)");
+  std::vector<uint64_t> rows, rp, cols;
+  std::vector<double>   vals;
+  c->a.coupling(which, rows, rp, cols, vals);
+  *n_rows = rows.size();
+  *nnz    = cols.size();
+  if (row_ids && rowptr && col && val && capacity_rows >= rows.size() && capacity_nnz >= cols.size())
+    {
+      std::copy(rows.begin(), rows.end(), row_ids);
+      std::copy(rp.begin(), rp.end(), rowptr);
+      std::copy(cols.begin(), cols.end(), col);
+      std::copy(vals.begin(), vals.end(), val);
+    }
   GDM_CATCH
 }
 

@@ -317,6 +317,10 @@ typedef struct gdm_cut_desc {
                                  use ghost_parameter = gamma_M, gp_h_power = 3) */
   double   outside_diagonal;  /* diagonal of the rows no active cell touches: 1 for a matrix that is solved with
                                  (cut_poisson_01_gdm.cc:324-329, wave/mass.h:246-248), 0 for the matrix-free residual */
+  int      no_surface_terms;      /* 1: no Nitsche terms on the cut surface (function_interface_dbc unset: the two-domain
+                                     runs couple there instead, wave/stiffness.h:441-574) */
+  int      domain_boundary_terms; /* 1: Nitsche terms on the box boundary for the part of it inside the domain
+                                     (function_domain_dbc, wave/stiffness.h:262-340) */
   uint64_t row_begin, row_end; /* rows (global DoFs) to assemble: the locally owned range of a rank
                                   (gdm_system_locally_owned_range); 0, 0 = all.  With a range the right-hand side is
                                   complete in that range only. */
@@ -337,6 +341,15 @@ int gdm_cut_rhs(gdm_cut_t cut, double *rhs /* n_dofs */);
 /* out[n_dofs] = (v, f) over the inside part + <gamma_D / h v - dv/dn, g> on the surface, for functions of the point: the
  * data-dependent part of the residual (wave/stiffness.h:186-260; time enters through `user`).  f or g may be NULL. */
 int gdm_cut_load_vector(gdm_cut_t cut, gdm_function_fn f, void *f_user, gdm_function_fn g, void *g_user, double *out);
+/* out[n_dofs] = <gamma_D / h v - dv/dn, g> on the box boundary (the load of domain_boundary_terms) */
+int gdm_cut_boundary_load_vector(gdm_cut_t cut, gdm_function_fn g, void *user, double *out);
+/* Interface coupling of the two-domain runs (wave/stiffness.h:441-574) as sparse matrices over the cut surface, n = normal
+ * of the level set:  which = 0: P_ij = <n . grad phi_i, phi_j>, 1: P^T, 2: Q_ij = <phi_i, phi_j>.  With [u] = u0 - u1 and
+ * tau = gamma_D / 2 the residuals get  r0 -= -1/2 P [u] - 1/2 P^T (u0 + u1) + tau / h Q [u],
+ * r1 -= -1/2 P [u] + 1/2 P^T (u0 + u1) - tau / h Q [u].  Always returns the sizes; fills the arrays (CSR rows in the
+ * form of gdm_operator_attach_csr, to be laid over an operator with scale 0) when they are given and large enough. */
+int gdm_cut_coupling_rows(gdm_cut_t cut, int which, uint64_t capacity_rows, uint64_t capacity_nnz, uint64_t *n_rows,
+                          uint64_t *nnz, uint64_t *row_ids, uint64_t *rowptr, uint64_t *col, double *val);
 int gdm_cut_locations(gdm_cut_t cut, uint8_t *location /* n_cells: 0 inside, 1 outside, 2 intersected */);
 /* sqrt( sum over non-outside cells of the integral over the inside part of (u_h - exact)^2 ); u = all DoFs */
 int gdm_cut_l2_error_inside(gdm_cut_t cut, const double *u, gdm_function_fn exact, void *user, double *error);

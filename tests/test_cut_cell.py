@@ -343,3 +343,79 @@ def test_cut_edge_cases(lib):
         (ip, iw), (sp_, sw, sn) = g.CutPoisson.quadrature(np.array(v), 4)
         frac = v[0] / (v[0] - v[1]) if v[0] < 0 else 1 - v[0] / (v[0] - v[1])
         assert abs(iw.sum() - frac) <= 1e-15 and len(sw) == 1
+
+
+# ----------------------------------------------------------------------- two-domain runs: product pieces vs oracle
+def _csr(n, rows, rowptr, col, val):
+    M = sp.csr_matrix((val, col.astype(np.int64), rowptr.astype(np.int64)), shape=(len(rows), n))
+    P = sp.csr_matrix((np.ones(len(rows)), (rows.astype(np.int64), np.arange(len(rows)))), shape=(n, len(rows)))
+    return (P @ M).tocsr()
+
+
+@pytest.mark.parametrize("dim,n1", [(1, 40), (2, 16), (3, 8)])
+def test_product_two_domain_pieces_match_oracle(lib, dim, n1):
+    """Outer-domain operator (negated level set, no surface terms, Nitsche on the box boundary: wave/stiffness.h:262-340),
+    its boundary load and the interface coupling matrices (wave/stiffness.h:441-574) from gdm_cut_* against the oracle."""
+    import gdm_b200 as g
+    s, ls = sphere_problem(dim, 3, n1)
+    n, gd = s.n_dofs(), 15.0
+    box = ([n1] * dim, [-1.21] * dim, [1.21] * dim)
+    c = g.CutPoisson(dim, 3, *box, -ls, ghost_penalty=True, ghost_parameter=1.5, nitsche_parameter=gd, rhs_value=0.0,
+                     boundary_value=0.0, outside_diagonal=0.0, surface_terms=False, domain_boundary_terms=True)
+    A, _, _ = cut.assemble_cut_poisson(s, -ls, True, 1.5, gd, rhs_value=0.0, boundary_value=0.0, outside_diagonal=0.0,
+                                       surface_terms=False)
+    B, bload = cut.domain_boundary_terms(s, -ls, gd)
+    ref = (A + B).tocsr()
+    assert abs(overlay_matrix(s, *c.rows()) - ref).max() <= 1e-13 * abs(ref).max()
+    gfun = lambda pts: np.cos(pts[:, 0]) + 0.25 * pts.sum(axis=1)
+    got = c.boundary_load_vector(lambda pt, comp: np.cos(pt[0]) + 0.25 * sum(pt[:dim]))
+    refb = cut.apply_load(n, bload, gfun)
+    assert np.abs(got - refb).max() <= 1e-13 * np.abs(refb).max()
+    ci = g.CutPoisson(dim, 3, *box, ls)
+    P, Q = cut.coupling_matrices(s, ls)
+    for which, refm in (("P", P), ("PT", P.T.tocsr()), ("Q", Q)):
+        got = _csr(n, *ci.coupling_rows(which))
+        assert abs(got - refm).max() <= 1e-13 * abs(refm).max(), which
+
+
+def test_product_setup_reproduces_wave_composite_golden_on_host(lib, golden_dir):
+    """applications/wave/tests/wave_composite_0.output from the product's operators, loads and coupling rows with the
+    oracle's RK4 and exact mass solves in between (no GPU here): first 6 printed steps of both fields."""
+    import gdm_b200 as g
+    import scipy.sparse.linalg as sla
+    from oracle import wave_app
+    prm = wave_app.wave_preset(1)
+    s, ls = sphere_problem(1, 3, 40)
+    n, gd, hmin = s.n_dofs(), prm["nitsche_parameter"], 2.42 / 40
+    box = ([40], [-1.21], [1.21])
+    k = 1.5 * np.pi
+    ex = lambda t: (lambda pt, c: np.cos(k * abs(pt[0])) * np.cos(k * t))
+    fields = []
+    for sign in (1.0, -1.0):
+        cm = g.CutPoisson(1, 3, *box, sign * ls, ghost_parameter=prm["ghost_parameter_M"], gp_h_power=3, kind="mass", rhs_value=0.0)
+        ca = g.CutPoisson(1, 3, *box, sign * ls, ghost_parameter=prm["ghost_parameter_A"], nitsche_parameter=gd, rhs_value=0.0,
+                          boundary_value=0.0, outside_diagonal=0.0, surface_terms=False, domain_boundary_terms=True)
+        fields.append((cm, ca, sla.factorized(overlay_matrix_kind(s, "mass", *cm.rows()).tocsc()), overlay_matrix(s, *ca.rows())))
+    ci = g.CutPoisson(1, 3, *box, ls)
+    P, PT, Q = (_csr(n, *ci.coupling_rows(w)) for w in ("P", "PT", "Q"))
+    tau = 0.5 * gd / hmin
+    u_init = O.interpolate(s, lambda pts, c: prm["exact"](pts, 0.0))
+    y = np.concatenate([u_init, u_init, np.zeros(n), np.zeros(n)])
+
+    def f(t, yy):
+        u0, u1 = yy[:n], yy[n:2 * n]
+        c_sym, c_avg, c_pen = -0.5 * (P @ (u0 - u1)), 0.5 * (PT @ (u0 + u1)), tau * (Q @ (u0 - u1))
+        out = []
+        for kk, ((cm, ca, solve, A), u) in enumerate(zip(fields, (u0, u1))):
+            r = -(A @ u) + ca.boundary_load_vector(ex(t)) - ((c_sym - c_avg + c_pen) if kk == 0 else (c_sym + c_avg - c_pen))
+            out.append(solve(r))
+        return np.concatenate([yy[2 * n:], out[0], out[1]])
+
+    gold = _app_golden(golden_dir, "app_wave_wave_composite_0.output")
+    rk, t, dt = O.ExplicitRungeKutta4(), 0.0, 0.3 * hmin
+    for step in range(6):
+        for kk in range(2):
+            e = fields[kk][0].error_norms_inside(y[kk * n:(kk + 1) * n], ex(t))
+            for i in range(3):
+                assert abs(e[i] - gold[2 * step + kk][2 + i]) <= 6e-9 * gold[2 * step + kk][2 + i], (step, kk, e, gold[2 * step + kk])
+        t, y = rk.evolve_one_time_step(f, t, dt, y)
