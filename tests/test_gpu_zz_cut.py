@@ -198,3 +198,70 @@ def test_wave_app_cpp_driver(lib, golden_dir, simulation, golden):
         assert int(r[0]) == g_[0] and abs(float(r[1]) - g_[1]) <= 5.1e-6
         for i in (2, 3, 4):
             assert abs(float(r[i]) - g_[i]) <= 2e-8 * g_[i], (r, g_)
+
+
+def test_wave_app_wave_composite_0(lib, golden_dir):
+    """applications/wave, simulation "wave-composite" in 1D (problem.h:347-437) on the GPU: two fields (inside / outside the
+    unit sphere), RK4 over four blocks [u0; u1; v0; v1], each field with its own cut mass and stiffness rows (the outer
+    one: negated level set + Nitsche on the box boundary), coupled on the surface through three CSR-only operators
+    (scale 0 + attached rows: P, P^T, Q of wave/stiffness.h:441-574); both error tables of
+    applications/wave/tests/wave_composite_0.output for the first 10 printed steps."""
+    import gdm_b200 as g
+    from oracle import wave_app
+    from test_cut_cell import _app_golden
+    prm = wave_app.wave_preset(1)
+    gs, gc, os_, oc = make_pair(1, 3, 1, [40], "none", lo=[-1.21], hi=[1.21])
+    ls = cut.interpolate_level_set(os_, cut.sphere_level_set([0.0], 1.0))
+    n, gd, hmin = gs.n_dofs(), prm["nitsche_parameter"], 2.42 / 40
+    box = ([40], [-1.21], [1.21])
+    k = 1.5 * np.pi
+    ex = lambda t: (lambda pt, c: np.cos(k * abs(pt[0])) * np.cos(k * t))
+    fields = []
+    for sign in (1.0, -1.0):
+        cm = g.CutPoisson(1, 3, *box, sign * ls, ghost_parameter=prm["ghost_parameter_M"], gp_h_power=3, kind="mass", rhs_value=0.0)
+        ca = g.CutPoisson(1, 3, *box, sign * ls, ghost_parameter=prm["ghost_parameter_A"], nitsche_parameter=gd, rhs_value=0.0,
+                          boundary_value=0.0, outside_diagonal=0.0, surface_terms=False, domain_boundary_terms=True)
+        M, A = make_operator(gs, gc, "mass"), make_operator(gs, gc, "stiffness")
+        M.attach_csr(*cm.rows())
+        A.attach_csr(*ca.rows())
+        pre = g.PreconditionJacobi()
+        pre.initialize(M)
+        fields.append((cm, ca, M, A, pre))
+    ci = g.CutPoisson(1, 3, *box, ls)
+    coupling = {}
+    for which in ("P", "PT", "Q"):
+        op = make_operator(gs, gc, "stiffness", scale=0.0)  # rows outside the attached set stay zero
+        op.attach_csr(*ci.coupling_rows(which))
+        coupling[which] = op
+    tau = 0.5 * gd / hmin
+    u_init = O.interpolate(os_, lambda pts, c: prm["exact"](pts, 0.0))
+    y = [g.Vector(gs, u_init), g.Vector(gs, u_init), g.Vector(gs), g.Vector(gs)]
+    jump, total, c_sym, c_avg, c_pen, rhs, load = (g.Vector(gs) for _ in range(7))
+
+    def f(t, yy, out):
+        out[0].equ(yy[2])                                   # du/dt = v, both fields
+        out[1].equ(yy[3])
+        jump.equ(yy[0]).add(-1.0, yy[1])
+        total.equ(yy[0]).add(1.0, yy[1])
+        coupling["P"].vmult(c_sym, jump)                    # -1/2 P [u]
+        coupling["PT"].vmult(c_avg, total)                  #  1/2 P^T (u0 + u1)
+        coupling["Q"].vmult(c_pen, jump)                    #  tau / h Q [u]
+        for kk, (cm, ca, M, A, pre) in enumerate(fields):
+            A.vmult(rhs, yy[kk])
+            rhs.scale(-1.0)
+            load.upload(ca.boundary_load_vector(ex(t)))
+            rhs.add(1.0, load)
+            s = 1.0 if kk == 0 else -1.0                    # r0 -= c_sym - c_avg + c_pen, r1 -= c_sym + c_avg - c_pen
+            rhs.add(0.5, c_sym).add(s * 0.5, c_avg).add(-s * tau, c_pen)
+            out[2 + kk].set(0.0)
+            g.SolverCG(g.ReductionControl(1000, 1e-20, 1e-14)).solve(M, out[2 + kk], rhs, pre)
+
+    gold = _app_golden(golden_dir, "app_wave_wave_composite_0.output")
+    rk = g.TimeStepping.ExplicitRungeKutta(g.TimeStepping.RK_CLASSIC_FOURTH_ORDER)
+    t, dt = 0.0, 0.3 * hmin
+    for step in range(10):
+        for kk in range(2):
+            e = fields[kk][0].error_norms_inside(y[kk].numpy(), ex(t))
+            for i in range(3):
+                assert abs(e[i] - gold[2 * step + kk][2 + i]) <= 2e-8 * gold[2 * step + kk][2 + i], (step, kk, e, gold[2 * step + kk])
+        t = rk.evolve_one_time_step(f, t, dt, y)
