@@ -611,82 +611,82 @@ namespace gdm
     {
       const bool   mass = desc.kind == 1;
       const double vol = cell_volume(), nitsche = desc.nitsche_parameter / h_min();
-        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        vertex_values(idx, v);
-        sc.ipts.clear();
-        sc.spts.clear();
-        cut_quadrature(dim, v, gauss, sc.ipts, sc.spts);
-        std::fill(local, local + (size_t)npc * npc, 0.0);
-        std::fill(lrhs, lrhs + npc, 0.0);
-        if (!sc.ipts.empty())
-          {
-            shape_at_points(idx, sc.ipts, sc.value, sc.grads);
-            // upper triangle only (the products commute, so the mirrored entries carry the same bits), direction sums
-            // written out so that the j loop vectorises
-            for (size_t q = 0; q < sc.ipts.size(); ++q)
-              {
-                const double  jxw = sc.ipts[q].w * vol;
-                const double *vq = sc.value.data() + q * npc, *a0 = sc.grads[0].data() + q * npc,
-                             *a1 = dim > 1 ? sc.grads[1].data() + q * npc : nullptr,
-                             *a2 = dim > 2 ? sc.grads[2].data() + q * npc : nullptr;
-                for (int i = 0; i < npc; ++i)
-                  {
-                    lrhs[i] += desc.rhs_value * vq[i] * jxw;
-                    double *row = local + (size_t)i * npc;
-                    if (mass)
-                      for (int j = i; j < npc; ++j)
-                        row[j] += (vq[i] * vq[j]) * jxw;
-                    else if (dim == 1)
-                      for (int j = i; j < npc; ++j)
-                        row[j] += (a0[i] * a0[j]) * jxw;
-                    else if (dim == 2)
-                      for (int j = i; j < npc; ++j)
-                        row[j] += (a0[i] * a0[j] + a1[i] * a1[j]) * jxw;
-                    else
-                      for (int j = i; j < npc; ++j)
-                        row[j] += ((a0[i] * a0[j] + a1[i] * a1[j]) + a2[i] * a2[j]) * jxw;
-                  }
-              }
-            for (int i = 1; i < npc; ++i)
-              for (int j = 0; j < i; ++j)
-                local[(size_t)i * npc + j] = local[(size_t)j * npc + i];
-          }
-        if (!sc.spts.empty() && !mass && !desc.no_surface_terms)
-          {
-            shape_at_points(idx, sc.spts, sc.value, sc.grads);
-            std::vector<double> ng(npc);
-            for (size_t q = 0; q < sc.spts.size(); ++q)
-              {
-                // unit-cell normal and measure -> physical (anisotropic spacing allowed)
-                double nph[3] = {0, 0, 0}, scale = 0;
-                for (int e = 0; e < dim; ++e)
-                  {
-                    nph[e] = sc.spts[q].n[e] / h[e];
-                    scale += nph[e] * nph[e];
-                  }
-                scale = std::sqrt(scale);
-                for (int e = 0; e < dim; ++e)
-                  nph[e] /= scale;
-                const double jxw = sc.spts[q].w * vol * scale;
-                for (int i = 0; i < npc; ++i)
-                  {
-                    double s = 0;
-                    for (int e = 0; e < dim; ++e)
-                      s += nph[e] * sc.grads[e][q * npc + i];
-                    ng[i] = s;
-                  }
-                for (int i = 0; i < npc; ++i)
-                  {
-                    const double vi = sc.value[q * npc + i];
-                    lrhs[i] += desc.boundary_value * (nitsche * vi - ng[i]) * jxw;
-                    for (int j = 0; j < npc; ++j)
-                      {
-                        const double vj = sc.value[q * npc + j];
-                        local[(size_t)i * npc + j] += (-ng[i] * vj - ng[j] * vi + nitsche * vi * vj) * jxw;
-                      }
-                  }
-              }
-          }
+      double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      vertex_values(idx, v);
+      sc.ipts.clear();
+      sc.spts.clear();
+      cut_quadrature(dim, v, gauss, sc.ipts, sc.spts);
+      std::fill(local, local + (size_t)npc * npc, 0.0);
+      std::fill(lrhs, lrhs + npc, 0.0);
+      if (!sc.ipts.empty())
+        {
+          shape_at_points(idx, sc.ipts, sc.value, sc.grads);
+          // upper triangle only (the products commute, so the mirrored entries carry the same bits), direction sums
+          // written out so that the j loop vectorises
+          for (size_t q = 0; q < sc.ipts.size(); ++q)
+            {
+              const double  jxw = sc.ipts[q].w * vol;
+              const double *vq = sc.value.data() + q * npc, *a0 = sc.grads[0].data() + q * npc,
+                           *a1 = dim > 1 ? sc.grads[1].data() + q * npc : nullptr,
+                           *a2 = dim > 2 ? sc.grads[2].data() + q * npc : nullptr;
+              for (int i = 0; i < npc; ++i)
+                {
+                  lrhs[i] += desc.rhs_value * vq[i] * jxw;
+                  double *row = local + (size_t)i * npc;
+                  if (mass)
+                    for (int j = i; j < npc; ++j)
+                      row[j] += (vq[i] * vq[j]) * jxw;
+                  else if (dim == 1)
+                    for (int j = i; j < npc; ++j)
+                      row[j] += (a0[i] * a0[j]) * jxw;
+                  else if (dim == 2)
+                    for (int j = i; j < npc; ++j)
+                      row[j] += (a0[i] * a0[j] + a1[i] * a1[j]) * jxw;
+                  else
+                    for (int j = i; j < npc; ++j)
+                      row[j] += ((a0[i] * a0[j] + a1[i] * a1[j]) + a2[i] * a2[j]) * jxw;
+                }
+            }
+          for (int i = 1; i < npc; ++i)
+            for (int j = 0; j < i; ++j)
+              local[(size_t)i * npc + j] = local[(size_t)j * npc + i];
+        }
+      if (!sc.spts.empty() && !mass && !desc.no_surface_terms)
+        {
+          shape_at_points(idx, sc.spts, sc.value, sc.grads);
+          std::vector<double> ng(npc);
+          for (size_t q = 0; q < sc.spts.size(); ++q)
+            {
+              // unit-cell normal and measure -> physical (anisotropic spacing allowed)
+              double nph[3] = {0, 0, 0}, scale = 0;
+              for (int e = 0; e < dim; ++e)
+                {
+                  nph[e] = sc.spts[q].n[e] / h[e];
+                  scale += nph[e] * nph[e];
+                }
+              scale = std::sqrt(scale);
+              for (int e = 0; e < dim; ++e)
+                nph[e] /= scale;
+              const double jxw = sc.spts[q].w * vol * scale;
+              for (int i = 0; i < npc; ++i)
+                {
+                  double s = 0;
+                  for (int e = 0; e < dim; ++e)
+                    s += nph[e] * sc.grads[e][q * npc + i];
+                  ng[i] = s;
+                }
+              for (int i = 0; i < npc; ++i)
+                {
+                  const double vi = sc.value[q * npc + i];
+                  lrhs[i] += desc.boundary_value * (nitsche * vi - ng[i]) * jxw;
+                  for (int j = 0; j < npc; ++j)
+                    {
+                      const double vj = sc.value[q * npc + j];
+                      local[(size_t)i * npc + j] += (-ng[i] * vj - ng[j] * vi + nitsche * vi * vj) * jxw;
+                    }
+                }
+            }
+        }
     }
 
 
@@ -1095,56 +1095,56 @@ namespace gdm
             worker(0);
           const double t1 = now();
           t_cut += t1 - t0;
-      for (uint64_t cell = b0; cell < b1; ++cell)
-        {
-          if (location[cell] == OUTSIDE)
-            continue;
-          cell_index(cell, idx);
-          cell_dofs(idx, off, dofs);
-          if (location[cell] == INSIDE)
+          for (uint64_t cell = b0; cell < b1; ++cell)
             {
-              const auto &t = inside_tables(idx);
-              for (int i = 0; i < npc; ++i)
-                rhs[dofs[i]] += t.second[i];
-              bool any = false;
-              for (int i = 0; i < npc && !any; ++i)
-                any = slot[dofs[i]] >= 0;
-              if (any)
-                scatter(dofs, off, dofs, off, t.first.data(), npc, 0, 0);
-            }
-          else
-            {
-              const double *local = &block_local[(size_t)block_slot[cell - b0] * npc * npc];
-              const double *lrhs  = &block_rhs[(size_t)block_slot[cell - b0] * npc];
-              for (int i = 0; i < npc; ++i)
-                rhs[dofs[i]] += lrhs[i];
-              if (cell_in_range(idx))
-                scatter(dofs, off, dofs, off, local, npc, 0, 0);
-            }
-          if (desc.domain_boundary_terms && !mass && at_box_boundary(idx) && cell_in_range(idx))
-            {
-              std::fill(local.begin(), local.end(), 0.0);
-              boundary_terms(idx, scratch[0], local.data(), nullptr, nullptr, nullptr);
-              scatter(dofs, off, dofs, off, local.data(), npc, 0, 0);
-            }
-          if (desc.ghost_penalty)
-            for (int d = 0; d < dim; ++d)
-              for (int side = 0; side < 2; ++side)
+              if (location[cell] == OUTSIDE)
+                continue;
+              cell_index(cell, idx);
+              cell_dofs(idx, off, dofs);
+              if (location[cell] == INSIDE)
                 {
-                  const int64_t nc = ghost_penalty_neighbor(idx, d, side);
-                  if (nc < 0)
-                    continue;
-                  int nidx[3];
-                  cell_index((uint64_t)nc, nidx);
-                  cell_dofs(nidx, noff, ndofs);
-                  const std::vector<double> &S = gp_matrix(idx, nidx, d, side);
-                  const int                  n2 = 2 * npc;
-                  scatter(dofs, off, dofs, off, S.data(), n2, 0, 0);
-                  scatter(dofs, off, ndofs, noff, S.data(), n2, 0, npc);
-                  scatter(ndofs, noff, dofs, off, S.data(), n2, npc, 0);
-                  scatter(ndofs, noff, ndofs, noff, S.data(), n2, npc, npc);
+                  const auto &t = inside_tables(idx);
+                  for (int i = 0; i < npc; ++i)
+                    rhs[dofs[i]] += t.second[i];
+                  bool any = false;
+                  for (int i = 0; i < npc && !any; ++i)
+                    any = slot[dofs[i]] >= 0;
+                  if (any)
+                    scatter(dofs, off, dofs, off, t.first.data(), npc, 0, 0);
                 }
-        }
+              else
+                {
+                  const double *local = &block_local[(size_t)block_slot[cell - b0] * npc * npc];
+                  const double *lrhs  = &block_rhs[(size_t)block_slot[cell - b0] * npc];
+                  for (int i = 0; i < npc; ++i)
+                    rhs[dofs[i]] += lrhs[i];
+                  if (cell_in_range(idx))
+                    scatter(dofs, off, dofs, off, local, npc, 0, 0);
+                }
+              if (desc.domain_boundary_terms && !mass && at_box_boundary(idx) && cell_in_range(idx))
+                {
+                  std::fill(local.begin(), local.end(), 0.0);
+                  boundary_terms(idx, scratch[0], local.data(), nullptr, nullptr, nullptr);
+                  scatter(dofs, off, dofs, off, local.data(), npc, 0, 0);
+                }
+              if (desc.ghost_penalty)
+                for (int d = 0; d < dim; ++d)
+                  for (int side = 0; side < 2; ++side)
+                    {
+                      const int64_t nc = ghost_penalty_neighbor(idx, d, side);
+                      if (nc < 0)
+                        continue;
+                      int nidx[3];
+                      cell_index((uint64_t)nc, nidx);
+                      cell_dofs(nidx, noff, ndofs);
+                      const std::vector<double> &S = gp_matrix(idx, nidx, d, side);
+                      const int                  n2 = 2 * npc;
+                      scatter(dofs, off, dofs, off, S.data(), n2, 0, 0);
+                      scatter(dofs, off, ndofs, noff, S.data(), n2, 0, npc);
+                      scatter(ndofs, noff, dofs, off, S.data(), n2, npc, 0);
+                      scatter(ndofs, noff, ndofs, noff, S.data(), n2, npc, npc);
+                    }
+            }
           b0 = b1;
           t_scatter += now() - t1;
         }
