@@ -908,6 +908,10 @@ namespace GDM
       double boundary_value    = 1.0;
       bool   kind_mass         = false;
       double outside_diagonal  = 1.0;
+      bool   surface_terms         = true;  // false: no Nitsche on the cut surface (two-domain runs couple there)
+      bool   domain_boundary_terms = false; // Nitsche on the box boundary (function_domain_dbc, wave/stiffness.h:262-340)
+      bool   negate_level_set      = false; // the domain is {level set > 0}: the outer field of the two-domain runs
+      unsigned long long row_begin = 0, row_end = 0; // locally owned rows of this rank; 0, 0 = all
     };
     CutCellSetup(const unsigned int fe_degree, const unsigned int n_subdivisions, const double left, const double right,
                  const Function<dim> &level_set_function, const Parameters &prm = Parameters())
@@ -931,6 +935,10 @@ namespace GDM
       d.boundary_value    = prm.boundary_value;
       d.kind              = prm.kind_mass ? 1 : 0;
       d.outside_diagonal  = prm.outside_diagonal;
+      d.no_surface_terms      = !prm.surface_terms;
+      d.domain_boundary_terms = prm.domain_boundary_terms;
+      d.row_begin             = prm.row_begin;
+      d.row_end               = prm.row_end;
       // VectorTools::interpolate of the level set into FE_Q(1): nodal values, x fastest
       std::vector<double> level_set(n_nodes);
       const double        h = (right - left) / n_subdivisions;
@@ -943,7 +951,7 @@ namespace GDM
               x[e] = left + (r % (n_subdivisions + 1)) * h;
               r /= n_subdivisions + 1;
             }
-          level_set[i] = level_set_function.value(x, 0);
+          level_set[i] = (prm.negate_level_set ? -1.0 : 1.0) * level_set_function.value(x, 0);
         }
       n_dofs = n_nodes;
       dealii::internal::check(gdm_cut_poisson_create(&d, level_set.data(), &cut));
@@ -984,6 +992,26 @@ namespace GDM
       double                  e = 0;
       dealii::internal::check(gdm_cut_l2_error_inside(cut, solution.data(), &VectorTools::fn_trampoline<dim>, &c, &e));
       return e;
+    }
+    // <gamma_D / h v - dv/dn, g> on the box boundary (the load that belongs to domain_boundary_terms)
+    std::vector<double> boundary_load_vector(const Function<dim> &g) const
+    {
+      std::vector<double>     b(n_dofs);
+      VectorTools::FnCtx<dim> c{&g};
+      dealii::internal::check(gdm_cut_boundary_load_vector(cut, &VectorTools::fn_trampoline<dim>, &c, b.data()));
+      return b;
+    }
+    // interface coupling of the two-domain runs (wave/stiffness.h:441-574) as a CSR-only operator: `matrix` must have
+    // been created with scale 0; which = 0: P_ij = <n . grad phi_i, phi_j>, 1: P^T, 2: Q_ij = <phi_i, phi_j>
+    void attach_coupling_to(SparseMatrix<double> &matrix, const int which) const
+    {
+      uint64_t n_rows = 0, nnz = 0;
+      dealii::internal::check(gdm_cut_coupling_rows(cut, which, 0, 0, &n_rows, &nnz, nullptr, nullptr, nullptr, nullptr));
+      std::vector<uint64_t> row_ids(n_rows), rowptr(n_rows + 1), col(nnz);
+      std::vector<double>   val(nnz);
+      dealii::internal::check(gdm_cut_coupling_rows(cut, which, n_rows, nnz, &n_rows, &nnz, row_ids.data(), rowptr.data(),
+                                                    col.data(), val.data()));
+      matrix.attach_irregular_rows(row_ids, rowptr, col, val);
     }
     // L2, L1, Linf over the inside part (wave/problem.h:531-615)
     std::array<double, 3> error_norms_inside(const std::vector<double> &solution, const Function<dim> &exact) const

@@ -18,7 +18,12 @@ What the reference does with deal.II's `NonMatching` classes before the hot path
                         terms on the surface, ghost penalty on the faces `face_has_ghost_penalty` flags (`:123-146`),
                         zero diagonal -> 1 (`:324-329`).  `gp_h_power=3` gives the scaling of the wave application's
                         matrix (`applications/wave/include/gdm/wave/stiffness.h:760-765`).
-* `l2_error_inside`     `prototypes/cut_poisson_01_gdm.cc:349-398`.
+* `l2_error_inside`     `prototypes/cut_poisson_01_gdm.cc:349-398`; `error_norms_inside`: the L2 / L1 / Linf columns of
+                        `applications/wave/include/gdm/wave/problem.h:531-615`.
+* `load_functionals`    the data-dependent part of the residual `wave/stiffness.h:186-260` (volume source, Nitsche data).
+* `domain_boundary_terms`, `coupling_matrices`  the two-domain runs: Nitsche on the box boundary (`wave/stiffness.h:262-340`)
+                        and the coupling on the cut surface (`:441-574`).
+`oracle/wave_app.py` drives these through the wave application's runs; pinned by `tests/test_cut_cell.py`.
 """
 import numpy as np
 import scipy.sparse as sp

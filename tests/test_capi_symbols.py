@@ -67,3 +67,10 @@ def test_cpp_drivers_compile_against_include_gdm(lib, tmp_path):
                                "-o", exe, os.path.join(ROOT, "examples", name + ".cc"), "-L" + pkg, "-lgdm_b200",
                                "-Wl,-rpath," + pkg])
         assert os.path.exists(exe)
+    # every member of the cut-cell set-up mirror, in every dimension (the drivers use only some of them)
+    tu = tmp_path / "instantiate.cc"
+    tu.write_text('#include <gdm/system.h>\n#include <gdm/matrix_creator.h>\n#include <gdm/vector_tools.h>\n'
+                  'template class GDM::CutCellSetup<1>;\ntemplate class GDM::CutCellSetup<2>;\n'
+                  'template class GDM::CutCellSetup<3>;\nint main() { return 0; }\n')
+    subprocess.check_call(["g++", "-O0", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           "-o", str(tmp_path / "instantiate"), str(tu), "-L" + pkg, "-lgdm_b200", "-Wl,-rpath," + pkg])
