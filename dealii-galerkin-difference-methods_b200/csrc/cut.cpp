@@ -267,7 +267,7 @@ namespace gdm
       const int k = height_direction(funcs);
       if (k < 0)
         {
-          if (depth >= 8)
+          if (depth >= 16)
             { // give up: plain Gauss points, sign test per point
               std::vector<Pt> pts;
               tensor_gauss(lo, hi, d, g, pts);
@@ -350,7 +350,7 @@ namespace gdm
       const int k = height_direction({f});
       if (k < 0)
         {
-          if (depth >= 8)
+          if (depth >= 16)
             return;
           int e = 0;
           for (int j = 1; j < d; ++j)

@@ -141,7 +141,7 @@ def _volume(funcs, signs, lo, hi, xg, wg, depth=0):
         return _line(funcs, signs, np.zeros((1, 0)), np.ones(1), 0, lo, hi, xg, wg)
     k = _height_direction(funcs)
     if k is None:
-        if depth >= 8:  # give up: low-order, sign test per point
+        if depth >= 16:  # give up: low-order, sign test per point
             pts, w = _tensor_gauss(lo, hi, xg, wg)
             ok = np.ones(len(w), dtype=bool)
             for c, s in zip(funcs, signs):
@@ -215,7 +215,7 @@ def _surface(c, lo, hi, xg, wg, depth=0):
         return np.array([[t]]), np.ones(1), np.array([[np.sign(b - a)]])
     k = _height_direction([c])
     if k is None:
-        if depth >= 8:
+        if depth >= 16:
             return np.zeros((0, d)), np.zeros(0), np.zeros((0, d))
         e = int(np.argmax(hi - lo))
         mid = 0.5 * (lo[e] + hi[e])
