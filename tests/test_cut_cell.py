@@ -419,3 +419,21 @@ def test_product_setup_reproduces_wave_composite_golden_on_host(lib, golden_dir)
             for i in range(3):
                 assert abs(e[i] - gold[2 * step + kk][2 + i]) <= 6e-9 * gold[2 * step + kk][2 + i], (step, kk, e, gold[2 * step + kk])
         t, y = rk.evolve_one_time_step(f, t, dt, y)
+
+
+def test_cut_rows_do_not_depend_on_thread_count(lib, monkeypatch):
+    """The intersected cells are evaluated by several threads and scattered in cell order: same bits for 1, 3 and the
+    default number of threads."""
+    import gdm_b200 as g
+    s, ls = sphere_problem(3, 3, 10)
+    ref = None
+    for threads in (None, "1", "3"):
+        if threads is None:
+            monkeypatch.delenv("GDM_CUT_THREADS", raising=False)
+        else:
+            monkeypatch.setenv("GDM_CUT_THREADS", threads)
+        c = g.CutPoisson(3, 3, [10] * 3, [-1.21] * 3, [1.21] * 3, ls, ghost_penalty=True)
+        got = c.rows() + (c.rhs(),)
+        if ref is None:
+            ref = got
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got))
