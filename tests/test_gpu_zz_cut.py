@@ -1,6 +1,10 @@
-"""(Named to run last: two of the three cases could not be run on a GPU before the round's GPU budget ended.)
-BASELINE configuration 5 in miniature on the GPU: the reference's cut Poisson prototype end to end -- cut-cell set-up
-on the host (`gdm_cut_*`), tensor-product stiffness apply with the cut / ghost-penalty rows attached as CSR, CG."""
+"""Cut-cell problems on the GPU: cut-cell set-up on the host (`gdm_cut_*`), tensor-product apply with the cut /
+ghost-penalty rows attached as CSR, CG and Runge-Kutta around it -- the reference's cut Poisson prototype (BASELINE
+configuration 5 in miniature) and the explicit runs of applications/wave.
+
+Named to run last: only `test_cut_poisson_01_gdm[False]` ran on a B200 before the round's GPU budget ended
+(profiles/r2/session_ao_cut_pytest.log); the other cases were checked on the CPU piece by piece (tests/test_cut_cell.py
+covers their host side against the goldens) and their logic against a numpy stand-in for the GPU classes."""
 import numpy as np
 import pytest
 
