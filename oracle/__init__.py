@@ -14,7 +14,7 @@ Pinning: the restatement is checked against the reference's committed golden
 outputs (`tests/golden/*.output`, copied by `tests/golden/make_golden.py`):
 poly_01, fe_02_gdm, poisson_01_gdm, poisson_02_gdm (1 and 3 ranks), mass_01_gdm,
 mass_02_gdm, elasticity_01_gdm, prototypes/cut_poisson_01_gdm (cut.py), applications/wave/tests/{wave_0, heat_0, heat_1,
-wave_composite_0, heat_composite_0} (wave_app.py, every printed step).  3D has no reference golden (`tests/fe_01_gdm.output` is missing
+wave_composite_0, heat_composite_0, wave_1 (2D, cut_q.py), step85_0 (2D, 5 digits)} (wave_app.py, every printed step).  3D has no reference golden (`tests/fe_01_gdm.output` is missing
 upstream): 3D parity is pinned only through the dimension-generic cell-loop
 restatement validated in 1D/2D.
 """

@@ -58,7 +58,10 @@ def cell_vertex_values(system, ls, cell):
 
 
 def classify(system, ls):
-    """Per cell INSIDE / OUTSIDE / INTERSECTED (`location_to_level_set`)."""
+    """Per cell INSIDE / OUTSIDE / INTERSECTED (`location_to_level_set`).  `ls`: nodal values of a Q1 level set, or a
+    geometry object with `classify(system)` and `rules(system, cell, n_gauss)` (`oracle/cut_q.py`: level set of degree p)."""
+    if hasattr(ls, "classify"):
+        return ls.classify(system)
     out = np.zeros(system.n_cells(), dtype=np.int8)
     for cell in range(system.n_cells()):
         v = cell_vertex_values(system, ls, cell)
@@ -255,6 +258,13 @@ def _surface(c, lo, hi, xg, wg, depth=0):
     return np.array(pts), np.array(wts), np.array(nrm)
 
 
+def cell_rules(system, ls, cell, n_gauss):
+    """Inside and surface rules of a cell for either kind of level set (see `classify`)."""
+    if hasattr(ls, "rules"):
+        return ls.rules(system, cell, n_gauss)
+    return cut_quadrature(cell_vertex_values(system, ls, cell), n_gauss)
+
+
 def cut_quadrature(vertex_values, n_gauss):
     """Inside ({psi < 0}) and surface ({psi = 0}) quadratures on the unit cell for the multilinear function with the
     given vertex values (shape (2,)*dim).  Returns (points, weights), (points, weights, normals)."""
@@ -357,7 +367,7 @@ def assemble_cut_poisson(system, ls, ghost_penalty=True, ghost_parameter=0.5, ni
             ref = np.stack([g.ravel() for g in grids[::-1]], axis=1)  # the point order of _cell_tables (x fastest)
             rhs[dofs] += np.einsum("q,q,qi->i", jxw_full, fval(physical_points(system, cell, ref)), value)
         else:
-            (ip, iw), (sp_, sw, sn) = cut_quadrature(cell_vertex_values(system, ls, cell), p + 1)
+            (ip, iw), (sp_, sw, sn) = cell_rules(system, ls, cell, p + 1)
             local = np.zeros((len(dofs), len(dofs)))
             lrhs = np.zeros(len(dofs))
             if len(iw):
@@ -437,7 +447,7 @@ def _errors_inside(system, ls, u, exact, location=None):
             ref = np.stack([g.ravel() for g in grids[::-1]], axis=1)
             jxw = jxw_full
         else:
-            (ref, w), _ = cut_quadrature(cell_vertex_values(system, ls, cell), p + 1)
+            (ref, w), _ = cell_rules(system, ls, cell, p + 1)
             if not len(w):
                 continue
             value, _ = shape_at_points(system, cell, ref)
@@ -475,7 +485,7 @@ def load_functionals(system, ls, nitsche_parameter=None, location=None):
             value, _ = get([system.variant(idx[e], e) for e in range(dim)])
             volume.append((dofs, physical_points(system, cell, full_ref), value * jxw_full[:, None]))
             continue
-        (ip, iw), (sp_, sw, sn) = cut_quadrature(cell_vertex_values(system, ls, cell), p + 1)
+        (ip, iw), (sp_, sw, sn) = cell_rules(system, ls, cell, p + 1)
         if len(iw):
             value, _ = shape_at_points(system, cell, ip)
             volume.append((dofs, physical_points(system, cell, ip), value * (iw * vol)[:, None]))
@@ -561,7 +571,7 @@ def coupling_matrices(system, ls):
     for cell in range(system.n_cells()):
         if location[cell] != INTERSECTED:
             continue
-        _, (sp_, sw, sn) = cut_quadrature(cell_vertex_values(system, ls, cell), p + 1)
+        _, (sp_, sw, sn) = cell_rules(system, ls, cell, p + 1)
         if not len(sw):
             continue
         dofs = np.asarray(system.get_dof_indices(cell))

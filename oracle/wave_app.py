@@ -50,6 +50,9 @@ def wave_operators(params):
     s = System(dim, p, 1, add_ghost_layer=True)
     s.subdivided_hyper_cube(params["n_subdivisions"], params["left"], params["right"])
     ls = cut.interpolate_level_set(s, cut.sphere_level_set([0.0] * dim, 1.0))
+    if params.get("level_set_degree", 1) > 1:  # the 2D presets: FE_Q(fe_degree) level set (`wave-app.cc:277`)
+        from .cut_q import LevelSetQ
+        ls = LevelSetQ(s, cut.sphere_level_set([0.0] * dim, 1.0), params["level_set_degree"])
     M, _, loc = cut.assemble_cut_poisson(s, ls, True, params["ghost_parameter_M"], rhs_value=0.0, gp_h_power=3, kind="mass")
     A, _, _ = cut.assemble_cut_poisson(s, ls, True, params["ghost_parameter_A"], params["nitsche_parameter"],
                                        rhs_value=0.0, boundary_value=0.0, gp_h_power=1, outside_diagonal=0.0)
@@ -192,3 +195,29 @@ def composite_run(params, second_order):
         postprocess(time.get_current_time() + time.get_next_step_size())
         time.advance_time()
     return rows
+
+
+def step85_preset(dim=2):
+    """`applications/wave/wave-app.cc:13-61` ("step85"): Poisson, f = 4, g = 1, exact 1 - 2/dim (|x|^2 - 1)."""
+    p = 3
+    return dict(dim=dim, fe_degree=p, n_subdivisions=40, left=-1.21, right=1.21, ghost_parameter_A=0.5,
+                nitsche_parameter=5.0 * p, level_set_degree=p,
+                exact=lambda pts, t: 1.0 - 2.0 / dim * ((pts ** 2).sum(axis=1) - 1.0))
+
+
+def poisson_run(params=None):
+    """`problem.h:46-70` ("poisson"): the assembled stiffness matrix of `wave/stiffness.h:589-799` (ghost penalty with
+    h^3, zero diagonal -> 1), right-hand side `compute_rhs(., 0, false, 0)` = (v, f) + <gamma_D / h v - d_n v, g>, one
+    solve, one printed line."""
+    params = params or step85_preset(2)
+    dim, p = params["dim"], params["fe_degree"]
+    s = System(dim, p, 1, add_ghost_layer=True)
+    s.subdivided_hyper_cube(params["n_subdivisions"], params["left"], params["right"])
+    ls = cut.interpolate_level_set(s, cut.sphere_level_set([0.0] * dim, 1.0))
+    if params.get("level_set_degree", 1) > 1:
+        from .cut_q import LevelSetQ
+        ls = LevelSetQ(s, cut.sphere_level_set([0.0] * dim, 1.0), params["level_set_degree"])
+    S, rhs, loc = cut.assemble_cut_poisson(s, ls, True, params["ghost_parameter_A"], params["nitsche_parameter"],
+                                           rhs_value=4.0, boundary_value=1.0, gp_h_power=3)
+    u = sla.spsolve(S.tocsc(), rhs)
+    return [(0, 0.0) + cut.error_norms_inside(s, ls, u, lambda pts: params["exact"](pts, 0.0), loc)]
