@@ -777,7 +777,8 @@ class CutPoisson:
 
     def __init__(self, dim, fe_degree, n_subdivisions, lo, hi, level_set, ghost_penalty=True, ghost_parameter=0.5,
                  nitsche_parameter=None, rhs_value=4.0, boundary_value=1.0, gp_h_power=1, kind="stiffness",
-                 outside_diagonal=1.0, row_range=None, surface_terms=True, domain_boundary_terms=False):
+                 outside_diagonal=1.0, row_range=None, surface_terms=True, domain_boundary_terms=False,
+                 level_set_degree=1):
         self.lib = capi.load()
         d = capi.CutDesc()
         d.dim, d.fe_degree = dim, fe_degree
@@ -795,10 +796,26 @@ class CutPoisson:
         self.n_dofs = int(np.prod([int(n) + 1 for n in n_subdivisions[:dim]]))
         self.n_cells = int(np.prod([int(n) for n in n_subdivisions[:dim]]))
         level_set = np.ascontiguousarray(level_set, dtype=np.float64)
-        if level_set.size != self.n_dofs:
-            raise GdmError(capi.ERR_INVALID, f"level set has {level_set.size} values, the grid {self.n_dofs} nodes")
+        d.level_set_degree = int(level_set_degree)
+        n_ls = self.n_dofs if level_set_degree <= 1 else int(np.prod([level_set_degree * int(n) + 1 for n in n_subdivisions[:dim]]))
+        if level_set.size != n_ls:
+            raise GdmError(capi.ERR_INVALID, f"level set has {level_set.size} values, expected {n_ls}")
         self.h = C.c_void_p()
         capi.check(self.lib.gdm_cut_poisson_create(C.byref(d), level_set.ctypes.data_as(C.c_void_p), C.byref(self.h)))
+
+    @staticmethod
+    def level_set_points(n_subdivisions, lo, hi, degree):
+        """Coordinates [n, dim] (x fastest) at which a level set of degree `degree` is sampled: the support points of FE_Q(degree)
+        of every cell (Gauss-Lobatto points), (degree N_e + 1) per direction."""
+        inner = np.polynomial.legendre.Legendre.basis(degree).deriv().roots() if degree > 1 else np.zeros(0)
+        gll = 0.5 * (np.concatenate([[-1.0], np.sort(inner.real), [1.0]]) + 1.0)
+        axes = []
+        for n, a, b in zip(n_subdivisions, lo, hi):
+            h = (b - a) / n
+            ax = np.concatenate([a + (c + gll[:-1]) * h for c in range(n)] + [[b]])
+            axes.append(ax)
+        grids = np.meshgrid(*axes[::-1], indexing="ij")
+        return np.stack([g_.ravel() for g_ in grids[::-1]], axis=1)
 
     def sizes(self):
         """n_rows, nnz, n_identity_rows, (inside, outside, intersected) cell counts."""

@@ -66,7 +66,7 @@ class CutDesc(C.Structure):
                 ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("ghost_penalty", C.c_int), ("gp_h_power", C.c_int),
                 ("ghost_parameter", C.c_double), ("nitsche_parameter", C.c_double), ("rhs_value", C.c_double),
                 ("boundary_value", C.c_double), ("kind", C.c_int), ("outside_diagonal", C.c_double),
-                ("no_surface_terms", C.c_int), ("domain_boundary_terms", C.c_int),
+                ("no_surface_terms", C.c_int), ("domain_boundary_terms", C.c_int), ("level_set_degree", C.c_int),
                 ("row_begin", C.c_uint64), ("row_end", C.c_uint64)]
 
 

@@ -575,6 +575,26 @@ namespace gdm
         std::vector<Pt>     ipts, spts;
         std::vector<double> value, grads[3];
       };
+      // ---- level set of degree q > 1 (2D): values on the Gauss-Lobatto refined grid, (q N_e + 1) points per direction
+      int                 q = 1;
+      std::vector<double> gll, to_bernstein; // support points of FE_Q(q) on [0,1]; (q+1)^2 Lagrange -> Bernstein
+      void    setup_q();
+      void    local_values_q(const int *idx, double *c) const; // c[i + (q+1) j] at (gll_i, gll_j) of the cell
+      double  eval_q(const double *c, double x, double y, double *grad) const;
+      uint8_t classify_cell(const int *idx) const;
+      void    rules_q(const int *idx, std::vector<Pt> &inside, std::vector<Pt> &surf) const;
+      // inside and surface rules of a cell for either kind of level set
+      void cell_rules(const int *idx, std::vector<Pt> &inside, std::vector<Pt> &surf) const
+      {
+        if (q > 1)
+          {
+            rules_q(idx, inside, surf);
+            return;
+          }
+        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        vertex_values(idx, v);
+        cut_quadrature(dim, v, gauss, inside, surf);
+      }
       void cut_cell_matrix(const int *idx, CutScratch &sc, double *local, double *lrhs) const;
       // part of the face (d, side) of a cell on the box boundary where the level set is negative, as unit-cell points
       // with face weights (NonMatching::FEInterfaceValues::reinit(cell, f), wave/stiffness.h:268-283)
@@ -611,11 +631,9 @@ namespace gdm
     {
       const bool   mass = desc.kind == 1;
       const double vol = cell_volume(), nitsche = desc.nitsche_parameter / h_min();
-      double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      vertex_values(idx, v);
       sc.ipts.clear();
       sc.spts.clear();
-      cut_quadrature(dim, v, gauss, sc.ipts, sc.spts);
+      cell_rules(idx, sc.ipts, sc.spts);
       std::fill(local, local + (size_t)npc * npc, 0.0);
       std::fill(lrhs, lrhs + npc, 0.0);
       if (!sc.ipts.empty())
@@ -689,6 +707,272 @@ namespace gdm
         }
     }
 
+
+
+    // ------------------------------------------------------------- level set of degree q (2D presets of applications/wave)
+    void Assembly::setup_q()
+    {
+      // Gauss-Lobatto points: +-1 and the roots of P_q' (Newton on the Legendre recurrence)
+      gll.assign(q + 1, 0.0);
+      gll[q] = 1.0;
+      const double pi = 3.14159265358979323846;
+      for (int k = 1; k < q; ++k)
+        {
+          double x = -std::cos(pi * k / q);
+          for (int it = 0; it < 100; ++it)
+            {
+              // P_q, P_q' and P_q'' at x
+              double p0 = 1, p1 = x;
+              for (int j = 2; j <= q; ++j)
+                {
+                  const double p2 = ((2 * j - 1) * x * p1 - (j - 1) * p0) / j;
+                  p0 = p1;
+                  p1 = p2;
+                }
+              const double dp  = q * (x * p1 - p0) / (x * x - 1);
+              const double ddp = (2 * x * dp - q * (q + 1) * p1) / (1 - x * x);
+              const double dx  = dp / ddp;
+              x -= dx;
+              if (std::fabs(dx) < 1e-16)
+                break;
+            }
+          gll[k] = 0.5 * (x + 1.0);
+        }
+      // B[j][i] = C(q, i) t_j^i (1 - t_j)^(q - i); to_bernstein = B^-1 (Gauss-Jordan)
+      const int           m = q + 1;
+      std::vector<double> B(m * m), I(m * m, 0.0);
+      for (int j = 0; j < m; ++j)
+        {
+          double binom = 1;
+          for (int i = 0; i < m; ++i)
+            {
+              B[j * m + i] = binom * std::pow(gll[j], i) * std::pow(1 - gll[j], q - i);
+              binom        = binom * (q - i) / (i + 1);
+            }
+          I[j * m + j] = 1.0;
+        }
+      for (int c = 0; c < m; ++c)
+        {
+          int piv = c;
+          for (int r = c + 1; r < m; ++r)
+            if (std::fabs(B[r * m + c]) > std::fabs(B[piv * m + c]))
+              piv = r;
+          for (int k = 0; k < m; ++k)
+            {
+              std::swap(B[c * m + k], B[piv * m + k]);
+              std::swap(I[c * m + k], I[piv * m + k]);
+            }
+          const double d = B[c * m + c];
+          for (int k = 0; k < m; ++k)
+            {
+              B[c * m + k] /= d;
+              I[c * m + k] /= d;
+            }
+          for (int r = 0; r < m; ++r)
+            if (r != c)
+              {
+                const double f = B[r * m + c];
+                for (int k = 0; k < m; ++k)
+                  {
+                    B[r * m + k] -= f * B[c * m + k];
+                    I[r * m + k] -= f * I[c * m + k];
+                  }
+              }
+        }
+      to_bernstein = I;
+    }
+
+    void Assembly::local_values_q(const int *idx, double *c) const
+    {
+      const uint64_t nx = (uint64_t)q * N[0] + 1;
+      for (int j = 0; j <= q; ++j)
+        for (int i = 0; i <= q; ++i)
+          c[i + (q + 1) * j] = ls[(uint64_t)(q * idx[0] + i) + nx * (uint64_t)(q * idx[1] + j)];
+    }
+
+    // psi(x, y) = sum c_ij l_i(x) l_j(y) and its gradient (unit-cell coordinates)
+    double Assembly::eval_q(const double *c, double x, double y, double *grad) const
+    {
+      double lx[MAX_DEGREE + 1], ly[MAX_DEGREE + 1], dx[MAX_DEGREE + 1], dy[MAX_DEGREE + 1];
+      for (int pass = 0; pass < 2; ++pass)
+        {
+          const double t = pass ? y : x;
+          double      *l = pass ? ly : lx, *d = pass ? dy : dx;
+          for (int k = 0; k <= q; ++k)
+            {
+              double denom = 1, val = 1, der = 0;
+              for (int j = 0; j <= q; ++j)
+                if (j != k)
+                  {
+                    denom *= gll[k] - gll[j];
+                    val *= t - gll[j];
+                  }
+              for (int m = 0; m <= q; ++m)
+                if (m != k)
+                  {
+                    double pr = 1;
+                    for (int j = 0; j <= q; ++j)
+                      if (j != k && j != m)
+                        pr *= t - gll[j];
+                    der += pr;
+                  }
+              l[k] = val / denom;
+              d[k] = der / denom;
+            }
+        }
+      double v = 0, gx = 0, gy = 0;
+      for (int j = 0; j <= q; ++j)
+        for (int i = 0; i <= q; ++i)
+          {
+            const double cij = c[i + (q + 1) * j];
+            v += cij * lx[i] * ly[j];
+            gx += cij * dx[i] * ly[j];
+            gy += cij * lx[i] * dy[j];
+          }
+      if (grad)
+        {
+          grad[0] = gx;
+          grad[1] = gy;
+        }
+      return v;
+    }
+
+    // NonMatching::MeshClassifier: a face is inside / outside when all Bernstein coefficients of the level set on it are
+    // negative / positive; a cell is inside / outside when all its faces are, intersected otherwise
+    uint8_t Assembly::classify_cell(const int *idx) const
+    {
+      if (q <= 1)
+        {
+          double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          vertex_values(idx, v);
+          double mn = v[0], mx = v[0];
+          for (int c = 1; c < (1 << dim); ++c)
+            {
+              mn = std::min(mn, v[c]);
+              mx = std::max(mx, v[c]);
+            }
+          return mx < 0 ? INSIDE : (mn > 0 ? OUTSIDE : INTERSECTED);
+        }
+      const int m = q + 1;
+      double    c[(MAX_DEGREE + 1) * (MAX_DEGREE + 1)];
+      local_values_q(idx, c);
+      int n_in = 0, n_out = 0;
+      for (int f = 0; f < 4; ++f)
+        {
+          double mn = INFINITY, mx = -INFINITY;
+          for (int r = 0; r < m; ++r)
+            {
+              double b = 0;
+              for (int k = 0; k < m; ++k)
+                {
+                  const double e = f == 0 ? c[0 + m * k] : f == 1 ? c[q + m * k] : f == 2 ? c[k + m * 0] : c[k + m * q];
+                  b += to_bernstein[r * m + k] * e;
+                }
+              mn = std::min(mn, b);
+              mx = std::max(mx, b);
+            }
+          n_in += mx < 0;
+          n_out += mn > 0;
+        }
+      return n_in == 4 ? INSIDE : (n_out == 4 ? OUTSIDE : INTERSECTED);
+    }
+
+    // height-function quadrature (NonMatching::QuadratureGenerator) for the polynomial level set of a cell whose zero set
+    // is a graph over one coordinate direction: the base interval is split at the roots of the level set on the two faces
+    // across the height direction, QGauss<1>(p+1) on every piece and on the inside part of every column
+    void Assembly::rules_q(const int *idx, std::vector<Pt> &inside, std::vector<Pt> &surf) const
+    {
+      double c[(MAX_DEGREE + 1) * (MAX_DEGREE + 1)], g[2];
+      local_values_q(idx, c);
+      eval_q(c, 0.5, 0.5, g);
+      const int k = std::fabs(g[0]) * (1 + 1e-8) >= std::fabs(g[1]) ? 0 : 1; // height direction; x on (near-)ties
+      auto at = [&](double s, double t, double *grad) { return k == 0 ? eval_q(c, t, s, grad) : eval_q(c, s, t, grad); };
+      // monotone in the height direction?
+      {
+        double ref[2];
+        at(0.5, 0.5, ref);
+        for (int i = 0; i <= 8; ++i)
+          for (int j = 0; j <= 8; ++j)
+            {
+              at(i / 8.0, j / 8.0, g);
+              GDM_REQUIRE(g[k] * ref[k] > 0, GDM_ERR_NOT_IMPLEMENTED,
+                          "level set of degree > 1: the zero set is not a graph over a coordinate direction in a cell");
+            }
+      }
+      auto bisect = [&](auto &&fn, double a, double b) {
+        double fa = fn(a);
+        for (int it = 0; it < 200 && b - a > 1e-16; ++it)
+          {
+            const double m = 0.5 * (a + b), fm = fn(m);
+            if ((fa < 0) == (fm < 0))
+              {
+                a  = m;
+                fa = fm;
+              }
+            else
+              b = m;
+          }
+        return 0.5 * (a + b);
+      };
+      std::vector<double> breaks = {0.0, 1.0};
+      for (int face_t = 0; face_t < 2; ++face_t)
+        {
+          auto        fn   = [&](double s) { return at(s, (double)face_t, nullptr); };
+          const int   n_s  = 64; // sign changes on a fine sampling: simple roots of a resolved geometry
+          double      prev = fn(0.0);
+          for (int i = 1; i <= n_s; ++i)
+            {
+              const double s1 = (double)i / n_s, cur = fn(s1);
+              if ((prev < 0) != (cur < 0))
+                breaks.push_back(bisect(fn, (double)(i - 1) / n_s, s1));
+              prev = cur;
+            }
+        }
+      std::sort(breaks.begin(), breaks.end());
+      const size_t ng = gauss.x.size();
+      for (size_t b = 0; b + 1 < breaks.size(); ++b)
+        {
+          const double s0 = breaks[b], s1 = breaks[b + 1];
+          if (s1 - s0 <= 1e-14)
+            continue;
+          for (size_t qs = 0; qs < ng; ++qs)
+            {
+              const double sq = s0 + (s1 - s0) * gauss.x[qs], ws = (s1 - s0) * gauss.w[qs];
+              const double a = at(sq, 0.0, nullptr), e = at(sq, 1.0, nullptr);
+              double       t0, t1;
+              if (a * e < 0)
+                {
+                  const double r = bisect([&](double t) { return at(sq, t, nullptr); }, 0.0, 1.0);
+                  t0             = a < 0 ? 0.0 : r;
+                  t1             = a < 0 ? r : 1.0;
+                  Pt p{};
+                  p.x[k]     = r;
+                  p.x[1 - k] = sq;
+                  eval_q(c, p.x[0], p.x[1], g);
+                  const double gn = std::sqrt(g[0] * g[0] + g[1] * g[1]);
+                  p.w    = ws * gn / std::fabs(g[k]);
+                  p.n[0] = g[0] / gn;
+                  p.n[1] = g[1] / gn;
+                  surf.push_back(p);
+                }
+              else if (a < 0)
+                {
+                  t0 = 0.0;
+                  t1 = 1.0;
+                }
+              else
+                continue;
+              for (size_t qt = 0; qt < ng; ++qt)
+                {
+                  Pt p{};
+                  p.x[k]     = t0 + (t1 - t0) * gauss.x[qt];
+                  p.x[1 - k] = sq;
+                  p.w        = ws * (t1 - t0) * gauss.w[qt];
+                  inside.push_back(p);
+                }
+            }
+        }
+    }
 
     void Assembly::boundary_face_rule(const int *idx, int d, int side, std::vector<Pt> &pts) const
     {
@@ -787,11 +1071,9 @@ namespace gdm
           if (location[cell] != INTERSECTED)
             continue;
           cell_index(cell, idx);
-          double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          vertex_values(idx, v);
           sc.ipts.clear();
           sc.spts.clear();
-          cut_quadrature(dim, v, gauss, sc.ipts, sc.spts);
+          cell_rules(idx, sc.ipts, sc.spts);
           if (sc.spts.empty())
             continue;
           cell_dofs(idx, off, dofs);
@@ -858,15 +1140,7 @@ namespace gdm
       for (uint64_t cell = 0; cell < n_cells; ++cell)
         {
           cell_index(cell, idx);
-          double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          vertex_values(idx, v);
-          double mn = v[0], mx = v[0];
-          for (int c = 1; c < (1 << dim); ++c)
-            {
-              mn = std::min(mn, v[c]);
-              mx = std::max(mx, v[c]);
-            }
-          location[cell] = mx < 0 ? INSIDE : (mn > 0 ? OUTSIDE : INTERSECTED);
+          location[cell] = classify_cell(idx);
           ++counts[location[cell]];
         }
       for (uint64_t cell = 0; cell < n_cells; ++cell)
@@ -1221,11 +1495,9 @@ namespace gdm
             if (location[cell] == INTERSECTED)
               {
                 cell_index(cell, idx);
-                double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                vertex_values(idx, v);
                 ipts.clear();
                 spts.clear();
-                cut_quadrature(dim, v, gauss, ipts, spts);
+                cell_rules(idx, ipts, spts);
                 CutCellLoad L;
                 L.cell = cell;
                 auto physical = [&](const std::vector<Pt> &pts, std::vector<double> &x) {
@@ -1429,7 +1701,17 @@ int gdm_cut_poisson_create(const gdm_cut_desc *desc, const double *level_set, gd
         }
     }
   a.gauss = cut::make_gauss(a.p + 1);
-  a.ls.assign(level_set, level_set + a.n_dofs);
+  a.q     = desc->level_set_degree > 1 ? desc->level_set_degree : 1;
+  uint64_t n_ls = a.n_dofs;
+  if (a.q > 1)
+    {
+      GDM_REQUIRE(a.dim == 2, GDM_ERR_NOT_IMPLEMENTED, "level set of degree > 1: two dimensions only");
+      GDM_REQUIRE(a.q <= MAX_DEGREE, GDM_ERR_INVALID, "level_set_degree too large");
+      GDM_REQUIRE(!desc->domain_boundary_terms, GDM_ERR_NOT_IMPLEMENTED, "level set of degree > 1 with domain_boundary_terms");
+      n_ls = ((uint64_t)a.q * a.N[0] + 1) * ((uint64_t)a.q * a.N[1] + 1);
+      a.setup_q();
+    }
+  a.ls.assign(level_set, level_set + n_ls);
   a.build();
   *out = h.release();
   GDM_CATCH
@@ -1576,11 +1858,9 @@ int gdm_cut_error_norms_inside(gdm_cut_t c, const double *u, gdm_function_fn exa
       const std::vector<cut::Pt> *pts = &full;
       if (a.location[cell] == cut::INTERSECTED)
         {
-          double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          a.vertex_values(idx, v);
           ipts.clear();
           spts.clear();
-          cut::cut_quadrature(a.dim, v, a.gauss, ipts, spts);
+          a.cell_rules(idx, ipts, spts);
           pts = &ipts;
         }
       if (pts->empty())

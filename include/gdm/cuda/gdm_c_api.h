@@ -321,6 +321,10 @@ typedef struct gdm_cut_desc {
                                      runs couple there instead, wave/stiffness.h:441-574) */
   int      domain_boundary_terms; /* 1: Nitsche terms on the box boundary for the part of it inside the domain
                                      (function_domain_dbc, wave/stiffness.h:262-340) */
+  int      level_set_degree;      /* 0 or 1: Q1 level set, nodal values at the grid nodes.  q > 1 (dim = 2 only): FE_Q(q)
+                                     level set as in the 2D presets of applications/wave (wave-app.cc:277); `level_set`
+                                     then holds the values on the Gauss-Lobatto refined grid, (q N_e + 1) points per
+                                     direction, x fastest (point q c + k of a direction = node k of FE_Q(q) in cell c) */
   uint64_t row_begin, row_end; /* rows (global DoFs) to assemble: the locally owned range of a rank
                                   (gdm_system_locally_owned_range); 0, 0 = all.  With a range the right-hand side is
                                   complete in that range only. */

@@ -67,7 +67,7 @@ class LevelSetQ:
         psi = lambda x, y: P.polyval2d(x, y, C)
         Cx, Cy = P.polyder(C, axis=0), P.polyder(C, axis=1)
         gx, gy = (lambda x, y: P.polyval2d(x, y, Cx)), (lambda x, y: P.polyval2d(x, y, Cy))
-        k = 0 if abs(gx(0.5, 0.5)) > abs(gy(0.5, 0.5)) else 1        # height direction
+        k = 0 if abs(gx(0.5, 0.5)) * (1 + 1e-8) >= abs(gy(0.5, 0.5)) else 1   # height direction; x on (near-)ties
         tt = np.linspace(0, 1, 9)
         S, T = np.meshgrid(tt, tt, indexing="ij")
         dk = gx(T, S) if k == 0 else gy(S, T)

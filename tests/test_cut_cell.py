@@ -460,8 +460,11 @@ def test_oracle_wave_2d_against_wave_1_golden(golden_dir):
 
 def test_oracle_reproduces_wave_1_golden_with_degree_3_level_set(golden_dir):
     """applications/wave/tests/wave_1.output with the preset's own geometry (level set interpolated with FE_Q(3),
-    `oracle/cut_q.py`): all three error columns to the 9 digits printed (first 31 of the 112 printed steps here; the whole
-    run agrees to 4.6e-9)."""
+    `oracle/cut_q.py`): the L2 and L1 columns to the 9 digits printed, the Linf column to 6e-8 (first 31 of the 112 printed
+    steps here; the whole run: 3e-9 / 5.7e-8).  The four cut cells on the diagonals have no preferred height direction
+    (|d_x psi| = |d_y psi| at the centre); deal.II's choice there is decided by rounding inside its bound estimates, this
+    restatement takes x.  With the comparison left to floating-point rounding (x in two of them, y in the other two) the
+    whole run agreed to 4.6e-9 in all columns."""
     from scipy.special import j0
     from oracle import wave_app
     k = 3 * np.pi
@@ -473,7 +476,7 @@ def test_oracle_reproduces_wave_1_golden_with_degree_3_level_set(golden_dir):
     for r, g_ in zip(rows, gold):
         assert r[0] == g_[0] and abs(r[1] - g_[1]) <= 5.1e-6
         for i in (2, 3, 4):
-            assert abs(r[i] - g_[i]) <= 6e-9 * g_[i], (r, g_)
+            assert abs(r[i] - g_[i]) <= (6e-9 if i < 4 else 1e-7) * g_[i], (r, g_)
 
 
 def test_oracle_reproduces_step85_0_golden(golden_dir):
@@ -485,3 +488,65 @@ def test_oracle_reproduces_step85_0_golden(golden_dir):
     g_ = _app_golden(golden_dir, "app_wave_step85_0.output")[0]
     for i in (2, 3, 4):
         assert abs(r[i] - g_[i]) <= 5e-5 * g_[i], (r, g_)
+
+
+# ------------------------------------------------------------------ level set of degree 3 (2D presets): product vs oracle
+def _degree_3_problem(n1):
+    import gdm_b200 as g
+    from oracle.cut_q import LevelSetQ
+    s = O.System(2, 3, 1)
+    s.subdivided_hyper_cube(n1, -1.21, 1.21)
+    fn = cut.sphere_level_set([0.0, 0.0], 1.0)
+    box = ([n1, n1], [-1.21] * 2, [1.21] * 2)
+    return s, LevelSetQ(s, fn, 3), box, fn(g.CutPoisson.level_set_points(*box, 3))
+
+
+def test_product_degree_3_level_set_matches_oracle(lib):
+    """gdm_cut_* with level_set_degree = 3 (FE_Q(3) level set on the Gauss-Lobatto refined grid, 2D) against
+    oracle/cut_q.py: cell locations through the Bernstein coefficients on the faces, stiffness + Nitsche + ghost penalty
+    rows, cut mass rows, right-hand side and load functionals."""
+    import gdm_b200 as g
+    s, geo, box, lsq = _degree_3_problem(20)
+    n = s.n_dofs()
+    c = g.CutPoisson(2, 3, *box, lsq, ghost_parameter=0.5, nitsche_parameter=15.0, level_set_degree=3)
+    A, rhs, loc = cut.assemble_cut_poisson(s, geo, True, 0.5, 15.0)
+    assert np.array_equal(c.locations(), loc)
+    assert abs(overlay_matrix(s, *c.rows()) - A).max() <= 1e-12 * abs(A).max()
+    assert np.abs(c.rhs() - rhs).max() <= 1e-13 * np.abs(rhs).max()
+    cm = g.CutPoisson(2, 3, *box, lsq, ghost_parameter=0.4, gp_h_power=3, kind="mass", rhs_value=0.0, level_set_degree=3)
+    M, _, _ = cut.assemble_cut_poisson(s, geo, True, 0.4, rhs_value=0.0, gp_h_power=3, kind="mass")
+    assert abs(overlay_matrix_kind(s, "mass", *cm.rows()) - M).max() <= 1e-12 * abs(M).max()
+    volume, surface = cut.load_functionals(s, geo, 15.0, loc)
+    ref = cut.apply_load(n, volume, lambda p_: np.sin(p_.sum(axis=1))) + cut.apply_load(n, surface, lambda p_: np.cos(p_[:, 0]))
+    got = c.load_vector(lambda pt, comp: np.sin(pt[0] + pt[1]), lambda pt, comp: np.cos(pt[0]))
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    with pytest.raises(g.GdmError):  # three dimensions: Q1 level sets only
+        g.CutPoisson(3, 3, [8] * 3, [-1.21] * 3, [1.21] * 3, np.zeros(25 ** 3), level_set_degree=3)
+
+
+def test_product_setup_reproduces_wave_1_golden_on_host(lib, golden_dir):
+    """applications/wave/tests/wave_1.output (2D, level set of degree 3) from the product's operators with the oracle's
+    RK4 and an exact mass solve in between (no GPU here): first 4 printed steps, all three columns."""
+    import gdm_b200 as g
+    import scipy.sparse.linalg as sla
+    from scipy.special import j0
+    from oracle import wave_app
+    prm = wave_app.wave_preset(1)
+    s, geo, box, lsq = _degree_3_problem(40)
+    n, k = s.n_dofs(), 3 * np.pi
+    cm = g.CutPoisson(2, 3, *box, lsq, ghost_parameter=prm["ghost_parameter_M"], gp_h_power=3, kind="mass", rhs_value=0.0,
+                      level_set_degree=3)
+    ca = g.CutPoisson(2, 3, *box, lsq, ghost_parameter=prm["ghost_parameter_A"], nitsche_parameter=prm["nitsche_parameter"],
+                      rhs_value=0.0, boundary_value=0.0, outside_diagonal=0.0, level_set_degree=3)
+    solve = sla.factorized(overlay_matrix_kind(s, "mass", *cm.rows()).tocsc())
+    A = overlay_matrix(s, *ca.rows())
+    ex = lambda t: (lambda pt, c: j0(k * np.hypot(pt[0], pt[1])) * np.cos(k * t))
+    y = np.concatenate([O.interpolate(s, lambda pts, c: j0(k * np.linalg.norm(pts, axis=1))), np.zeros(n)])
+    f = lambda t, yy: np.concatenate([yy[n:], solve(-(A @ yy[:n]) + ca.load_vector(None, ex(t)))])
+    gold = _app_golden(golden_dir, "app_wave_wave_1.output")
+    rk, t, dt = O.ExplicitRungeKutta4(), 0.0, 0.3 * 2.42 / 40
+    for step in range(4):
+        e = cm.error_norms_inside(y[:n], ex(t))
+        for i in range(3):
+            assert abs(e[i] - gold[step][2 + i]) <= (6e-9 if i < 2 else 1e-7) * gold[step][2 + i], (step, e, gold[step])
+        t, y = rk.evolve_one_time_step(f, t, dt, y)
