@@ -134,6 +134,7 @@ SIGNATURES = {
     "gdm_operator_create": (C.c_int, [_H, _H, C.POINTER(OperatorDesc), _PH]),
     "gdm_system_write_vtu": (C.c_int, [_H, C.POINTER(C.c_double), C.c_char_p, C.c_char_p]),
     "gdm_cut_poisson_create": (C.c_int, [C.POINTER(CutDesc), C.c_void_p, _PH]),
+    "gdm_cut_level_set_points": (C.c_int, [C.POINTER(CutDesc), _PU64, C.c_void_p]),
     "gdm_cut_destroy": (C.c_int, [_H]),
     "gdm_cut_sizes": (C.c_int, [_H, _PU64, _PU64, _PU64, _PU64]),
     "gdm_cut_rows": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

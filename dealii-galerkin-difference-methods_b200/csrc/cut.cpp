@@ -1668,6 +1668,41 @@ int gdm_cut_quadrature(int dim, const double *vertex_values, int n_gauss, uint64
   GDM_CATCH
 }
 
+int gdm_cut_level_set_points(const gdm_cut_desc *desc, uint64_t *n_points, double *points)
+{
+  GDM_TRY
+  GDM_ARG(desc);
+  GDM_ARG(n_points);
+  GDM_REQUIRE(desc->dim >= 1 && desc->dim <= 3, GDM_ERR_INVALID, "dim must be 1, 2 or 3");
+  const int     q = desc->level_set_degree > 1 ? desc->level_set_degree : 1;
+  GDM_REQUIRE(q <= MAX_DEGREE, GDM_ERR_INVALID, "level_set_degree too large");
+  cut::Assembly a;
+  a.q = q;
+  a.setup_q();
+  uint64_t n[3] = {1, 1, 1}, total = 1;
+  for (int e = 0; e < desc->dim; ++e)
+    {
+      GDM_REQUIRE(desc->n_subdivisions[e] >= 1, GDM_ERR_INVALID, "n_subdivisions");
+      n[e] = (uint64_t)q * desc->n_subdivisions[e] + 1;
+      total *= n[e];
+    }
+  *n_points = total;
+  if (points)
+    for (uint64_t i = 0; i < total; ++i)
+      {
+        uint64_t r = i;
+        for (int e = 0; e < desc->dim; ++e)
+          {
+            const uint64_t k = r % n[e];
+            r /= n[e];
+            const double h = (desc->hi[e] - desc->lo[e]) / desc->n_subdivisions[e];
+            points[i * desc->dim + e] =
+              k == n[e] - 1 ? desc->hi[e] : desc->lo[e] + ((double)(k / q) + a.gll[k % q]) * h;
+          }
+      }
+  GDM_CATCH
+}
+
 int gdm_cut_poisson_create(const gdm_cut_desc *desc, const double *level_set, gdm_cut_t *out)
 {
   GDM_TRY

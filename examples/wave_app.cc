@@ -1,11 +1,11 @@
 // The explicit runs of the reference's applications/wave/wave-app.cc written against include/gdm of this repository:
 //   ./wave_app 1 wave      (wave-app.cc:222-284, wave/problem.h:280-345: RK4 on [u; v], cut mass solves)
 //   ./wave_app 1 heat-rk   (wave-app.cc:62-150,  wave/problem.h:72-127)
+//   ./wave_app 2 wave      (the 2D preset: Bessel solution, level set interpolated with FE_Q(3))
 // Cut-cell set-up on the host (GDM::CutCellSetup), mass / stiffness operators with the cut rows attached, Jacobi-CG
 // mass solves and the Runge-Kutta stages on the GPU.  stdout has the reference's format (wave/problem.h:609-615 and
 // the " [L] solved in k" lines of :498); tests/test_gpu_zz_cut.py diffs the error columns against
-// applications/wave/tests/{wave_0,heat_1}.output.  The level set is interpolated with FE_Q(1) (the presets use FE_Q(p)),
-// which is the same function in 1D.
+// applications/wave/tests/{wave_0,heat_1,wave_1}.output.
 #include <gdm/system.h>
 #include <gdm/matrix_creator.h>
 #include <gdm/vector_tools.h>
@@ -46,6 +46,7 @@ struct Parameters // applications/wave/include/gdm/wave/parameters.h
   double       ghost_parameter_M = -1, ghost_parameter_A = -1, nitsche_parameter = -1;
   TimeFunction<dim> exact_solution, function_rhs;
   bool              has_rhs = false;
+  int               level_set_degree = 1;
   double            start_t = 0, end_t = 0, cfl = 0, cfl_pow = 1;
 };
 
@@ -59,12 +60,18 @@ void fill_parameters(Parameters<dim> &params, const std::string &simulation_name
       params.ghost_parameter_M = 0.25 * std::sqrt(3.0);
       params.ghost_parameter_A = 0.50 * std::sqrt(3.0);
       params.nitsche_parameter = 5.0 * params.fe_degree;
-      if (dim != 1)
-        throw ExcNotImplemented("wave preset: 2D needs a Bessel function and a level set of degree 3");
       params.exact_solution.fn = [pi](const double t, const Point<dim> &p) {
-        const double k = 1.5 * pi;
-        return std::cos(k * std::abs(p[0])) * std::cos(k * t);
+        double r2 = 0;
+        for (int d = 0; d < dim; ++d)
+          r2 += p[d] * p[d];
+        const double r = std::sqrt(r2);
+        if (dim == 1)
+          return std::cos(1.5 * pi * r) * std::cos(1.5 * pi * t);
+        return std::cyl_bessel_j(0.0, 3.0 * pi * r) * std::cos(3.0 * pi * t); // dim == 2 (wave-app.cc:256-261)
       };
+      if (dim > 2)
+        throw ExcNotImplemented("wave preset: dim 1 and 2");
+      params.level_set_degree = dim == 1 ? 1 : params.fe_degree; // wave-app.cc:277 (in 1D |x| - 1 is linear on the cut cells)
       params.end_t = 2.0;
       params.cfl   = 0.3;
     }
@@ -116,6 +123,7 @@ void run(Parameters<dim> &params)
   pa.nitsche_parameter = params.nitsche_parameter;
   pa.rhs_value = pa.boundary_value = 0.0;
   pa.outside_diagonal = 0.0;
+  pm.level_set_degree = pa.level_set_degree = params.level_set_degree;
   const SignedDistanceSphere<dim> level_set;
   GDM::CutCellSetup<dim> cut_m(p, n, params.geometry_left, params.geometry_right, level_set, pm);
   GDM::CutCellSetup<dim> cut_a(p, n, params.geometry_left, params.geometry_right, level_set, pa);
@@ -228,17 +236,27 @@ int main(int argc, char **argv)
   if (argc != 3)
     {
       std::cout << "Usage: ./wave_app dim simulation" << std::endl << std::endl;
-      std::cout << "dim         number of dimensions (1)" << std::endl;
+      std::cout << "dim         number of dimensions (1, 2)" << std::endl;
       std::cout << "simulation  name of simulation (wave, heat-rk)" << std::endl;
       return 1;
     }
   try
     {
-      if (std::atoi(argv[1]) != 1)
-        throw ExcNotImplemented("only dim = 1 presets are set up (the 2D presets use a level set of degree 3)");
-      Parameters<1> params;
-      fill_parameters(params, argv[2]);
-      run(params);
+      const int dim = std::atoi(argv[1]);
+      if (dim == 1)
+        {
+          Parameters<1> params;
+          fill_parameters(params, argv[2]);
+          run(params);
+        }
+      else if (dim == 2)
+        {
+          Parameters<2> params;
+          fill_parameters(params, argv[2]);
+          run(params);
+        }
+      else
+        throw ExcNotImplemented("dim must be 1 or 2");
     }
   catch (const std::exception &e)
     {

@@ -333,6 +333,9 @@ typedef struct gdm_cut_s *gdm_cut_t;
 /* level_set: nodal values of the Q1 level set at the grid nodes, DoF order (x fastest); negative = inside.  A level set
  * that vanishes exactly on a whole grid plane is degenerate (the cells on its positive side classify as intersected with
  * an empty inside part, as with deal.II's classifier, and the surface rule on that plane is empty): shift it. */
+/* where the level set is to be sampled for this description: points[n_points * dim] (x fastest; the grid nodes for a Q1
+ * level set, the support points of FE_Q(level_set_degree) of every cell otherwise).  points may be NULL (count only). */
+int gdm_cut_level_set_points(const gdm_cut_desc *desc, uint64_t *n_points, double *points);
 int gdm_cut_poisson_create(const gdm_cut_desc *desc, const double *level_set, gdm_cut_t *cut);
 int gdm_cut_destroy(gdm_cut_t cut);
 /* n_rows = rows to attach (band rows around the surface + identity rows of DoFs no active cell touches);

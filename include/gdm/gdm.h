@@ -912,6 +912,7 @@ namespace GDM
       bool   domain_boundary_terms = false; // Nitsche on the box boundary (function_domain_dbc, wave/stiffness.h:262-340)
       bool   negate_level_set      = false; // the domain is {level set > 0}: the outer field of the two-domain runs
       unsigned long long row_begin = 0, row_end = 0; // locally owned rows of this rank; 0, 0 = all
+      int    level_set_degree      = 1;     // > 1 (2D): FE_Q(q) level set as in the 2D presets of applications/wave
     };
     CutCellSetup(const unsigned int fe_degree, const unsigned int n_subdivisions, const double left, const double right,
                  const Function<dim> &level_set_function, const Parameters &prm = Parameters())
@@ -939,18 +940,17 @@ namespace GDM
       d.domain_boundary_terms = prm.domain_boundary_terms;
       d.row_begin             = prm.row_begin;
       d.row_end               = prm.row_end;
-      // VectorTools::interpolate of the level set into FE_Q(1): nodal values, x fastest
-      std::vector<double> level_set(n_nodes);
-      const double        h = (right - left) / n_subdivisions;
-      for (std::size_t i = 0; i < n_nodes; ++i)
+      d.level_set_degree      = prm.level_set_degree;
+      // VectorTools::interpolate of the level set into FE_Q(level_set_degree): values at its support points, x fastest
+      uint64_t n_points = 0;
+      dealii::internal::check(gdm_cut_level_set_points(&d, &n_points, nullptr));
+      std::vector<double> points(n_points * dim), level_set(n_points);
+      dealii::internal::check(gdm_cut_level_set_points(&d, &n_points, points.data()));
+      for (std::size_t i = 0; i < n_points; ++i)
         {
-          Point<dim>  x;
-          std::size_t r = i;
+          Point<dim> x;
           for (int e = 0; e < dim; ++e)
-            {
-              x[e] = left + (r % (n_subdivisions + 1)) * h;
-              r /= n_subdivisions + 1;
-            }
+            x[e] = points[i * dim + e];
           level_set[i] = (prm.negate_level_set ? -1.0 : 1.0) * level_set_function.value(x, 0);
         }
       n_dofs = n_nodes;

@@ -520,6 +520,17 @@ def test_product_degree_3_level_set_matches_oracle(lib):
     ref = cut.apply_load(n, volume, lambda p_: np.sin(p_.sum(axis=1))) + cut.apply_load(n, surface, lambda p_: np.cos(p_[:, 0]))
     got = c.load_vector(lambda pt, comp: np.sin(pt[0] + pt[1]), lambda pt, comp: np.cos(pt[0]))
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    # the sampling points a C / C++ caller gets from the library are the ones used above
+    import ctypes as C
+    d = g.capi.CutDesc()
+    d.dim, d.fe_degree, d.level_set_degree = 2, 3, 3
+    for e in range(2):
+        d.n_subdivisions[e], d.lo[e], d.hi[e] = 20, -1.21, 1.21
+    npts = C.c_uint64()
+    assert lib.gdm_cut_level_set_points(C.byref(d), C.byref(npts), None) == 0 and npts.value == 61 * 61
+    pts = np.zeros((npts.value, 2))
+    assert lib.gdm_cut_level_set_points(C.byref(d), C.byref(npts), pts.ctypes.data_as(C.c_void_p)) == 0
+    assert np.abs(pts - g.CutPoisson.level_set_points(*box, 3)).max() <= 1e-15
     with pytest.raises(g.GdmError):  # three dimensions: Q1 level sets only
         g.CutPoisson(3, 3, [8] * 3, [-1.21] * 3, [1.21] * 3, np.zeros(25 ** 3), level_set_degree=3)
 

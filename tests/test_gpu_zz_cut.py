@@ -186,22 +186,24 @@ def test_cut_poisson_01_gdm_cpp_driver(lib, golden_dir):
         assert abs(h - 0.0378) < 1e-4 and abs(e - ge) <= 1.5e-8, (out, gold)
 
 
-@pytest.mark.parametrize("simulation,golden", [("wave", "app_wave_wave_0.output"), ("heat-rk", "app_wave_heat_1.output")])
-def test_wave_app_cpp_driver(lib, golden_dir, simulation, golden):
+@pytest.mark.parametrize("dim,simulation,golden", [(1, "wave", "app_wave_wave_0.output"), (1, "heat-rk", "app_wave_heat_1.output"),
+                                                   (2, "wave", "app_wave_wave_1.output")])
+def test_wave_app_cpp_driver(lib, golden_dir, dim, simulation, golden):
     """examples/wave_app.cc (the explicit runs of applications/wave/wave-app.cc against include/gdm) on the GPU: every
-    printed step of applications/wave/tests/{wave_0,heat_1}.output, all three error columns; the ` [L] solved in k`
+    printed step of applications/wave/tests/{wave_0,heat_1,wave_1}.output (wave_1: 2D, level set of degree 3), all three
+    error columns; the ` [L] solved in k`
     lines carry this library's Jacobi-CG counts instead of the reference's AMG / ILU counts and are not compared."""
     from test_gpu_examples import _run
     from test_cut_cell import _app_golden
-    out = _run("wave_app", 1, simulation)
+    out = _run("wave_app", dim, simulation)
     rows = [l.split() for l in out.splitlines() if l.strip() and not l.startswith(" [L]")]
     gold = _app_golden(golden_dir, golden)
     assert len(rows) == len(gold), out[-2000:]
     assert out.count(" [L] solved in") == 4 * (len(gold) - 1)
     for r, g_ in zip(rows, gold):
         assert int(r[0]) == g_[0] and abs(float(r[1]) - g_[1]) <= 5.1e-6
-        for i in (2, 3, 4):
-            assert abs(float(r[i]) - g_[i]) <= 2e-8 * g_[i], (r, g_)
+        for i in (2, 3, 4):  # 2D: the Linf column depends on the height direction taken in the four diagonal cut cells
+            assert abs(float(r[i]) - g_[i]) <= (2e-8 if dim == 1 or i < 4 else 1e-7) * g_[i], (r, g_)
 
 
 def test_wave_app_wave_composite_0(lib, golden_dir):
