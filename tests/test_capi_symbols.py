@@ -74,3 +74,41 @@ def test_cpp_drivers_compile_against_include_gdm(lib, tmp_path):
                   'template class GDM::CutCellSetup<3>;\nint main() { return 0; }\n')
     subprocess.check_call(["g++", "-O0", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
                            "-o", str(tmp_path / "instantiate"), str(tu), "-L" + pkg, "-lgdm_b200", "-Wl,-rpath," + pkg])
+
+
+def test_cpp_cut_setup_mirror_on_the_host(lib, tmp_path, golden_dir):
+    """GDM::CutCellSetup is host-only: the first line of applications/wave/tests/wave_1.output (interpolation error of
+    J0(3 pi r) over the inside part, 2D, level set of degree 3) from a C++ program over include/gdm, no GPU involved."""
+    pkg = os.path.join(ROOT, "dealii-galerkin-difference-methods_b200")
+    tu = tmp_path / "cut_host.cc"
+    tu.write_text(r"""
+#include <gdm/system.h>
+#include <gdm/matrix_creator.h>
+#include <gdm/vector_tools.h>
+#include <cmath>
+#include <cstdio>
+using namespace dealii;
+struct Sphere : Function<2> { double value(const Point<2> &p, const unsigned int = 0) const override { return std::sqrt(p[0] * p[0] + p[1] * p[1]) - 1.0; } };
+struct Exact : Function<2> { double value(const Point<2> &p, const unsigned int = 0) const override { return std::cyl_bessel_j(0.0, 3.0 * M_PI * std::sqrt(p[0] * p[0] + p[1] * p[1])); } };
+int main()
+{
+  GDM::CutCellSetup<2>::Parameters prm;
+  prm.kind_mass = true; prm.gp_h_power = 3; prm.ghost_parameter = 0.25 * std::sqrt(3.0); prm.rhs_value = 0.0; prm.level_set_degree = 3;
+  GDM::CutCellSetup<2> cut(3, 40, -1.21, 1.21, Sphere(), prm);
+  std::vector<double> u(41 * 41);
+  Exact exact;
+  for (int j = 0; j < 41; ++j)
+    for (int i = 0; i < 41; ++i)
+      { Point<2> x; x[0] = -1.21 + i * (2.42 / 40); x[1] = -1.21 + j * (2.42 / 40); u[i + 41 * j] = exact.value(x); }
+  const auto e = cut.error_norms_inside(u, exact);
+  printf("%5d %8.5f %14.8e %14.8e %14.8e\n", 0, 0.0, e[0], e[1], e[2]);
+}
+""")
+    exe = str(tmp_path / "cut_host")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", exe, str(tu),
+                           "-L" + pkg, "-lgdm_b200", "-Wl,-rpath," + pkg])
+    out = subprocess.check_output([exe], text=True).split()
+    gold = open(os.path.join(golden_dir, "app_wave_wave_1.output")).readline().split()
+    assert out[:2] == gold[:2]
+    for a, b in zip(out[2:], gold[2:]):
+        assert abs(float(a) - float(b)) <= 6e-9 * float(b), (out, gold)
