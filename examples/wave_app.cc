@@ -2,6 +2,7 @@
 //   ./wave_app 1 wave      (wave-app.cc:222-284, wave/problem.h:280-345: RK4 on [u; v], cut mass solves)
 //   ./wave_app 1 heat-rk   (wave-app.cc:62-150,  wave/problem.h:72-127)
 //   ./wave_app 2 wave      (the 2D preset: Bessel solution, level set interpolated with FE_Q(3))
+//   ./wave_app 2 step85    (wave-app.cc:13-61, wave/problem.h:46-70: Poisson with the assembled cut matrix)
 // Cut-cell set-up on the host (GDM::CutCellSetup), mass / stiffness operators with the cut rows attached, Jacobi-CG
 // mass solves and the Runge-Kutta stages on the GPU.  stdout has the reference's format (wave/problem.h:609-615 and
 // the " [L] solved in k" lines of :498); tests/test_gpu_zz_cut.py diffs the error columns against
@@ -40,6 +41,7 @@ struct SignedDistanceSphere : public Function<dim>
 template <int dim>
 struct Parameters // applications/wave/include/gdm/wave/parameters.h
 {
+  bool         poisson = false;      // "poisson": one solve with the assembled matrix (wave/problem.h:46-70)
   bool         second_order = false; // "wave-rk" ([u; v]) or "heat-rk"
   unsigned int fe_degree = 3, n_subdivisions_1D = 40;
   double       geometry_left = -1.21, geometry_right = 1.21;
@@ -74,6 +76,22 @@ void fill_parameters(Parameters<dim> &params, const std::string &simulation_name
       params.level_set_degree = dim == 1 ? 1 : params.fe_degree; // wave-app.cc:277 (in 1D |x| - 1 is linear on the cut cells)
       params.end_t = 2.0;
       params.cfl   = 0.3;
+    }
+  else if (simulation_name == "step85")
+    {
+      // wave-app.cc:13-61: Poisson, f = 4, g = 1 on the unit circle / sphere, exact solution 1 - 2/dim (|x|^2 - 1)
+      params.poisson           = true;
+      params.ghost_parameter_A = 0.5;
+      params.nitsche_parameter = 5.0 * params.fe_degree;
+      params.exact_solution.fn = [](const double, const Point<dim> &p) {
+        double r2 = 0;
+        for (int d = 0; d < dim; ++d)
+          r2 += p[d] * p[d];
+        return 1. - 2. / dim * (r2 - 1.);
+      };
+      if (dim != 2)
+        throw ExcNotImplemented("step85 preset: dim 2");
+      params.level_set_degree = params.fe_degree;
     }
   else if (simulation_name == "heat-rk")
     {
@@ -111,6 +129,35 @@ void run(Parameters<dim> &params)
   AffineConstraints<double> constraints;
   constraints.close();
   system.categorize();
+
+  if (params.poisson)
+    {
+      // assembled stiffness matrix (wave/stiffness.h:589-799: ghost penalty with h^3, zero diagonal -> 1) and the right-hand
+      // side compute_rhs(., 0, false, 0) = (v, 4) + <gamma_D / h v - dv/dn, 1>
+      typename GDM::CutCellSetup<dim>::Parameters ps;
+      ps.ghost_parameter   = params.ghost_parameter_A;
+      ps.gp_h_power        = 3;
+      ps.nitsche_parameter = params.nitsche_parameter;
+      ps.rhs_value         = 4.0;
+      ps.boundary_value    = 1.0;
+      ps.level_set_degree  = params.level_set_degree;
+      GDM::CutCellSetup<dim> cut_s(p, n, params.geometry_left, params.geometry_right, SignedDistanceSphere<dim>(), ps);
+      SparseMatrix<double> matrix;
+      GDM::MatrixCreator::create_laplace_matrix(mapping, system, quadrature, matrix, constraints);
+      cut_s.attach_to(matrix);
+      VectorType solution(system), rhs(system);
+      rhs.from_host(cut_s.rhs());
+      solution = 0.0;
+      PreconditionJacobi<SparseMatrix<double>> preconditioner;
+      preconditioner.initialize(matrix);
+      ReductionControl     solver_control(1000, 1.e-20, 1.e-14);
+      SolverCG<VectorType> solver(solver_control);
+      solver.solve(matrix, solution, rhs, preconditioner);
+      printf(" [L] solved in %u\n", solver_control.last_step());
+      const auto e = cut_s.error_norms_inside(solution.to_host(), params.exact_solution);
+      printf("%5d %8.5f %14.8e %14.8e %14.8e\n", 0, 0.0, e[0], e[1], e[2]);
+      return;
+    }
 
   // cut mass matrix (wave/mass.h:47-249) and the linear part of the residual (wave/stiffness.h:42-407)
   typename GDM::CutCellSetup<dim>::Parameters pm, pa;
@@ -237,7 +284,7 @@ int main(int argc, char **argv)
     {
       std::cout << "Usage: ./wave_app dim simulation" << std::endl << std::endl;
       std::cout << "dim         number of dimensions (1, 2)" << std::endl;
-      std::cout << "simulation  name of simulation (wave, heat-rk)" << std::endl;
+      std::cout << "simulation  name of simulation (wave, heat-rk, step85)" << std::endl;
       return 1;
     }
   try

@@ -271,3 +271,18 @@ def test_wave_app_wave_composite_0(lib, golden_dir):
             for i in range(3):
                 assert abs(e[i] - gold[2 * step + kk][2 + i]) <= 2e-8 * gold[2 * step + kk][2 + i], (step, kk, e, gold[2 * step + kk])
         t = rk.evolve_one_time_step(f, t, dt, y)
+
+
+def test_wave_app_cpp_driver_step85(lib, golden_dir):
+    """`wave_app 2 step85` (wave-app.cc:13-61): 2D Poisson through the application with the assembled cut matrix (ghost
+    penalty with h^3) and a level set of degree 3; the three errors of applications/wave/tests/step85_0.output are pure
+    cut-cell quadrature error (the exact solution lies in the discrete space) and are reproduced to 5e-5 (host check with
+    the oracle's CG: 2e-8, 3e-5, 1e-9)."""
+    from test_gpu_examples import _run
+    from test_cut_cell import _app_golden
+    out = _run("wave_app", 2, "step85")
+    rows = [l.split() for l in out.splitlines() if l.strip() and not l.startswith(" [L]")]
+    g_ = _app_golden(golden_dir, "app_wave_step85_0.output")[0]
+    assert len(rows) == 1 and out.count(" [L] solved in") == 1, out
+    for i in (2, 3, 4):
+        assert abs(float(rows[0][i]) - g_[i]) <= 5e-5 * g_[i], (rows, g_)
